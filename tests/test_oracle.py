@@ -1,0 +1,97 @@
+"""The oracle against the reference-generated golden vectors, and the sparse oracle
+against the dense one (CPU only)."""
+import numpy as np
+import pytest
+
+from conftest import rel_inf, load_golden
+from oracle import flock_env, learner, sparse
+
+TOL_ACTION = 1e-5      # north_star: actions within 1e-5 relative fp32
+
+
+def replay(g):
+    """Teacher-forced replay of a golden trajectory through the numpy oracle."""
+    layers = learner.weights_from_state_dict(g["state_dict"])
+    R2 = g["comm_radius"] ** 2
+    state = None
+    for t in range(g["steps"]):
+        sv, sn, adj, deg = flock_env.compute_helpers(g["x"][t], R2)
+        state = learner.DelayState((sv, sn), prev_state=state, k=g["k"])
+        yield t, sv, deg, state, layers
+
+
+def test_env_restatement_matches_recorded_trajectory(golden):
+    g = golden
+    for t, sv, deg, state, layers in replay(g):
+        assert np.array_equal(deg, g["deg"][t])
+        np.testing.assert_array_equal(sv, g["values"][t])
+        if t + 1 < g["steps"]:
+            xn = flock_env.integrate(g["x"][t], g["action"][t], g["dt"])
+            np.testing.assert_array_equal(xn, g["x"][t + 1])
+            assert flock_env.instant_cost(xn) == pytest.approx(float(g["reward"][t]), rel=1e-12)
+
+
+def test_learner_restatement_matches_reference(golden):
+    g = golden
+    for t, sv, deg, state, layers in replay(g):
+        z = learner.aggregate(state.delay_state, state.delay_gso)[0]
+        assert rel_inf(z, g["z"][t]) <= 2e-6
+        a = learner.select_action(layers, state)
+        assert rel_inf(a, g["action"][t]) <= TOL_ACTION
+
+
+def test_delay_state_structure():
+    g = load_golden("ckpt_n100_k3")
+    states = [s for _, _, _, s, _ in replay(g)]
+    s0, s1, s2 = states[0], states[1], states[2]
+    n = g["n_agents"]
+    assert np.array_equal(s0.delay_gso[0, 0], np.eye(n, dtype=np.float32))
+    assert not s0.delay_gso[0, 1:].any() and not s0.delay_state[0, 1:].any()
+    assert np.array_equal(s1.delay_gso[0, 1], s1.network[0, 0])
+    assert not s1.delay_gso[0, 2].any()
+    np.testing.assert_allclose(s2.delay_gso[0, 2], s2.network[0, 0] @ s1.network[0, 0], rtol=1e-6, atol=1e-8)
+    assert np.array_equal(s2.delay_state[0, 2], s0.delay_state[0, 0])
+
+
+@pytest.mark.parametrize("n,R", [(150, 1.0), (400, 1.5), (64, 0.8)])
+def test_sparse_oracle_equals_dense(n, R):
+    x = flock_env.synthetic_state(n, seed=n, density=1.6)
+    sv, sn, adj, deg = flock_env.compute_helpers(x, R * R)
+    sv_s, deg_s, i, j = sparse.compute_helpers_sparse(x, R)
+    assert np.array_equal(deg, deg_s)
+    ii, jj = np.nonzero(adj)
+    assert np.array_equal(ii, i) and np.array_equal(jj, j)
+    np.testing.assert_allclose(sv_s, sv, rtol=1e-12, atol=1e-9)
+    a = sparse.network_csr(n, deg_s, i, j).toarray()
+    np.testing.assert_array_equal(a, sn.astype(np.float32))
+
+
+def test_sparse_delay_state_equals_dense_path():
+    g = load_golden("rand_n100_k4_h64_l2")
+    layers = learner.weights_from_state_dict(g["state_dict"])
+    R = g["comm_radius"]
+    sstate = None
+    for t in range(g["steps"]):
+        sv, deg, i, j = sparse.compute_helpers_sparse(g["x"][t], R)
+        a = sparse.network_csr(g["n_agents"], deg, i, j)
+        sstate = sparse.SparseDelayState(sv, a, prev_state=sstate, k=g["k"])
+        z = sstate.aggregate()                       # (K,N,F)
+        assert rel_inf(z.transpose(0, 2, 1), g["z"][t]) <= 2e-6
+        act = sparse.readout(layers, z)
+        assert rel_inf(act, g["action"][t]) <= TOL_ACTION
+
+
+def test_integrator_and_cost_small_case():
+    x = np.array([[0.0, 0.0, 1.0, 0.0], [1.0, 2.0, 0.0, -1.0]])
+    u = np.array([[0.1, 0.0], [0.0, -0.2]])
+    xn = flock_env.integrate(x, u, 0.5, action_scalar=10.0)
+    np.testing.assert_allclose(xn, [[0.5 + 0.125, 0.0, 1.5, 0.0], [1.0, 2.0 - 0.5 - 0.25, 0.0, -2.0]])
+    assert flock_env.instant_cost(xn) == pytest.approx(-(np.var([1.5, 0.0]) + np.var([0.0, -2.0])))
+
+
+def test_controller_shapes_and_clip():
+    env = flock_env.FlockingRelativeOracle(n_agents=30, rng=np.random.RandomState(0))
+    env.reset()
+    for c in (True, False, None):
+        u = env.controller(c)
+        assert u.shape == (30, 2) and np.all(np.abs(u) <= 1.0 + 1e-12)
