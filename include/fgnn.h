@@ -1,0 +1,129 @@
+/*
+ * fgnn.h -- C ABI of the B200-native flocking-GNN rollout engine (libfgnn.so).
+ *
+ * The reference (katetolstaya/multiagent_gnn_policies) has no FFI: its boundary for the
+ * hot path is a Python call surface.  Each entry point below names the reference
+ * interface it replaces (paths relative to the reference tree).  A Python host binds these
+ * with ctypes (multiagent_gnn_policies_b200/engine.py); INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; fgnn_last_error() gives text.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - data pointers marked [h/d] may be HOST or DEVICE pointers (UVA, cudaMemcpyDefault);
+ *     copies are stream-ordered (truly asynchronous only for pinned host memory).
+ *   - agents are indexed a = episode * n_agents + i, in the caller's order, everywhere.
+ *   - a handle is not re-entrant; distinct handles are independent.  No host threads.
+ */
+#ifndef FGNN_H
+#define FGNN_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fgnn_handle fgnn_handle;
+
+typedef struct fgnn_config {
+    int32_t n_agents;        /* N, agents per episode            (cfg key n_agents)           */
+    int32_t n_episodes;      /* B, independent episodes (block-diagonal graph), >= 1          */
+    int32_t k;               /* filter taps K, 1..4              (cfg key k)                  */
+    int32_t n_states;        /* F, must be 6                     (cfg key n_states)           */
+    int32_t n_actions;       /* A, must be 2                     (cfg key n_actions)          */
+    int32_t hidden;          /* H, 1..128                        (cfg key hidden_size)        */
+    int32_t n_layers;        /* hidden layers L, 1..4            (cfg key n_layers, default 2)*/
+    int32_t mean_pooling;    /* 1: state_network = adj / max(deg,1)  (gym_flock default)      */
+    int32_t half_accel_term; /* 1: p += v dt + a dt^2/2 ; 0: p += v dt                        */
+    int32_t device;          /* CUDA device ordinal                                           */
+    int32_t grid_dim;        /* cells per side of the wrapped cell grid, 0 = auto             */
+    int32_t edge_capacity;   /* directed-edge capacity per agent (mean), 0 = auto (48)        */
+    int32_t readout_mode;    /* 0 = auto, 1 = FFMA (CUDA cores), 2 = tensor cores (3xTF32)    */
+    int32_t reserved0;
+    double  comm_radius;     /* R                                (cfg key comm_radius)        */
+    double  dt;              /*                                  (cfg key dt)                 */
+    double  action_scalar;   /* gym_flock gain, 10.0                                          */
+} fgnn_config;
+
+typedef struct fgnn_stats {
+    int64_t step;            /* index t of the current graph (0 right after reset)            */
+    int64_t n_edges;         /* directed edges of the current graph                           */
+    int32_t overflow;        /* 1 if the edge capacity was exceeded at any time (results void) */
+    int32_t grid_dim;
+    int64_t n_cells;
+    int64_t edge_capacity;   /* total directed-edge capacity                                   */
+} fgnn_stats;
+
+const char* fgnn_last_error(void);
+int fgnn_version(void);
+
+/* Lifetime.  Replaces: gym.make + env.env.params_from_cfg (train.py:17-21) and
+ * DAGGER.__init__/Actor.__init__ (learner/gnn_dagger.py:20-53, learner/actor.py:9-42). */
+int fgnn_create(const fgnn_config* cfg, fgnn_handle** out);
+int fgnn_destroy(fgnn_handle* h);
+
+/* Actor weights, conv layout of the reference checkpoint (learner/actor.py:30-40):
+ * layer 0: W (H, F, K) [= conv weight (out,in,step,1)], layers 1..L-1: W (H, H), layer L: W (A, H);
+ * b (out,).  fp32, [h/d].  Replaces Actor.load_state_dict (learner/gnn_dagger.py:114-123). */
+int fgnn_set_weights(fgnn_handle* h, int32_t layer, const float* W, const float* b, void* stream);
+
+/* env.reset() (learner/gnn_dagger.py:150): install x (B*N,4) f64 [px,py,vx,vy] [h/d], clear the
+ * K-deep history, t = 0, build graph + features of step 0. */
+int fgnn_reset(fgnn_handle* h, const double* x_bn4, void* stream);
+
+/* Teacher forcing for parity tests: overwrite the 4-d state, keep history, do not rebuild. */
+int fgnn_set_state(fgnn_handle* h, const double* x_bn4, void* stream);
+
+/* gym_flock compute_helpers (called by env.step/reset): radius adjacency (CSR), degrees,
+ * 6-d relative features of the CURRENT state into history slot t.  advance != 0 first moves
+ * t -> t+1 (what env.step does after integrating). */
+int fgnn_build_graph(fgnn_handle* h, int32_t advance, void* stream);
+
+/* First half of env.step(u) (learner/gnn_dagger.py:163): double-integrator update from
+ * u (B*N,2) fp32 [h/d]; reward_b (B,) f64 [h/d] or NULL receives instant_cost per episode. */
+int fgnn_integrate(fgnn_handle* h, const float* u_bn2, double* reward_b, void* stream);
+
+/* env.step(u) = fgnn_integrate + fgnn_build_graph(advance=1). */
+int fgnn_env_step(fgnn_handle* h, const float* u_bn2, double* reward_b, void* stream);
+
+/* DAGGER.select_action(state) (learner/gnn_dagger.py:55-72) = MultiAgentStateWithDelay history
+ * (learner/state_with_delay.py:44-53) + Actor.forward (learner/actor.py:45-86) on the sparse
+ * history the engine keeps: K-hop aggregation + readout.  action_bn2 (B*N,2) fp32 [h/d]. */
+int fgnn_policy(fgnn_handle* h, float* action_bn2, void* stream);
+
+/* One closed-loop rollout step (learner/gnn_dagger.py:196-201, test_model.py:38-45):
+ * select_action -> env.step(action).  action_bn2 / reward_b may be NULL. */
+int fgnn_step(fgnn_handle* h, float* action_bn2, double* reward_b, void* stream);
+
+/* T closed-loop steps, CUDA-graph replayed; reward_bt (T,B) f64 [h/d] or NULL. */
+int fgnn_rollout(fgnn_handle* h, int32_t T, double* reward_bt, void* stream);
+
+/* Actor.forward(delay_state, delay_gso) on dense tensors (learner/actor.py:45-86):
+ * delay_state (B2,K,F,N2), delay_gso (B2,K,N2,N2), out (B2,1,A,N2); fp32 DEVICE pointers. */
+int fgnn_actor_forward_dense(fgnn_handle* h, int32_t batch, int32_t n_agents, const float* delay_state,
+                             const float* delay_gso, float* out, void* stream);
+
+/* Read-back (tests, small-N compatibility with the dense reference API). */
+int fgnn_get_state(fgnn_handle* h, double* x_bn4, void* stream);
+int fgnn_get_features(fgnn_handle* h, int32_t age, float* values_bn6, void* stream);       /* x_{t-age} */
+int fgnn_get_degrees(fgnn_handle* h, int32_t age, int32_t* deg_bn, void* stream);
+int fgnn_get_aggregated(fgnn_handle* h, float* z_k_bn_6, void* stream);   /* (K, B*N, 6) of the last policy call */
+int fgnn_get_action(fgnn_handle* h, float* action_bn2, void* stream);
+/* Row-normalised state_network of graph t-age as dense (B, N, N) fp32 (state_with_delay.py:35). */
+int fgnn_export_network_dense(fgnn_handle* h, int32_t age, float* network_bnn, void* stream);
+/* CSR of graph t-age: device pointers valid until the next build; rows are (row_start[a], deg[a]). */
+int fgnn_get_csr(fgnn_handle* h, int32_t age, const uint32_t** row_start, const int32_t** deg,
+                 const int32_t** cols, const float** src_scale);
+int fgnn_get_stats(fgnn_handle* h, fgnn_stats* out, void* stream);   /* synchronises the stream */
+
+/* Stream-ordered copy between any two host/device buffers (cudaMemcpyDefault) + stream sync; lets a
+ * ctypes host read the device arrays fgnn_get_csr points at without binding the CUDA runtime. */
+int fgnn_memcpy_sync(void* dst, const void* src, uint64_t bytes, void* stream);
+
+/* Number of kernel launches issued by this handle so far (bench `gpu_launches`). */
+int64_t fgnn_launch_count(fgnn_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FGNN_H */

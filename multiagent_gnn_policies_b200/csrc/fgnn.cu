@@ -1,0 +1,572 @@
+// fgnn.cu -- host side of libfgnn.so: handle, memory, launches, CUDA-graph rollout, C ABI (include/fgnn.h).
+#define FGNN_MAIN_TU 1
+#include "fgnn_kernels.cuh"
+#include "../../include/fgnn.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace fgnn;
+
+static thread_local std::string g_err;
+static int fail(const std::string& msg) { g_err = msg; return 1; }
+
+#define CK(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e__ = (call);                                                                    \
+        if (e__ != cudaSuccess) {                                                                    \
+            char buf__[512];                                                                         \
+            snprintf(buf__, sizeof buf__, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return fail(buf__);                                                                      \
+        }                                                                                            \
+    } while (0)
+
+struct fgnn_handle {
+    fgnn_config cfg;
+    Params p;
+    int HP = 0;
+    int sm_count = 148;
+    size_t weights_floats = 0;
+    std::vector<float> w_host;       // packed weights, host mirror
+    float* d_weights = nullptr;
+    float* d_u_in = nullptr;         // [M][2] staged external action
+    float* d_staging = nullptr;      // read-back staging (K*M*6 floats)
+    double* d_reward_log = nullptr;
+    int reward_log_cap = 0;          // in steps
+    bool binned = false;             // cell_of/cell_count describe the current positions
+    bool weights_dirty = true;
+    int64_t launches = 0;
+    int64_t t_host = -1;
+    std::vector<void*> allocs;
+    // graph of one closed-loop step
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+    int graph_kernels = 0;
+    int final_grid_closed = 0, final_grid_open = 0;
+    size_t final_smem = 0;
+};
+
+template <typename T>
+static int dalloc(fgnn_handle* h, T** ptr, size_t count, bool zero = true) {
+    void* q = nullptr;
+    size_t bytes = count * sizeof(T);
+    if (bytes == 0) bytes = sizeof(T);
+    CK(cudaMalloc(&q, bytes));
+    if (zero) CK(cudaMemset(q, 0, bytes));
+    h->allocs.push_back(q);
+    *ptr = reinterpret_cast<T*>(q);
+    return 0;
+}
+
+static int pad_hidden(int H) { return H <= 16 ? 16 : H <= 32 ? 32 : H <= 64 ? 64 : 128; }
+
+// ---- kernel dispatch ------------------------------------------------------------------------
+typedef void (*final_kernel_t)(Params);
+typedef void (*dense_kernel_t)(const float*, const float*, float*, const float*, int, int);
+
+namespace fgnn {
+#define FGNN_DECL(K, HP) final_kernel_t get_final_k##K##_hp##HP(bool closed); dense_kernel_t get_dense_k##K##_hp##HP();
+#define FGNN_DECL_K(K) FGNN_DECL(K, 16) FGNN_DECL(K, 32) FGNN_DECL(K, 64) FGNN_DECL(K, 128)
+FGNN_DECL_K(1) FGNN_DECL_K(2) FGNN_DECL_K(3) FGNN_DECL_K(4)
+}
+
+#define FGNN_CASE_HP(K, HP) case HP: return closed_or_dense == 2 ? (void*)get_dense_k##K##_hp##HP() : (void*)get_final_k##K##_hp##HP(closed_or_dense == 1);
+#define FGNN_CASE_K(K) case K: switch (HP) { FGNN_CASE_HP(K, 16) FGNN_CASE_HP(K, 32) FGNN_CASE_HP(K, 64) default: FGNN_CASE_HP(K, 128) } break;
+static void* kernel_lookup(int K, int HP, int closed_or_dense) {
+    switch (K) { FGNN_CASE_K(1) FGNN_CASE_K(2) FGNN_CASE_K(3) default: FGNN_CASE_K(4) }
+    return nullptr;
+}
+static final_kernel_t final_kernel(int K, int HP, bool closed) { return (final_kernel_t)kernel_lookup(K, HP, closed ? 1 : 0); }
+static dense_kernel_t dense_kernel(int K, int HP) { return (dense_kernel_t)kernel_lookup(K, HP, 2); }
+
+static size_t final_smem_bytes(const fgnn_handle* h) {
+    WeightLayout wl{F * h->cfg.k, h->HP, h->cfg.n_layers};
+    if (h->HP > 64) return (size_t)2 * h->HP * FINAL_THREADS * sizeof(float);
+    return (size_t)wl.total() * sizeof(float);
+}
+
+static inline int blocks_for(int n, int threads) { return (n + threads - 1) / threads; }
+
+// ---- ABI --------------------------------------------------------------------------------------
+extern "C" const char* fgnn_last_error(void) { return g_err.c_str(); }
+extern "C" int fgnn_version(void) { return 100; }
+
+extern "C" int fgnn_create(const fgnn_config* cfg, fgnn_handle** out) {
+    if (!cfg || !out) return fail("fgnn_create: null argument");
+    if (cfg->n_agents < 1 || cfg->n_episodes < 1) return fail("fgnn_create: n_agents and n_episodes must be >= 1");
+    if (cfg->k < 1 || cfg->k > KMAX) return fail("fgnn_create: k must be in 1..4");
+    if (cfg->n_states != F) return fail("fgnn_create: n_states must be 6 (FlockingRelative features)");
+    if (cfg->n_actions != 2) return fail("fgnn_create: n_actions must be 2");
+    if (cfg->hidden < 1 || cfg->hidden > 128) return fail("fgnn_create: hidden must be in 1..128");
+    if (cfg->n_layers < 1 || cfg->n_layers > LMAX) return fail("fgnn_create: n_layers must be in 1..4");
+    if (!(cfg->comm_radius > 0.0) || !(cfg->dt > 0.0)) return fail("fgnn_create: comm_radius and dt must be > 0");
+    const long long M64 = (long long)cfg->n_agents * cfg->n_episodes;
+    if (M64 > (1ll << 30) - 1) return fail("fgnn_create: more than 2^30-1 agents on one device");
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail("fgnn_create: no such CUDA device");
+    CK(cudaSetDevice(cfg->device));
+
+    fgnn_handle* h = new fgnn_handle();
+    h->cfg = *cfg;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, cfg->device));
+    h->sm_count = prop.multiProcessorCount;
+    h->HP = pad_hidden(cfg->hidden);
+    Params& p = h->p;
+    memset(&p, 0, sizeof p);
+    p.M = (int)M64; p.N = cfg->n_agents; p.B = cfg->n_episodes; p.K = cfg->k; p.L = cfg->n_layers;
+    int G = cfg->grid_dim > 0 ? cfg->grid_dim : (int)std::ceil(std::sqrt((double)cfg->n_agents));
+    if (G < 3) G = 3;
+    if ((long long)G * G * cfg->n_episodes > (1ll << 30)) return fail("fgnn_create: cell grid too large");
+    p.G = G; p.C = G * G * cfg->n_episodes;
+    p.mean_pooling = cfg->mean_pooling; p.half_accel = cfg->half_accel_term;
+    const long long cap_per = cfg->edge_capacity > 0 ? cfg->edge_capacity : 48;
+    long long cap = cap_per * M64;
+    if (cap > 0xfffffff0ll) cap = 0xfffffff0ll;
+    if (cap < 1024) cap = 1024;
+    p.nnz_cap = (unsigned)cap;
+    p.inv_cell = 1.0 / (cfg->comm_radius * (1.0 + 1.0 / 1048576.0));
+    p.R2 = cfg->comm_radius * cfg->comm_radius;
+    p.dt = cfg->dt;
+    p.gain = cfg->action_scalar;
+    p.n_tiles = blocks_for(p.C + 1, SCAN_TILE);
+
+    const size_t M = p.M, K = p.K;
+    int rc = 0;
+    rc |= dalloc(h, &p.t, 1);
+    rc |= dalloc(h, &p.state, M);
+    rc |= dalloc(h, &p.cell_of, M);
+    rc |= dalloc(h, &p.cell_count, (size_t)p.C + 1);
+    rc |= dalloc(h, &p.cell_start, (size_t)p.C + 1);
+    rc |= dalloc(h, &p.tmp_id, M);
+    rc |= dalloc(h, &p.sorted_id, M);
+    rc |= dalloc(h, &p.sorted_state, M);
+    rc |= dalloc(h, &p.tile_status, (size_t)p.n_tiles);
+    rc |= dalloc(h, &p.tile_counter, 1);
+    rc |= dalloc(h, &p.xhist, K * M * ROW);
+    rc |= dalloc(h, &p.sinv, K * M);
+    rc |= dalloc(h, &p.row_start, K * M);
+    rc |= dalloc(h, &p.deg, K * M);
+    rc |= dalloc(h, &p.cols, K * (size_t)p.nnz_cap, false);
+    rc |= dalloc(h, &p.nnz_cursor, K);
+    rc |= dalloc(h, &p.overflow, 1);
+    rc |= dalloc(h, &p.zbuf, K * M * ROW);
+    rc |= dalloc(h, &p.ybuf, 2 * K * M * ROW);
+    rc |= dalloc(h, &p.action, M * 2);
+    rc |= dalloc(h, &p.racc, (size_t)p.B * 4);
+    rc |= dalloc(h, &p.reward, (size_t)p.B);
+    rc |= dalloc(h, &p.reward_pending, 1);
+    rc |= dalloc(h, &p.log_index, 1);
+    rc |= dalloc(h, &h->d_u_in, M * 2);
+    rc |= dalloc(h, &h->d_staging, K * M * F > (size_t)M * 4 * 2 ? K * M * F : (size_t)M * 4 * 2);
+    WeightLayout wl{F * p.K, h->HP, p.L};
+    h->weights_floats = wl.total();
+    h->w_host.assign(h->weights_floats, 0.f);
+    rc |= dalloc(h, &h->d_weights, h->weights_floats);
+    if (rc) { fgnn_destroy(h); return 1; }
+    p.weights = h->d_weights;
+    p.reward_log = nullptr;
+
+    // launch geometry of the fused final kernel: persistent grid sized to the SM count x occupancy
+    h->final_smem = final_smem_bytes(h);
+    for (int closed = 0; closed < 2; ++closed) {
+        final_kernel_t fk = final_kernel(p.K, h->HP, closed != 0);
+        CK(cudaFuncSetAttribute((const void*)fk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->final_smem));
+        int occ = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)fk, FINAL_THREADS, h->final_smem));
+        if (occ < 1) occ = 1;
+        int grid = h->sm_count * occ;
+        int tiles = blocks_for(p.M, FINAL_THREADS);
+        if (grid > tiles) grid = tiles;
+        (closed ? h->final_grid_closed : h->final_grid_open) = grid;
+    }
+    *out = h;
+    return 0;
+}
+
+extern "C" int fgnn_destroy(fgnn_handle* h) {
+    if (!h) return 0;
+    cudaSetDevice(h->cfg.device);
+    if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+    if (h->graph) cudaGraphDestroy(h->graph);
+    for (void* q : h->allocs) cudaFree(q);
+    if (h->d_reward_log) cudaFree(h->d_reward_log);
+    delete h;
+    return 0;
+}
+
+extern "C" int fgnn_set_weights(fgnn_handle* h, int32_t layer, const float* W, const float* b, void* stream) {
+    if (!h || !W || !b) return fail("fgnn_set_weights: null argument");
+    const int K = h->cfg.k, H = h->cfg.hidden, L = h->cfg.n_layers, HP = h->HP;
+    if (layer < 0 || layer > L) return fail("fgnn_set_weights: layer out of range");
+    cudaStream_t st = (cudaStream_t)stream;
+    WeightLayout wl{F * K, HP, L};
+    const int out_dim = layer == L ? 2 : H;
+    const int in_dim = layer == 0 ? F * K : H;
+    std::vector<float> w((size_t)out_dim * in_dim), bb(out_dim);
+    CK(cudaMemcpyAsync(w.data(), W, w.size() * sizeof(float), cudaMemcpyDefault, st));
+    CK(cudaMemcpyAsync(bb.data(), b, bb.size() * sizeof(float), cudaMemcpyDefault, st));
+    CK(cudaStreamSynchronize(st));
+    float* dst = h->w_host.data();
+    if (layer == 0 && L >= 1) {
+        // W (H, F, K) -> w0[(k*F + f)][g]
+        for (int i = 0; i < F * K * HP; ++i) dst[wl.off_w0() + i] = 0.f;
+        for (int g = 0; g < HP; ++g) dst[wl.off_b0() + g] = 0.f;
+        for (int g = 0; g < H; ++g) {
+            for (int f = 0; f < F; ++f)
+                for (int k = 0; k < K; ++k) dst[wl.off_w0() + (k * F + f) * HP + g] = w[((size_t)g * F + f) * K + k];
+            dst[wl.off_b0() + g] = bb[g];
+        }
+    } else if (layer < L) {
+        for (int i = 0; i < HP * HP; ++i) dst[wl.off_wh(layer) + i] = 0.f;
+        for (int g = 0; g < HP; ++g) dst[wl.off_bh(layer) + g] = 0.f;
+        for (int g = 0; g < H; ++g) {
+            for (int i = 0; i < H; ++i) dst[wl.off_wh(layer) + i * HP + g] = w[(size_t)g * H + i];
+            dst[wl.off_bh(layer) + g] = bb[g];
+        }
+    } else {
+        for (int i = 0; i < HP * 2; ++i) dst[wl.off_wl() + i] = 0.f;
+        for (int a = 0; a < 2; ++a) {
+            for (int i = 0; i < H; ++i) dst[wl.off_wl() + i * 2 + a] = w[(size_t)a * H + i];
+            dst[wl.off_bl() + a] = bb[a];
+        }
+    }
+    CK(cudaMemcpyAsync(h->d_weights, h->w_host.data(), h->weights_floats * sizeof(float), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+static int launch_check(fgnn_handle* h, int n = 1) {
+    h->launches += n;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// bin (if needed) -> scan -> scatter -> canon -> adjacency
+static int enqueue_build(fgnn_handle* h, int advance, cudaStream_t st) {
+    Params& p = h->p;
+    const int gb = blocks_for(p.M, 256);
+    if (!h->binned) {
+        k_bin<<<gb, 256, 0, st>>>(p);
+        if (launch_check(h)) return 1;
+    }
+    k_scan<<<p.n_tiles, SCAN_THREADS, 0, st>>>(p, advance);
+    k_scatter<<<gb, 256, 0, st>>>(p);
+    k_canon<<<gb, 256, 0, st>>>(p);
+    k_adjacency<<<gb, 256, 0, st>>>(p);
+    if (launch_check(h, 4)) return 1;
+    h->binned = false;
+    if (advance) h->t_host += 1;
+    return 0;
+}
+
+static int enqueue_hops(fgnn_handle* h, cudaStream_t st) {
+    Params& p = h->p;
+    const int gb = blocks_for(p.M, 256);
+    for (int j = 0; j + 2 < p.K; ++j) {     // hops 0 .. K-3 ; hop K-2 lives in the final kernel
+        const int nb = p.K - 1 - j;
+        if (nb == 3) k_hop<3><<<gb, 256, 0, st>>>(p, j);
+        else if (nb == 2) k_hop<2><<<gb, 256, 0, st>>>(p, j);
+        else k_hop<1><<<gb, 256, 0, st>>>(p, j);
+        if (launch_check(h)) return 1;
+    }
+    return 0;
+}
+
+static int enqueue_final(fgnn_handle* h, bool closed, int write_z, cudaStream_t st) {
+    Params p = h->p;
+    p.write_z_last = write_z;
+    final_kernel_t fk = final_kernel(p.K, h->HP, closed);
+    const int grid = closed ? h->final_grid_closed : h->final_grid_open;
+    fk<<<grid, FINAL_THREADS, h->final_smem, st>>>(p);
+    if (launch_check(h)) return 1;
+    if (closed) h->binned = true;
+    return 0;
+}
+
+static int copy_out(void* dst, const void* src, size_t bytes, cudaStream_t st) {
+    if (!dst) return 0;
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, st));
+    return 0;
+}
+
+extern "C" int fgnn_set_state(fgnn_handle* h, const double* x, void* stream) {
+    if (!h || !x) return fail("fgnn_set_state: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaMemcpyAsync(h->p.state, x, (size_t)h->p.M * sizeof(double4), cudaMemcpyDefault, st));
+    if (h->binned) {
+        CK(cudaMemsetAsync(h->p.cell_count, 0, ((size_t)h->p.C + 1) * sizeof(int), st));
+        CK(cudaMemsetAsync(h->p.racc, 0, (size_t)h->p.B * 4 * sizeof(double), st));
+        CK(cudaMemsetAsync(h->p.reward_pending, 0, sizeof(int), st));
+        h->binned = false;
+    }
+    return 0;
+}
+
+extern "C" int fgnn_reset(fgnn_handle* h, const double* x, void* stream) {
+    if (!h || !x) return fail("fgnn_reset: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    Params& p = h->p;
+    CK(cudaSetDevice(h->cfg.device));
+    const size_t M = p.M, K = p.K;
+    CK(cudaMemsetAsync(p.xhist, 0, K * M * ROW * sizeof(float), st));
+    CK(cudaMemsetAsync(p.zbuf, 0, K * M * ROW * sizeof(float), st));
+    CK(cudaMemsetAsync(p.ybuf, 0, 2 * K * M * ROW * sizeof(float), st));
+    CK(cudaMemsetAsync(p.sinv, 0, K * M * sizeof(float), st));
+    CK(cudaMemsetAsync(p.row_start, 0, K * M * sizeof(unsigned), st));
+    CK(cudaMemsetAsync(p.deg, 0, K * M * sizeof(int), st));
+    CK(cudaMemsetAsync(p.nnz_cursor, 0, K * sizeof(unsigned), st));
+    CK(cudaMemsetAsync(p.t, 0, sizeof(int), st));
+    CK(cudaMemsetAsync(p.cell_count, 0, ((size_t)p.C + 1) * sizeof(int), st));
+    CK(cudaMemsetAsync(p.tile_status, 0, (size_t)p.n_tiles * sizeof(unsigned), st));
+    CK(cudaMemsetAsync(p.tile_counter, 0, sizeof(int), st));
+    CK(cudaMemsetAsync(p.racc, 0, (size_t)p.B * 4 * sizeof(double), st));
+    CK(cudaMemsetAsync(p.reward, 0, (size_t)p.B * sizeof(double), st));
+    CK(cudaMemsetAsync(p.reward_pending, 0, sizeof(int), st));
+    CK(cudaMemsetAsync(p.action, 0, M * 2 * sizeof(float), st));
+    h->binned = false;
+    h->t_host = 0;
+    CK(cudaMemcpyAsync(p.state, x, M * sizeof(double4), cudaMemcpyDefault, st));
+    return enqueue_build(h, 0, st);
+}
+
+extern "C" int fgnn_build_graph(fgnn_handle* h, int32_t advance, void* stream) {
+    if (!h) return fail("fgnn_build_graph: null handle");
+    CK(cudaSetDevice(h->cfg.device));
+    return enqueue_build(h, advance, (cudaStream_t)stream);
+}
+
+extern "C" int fgnn_integrate(fgnn_handle* h, const float* u, double* reward_b, void* stream) {
+    if (!h || !u) return fail("fgnn_integrate: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    Params& p = h->p;
+    CK(cudaSetDevice(h->cfg.device));
+    if (h->binned) {      // positions were binned already (closed-loop kernel or a previous integrate): start over
+        CK(cudaMemsetAsync(p.cell_count, 0, ((size_t)p.C + 1) * sizeof(int), st));
+        CK(cudaMemsetAsync(p.racc, 0, (size_t)p.B * 4 * sizeof(double), st));
+    }
+    CK(cudaMemcpyAsync(h->d_u_in, u, (size_t)p.M * 2 * sizeof(float), cudaMemcpyDefault, st));
+    k_integrate<<<blocks_for(p.M, 256), 256, 0, st>>>(p, h->d_u_in);
+    if (launch_check(h)) return 1;
+    h->binned = true;
+    if (reward_b) {
+        k_finalize_reward<<<1, 256, 0, st>>>(p);
+        if (launch_check(h)) return 1;
+        return copy_out(reward_b, p.reward, (size_t)p.B * sizeof(double), st);
+    }
+    return 0;
+}
+
+extern "C" int fgnn_env_step(fgnn_handle* h, const float* u, double* reward_b, void* stream) {
+    if (fgnn_integrate(h, u, nullptr, stream)) return 1;
+    if (enqueue_build(h, 1, (cudaStream_t)stream)) return 1;
+    return copy_out(reward_b, h->p.reward, (size_t)h->p.B * sizeof(double), (cudaStream_t)stream);
+}
+
+extern "C" int fgnn_policy(fgnn_handle* h, float* action, void* stream) {
+    if (!h) return fail("fgnn_policy: null handle");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(h->cfg.device));
+    if (enqueue_hops(h, st)) return 1;
+    if (enqueue_final(h, false, 1, st)) return 1;
+    return copy_out(action, h->p.action, (size_t)h->p.M * 2 * sizeof(float), st);
+}
+
+static int enqueue_closed_step(fgnn_handle* h, cudaStream_t st) {
+    if (enqueue_hops(h, st)) return 1;
+    if (enqueue_final(h, true, 0, st)) return 1;
+    return enqueue_build(h, 1, st);
+}
+
+extern "C" int fgnn_step(fgnn_handle* h, float* action, double* reward_b, void* stream) {
+    if (!h) return fail("fgnn_step: null handle");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(h->cfg.device));
+    if (h->binned) return fail("fgnn_step: state was integrated but the graph not rebuilt (call fgnn_build_graph)");
+    if (enqueue_closed_step(h, st)) return 1;
+    if (copy_out(action, h->p.action, (size_t)h->p.M * 2 * sizeof(float), st)) return 1;
+    return copy_out(reward_b, h->p.reward, (size_t)h->p.B * sizeof(double), st);
+}
+
+extern "C" int fgnn_rollout(fgnn_handle* h, int32_t T, double* reward_bt, void* stream) {
+    if (!h || T < 0) return fail("fgnn_rollout: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    Params& p = h->p;
+    CK(cudaSetDevice(h->cfg.device));
+    if (h->binned) return fail("fgnn_rollout: state was integrated but the graph not rebuilt");
+    if (T == 0) return 0;
+    const bool want_log = reward_bt != nullptr;
+    if (T > h->reward_log_cap) {
+        if (h->d_reward_log) CK(cudaFree(h->d_reward_log));
+        h->d_reward_log = nullptr;
+        int cap = T < 256 ? 256 : T;
+        CK(cudaMalloc(&h->d_reward_log, (size_t)cap * p.B * sizeof(double)));
+        h->reward_log_cap = cap;
+        if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+        if (h->graph) { cudaGraphDestroy(h->graph); h->graph = nullptr; }
+    }
+    if (!h->graph_exec) {
+        // capture one closed-loop step; the device step counter makes the same graph valid for every t
+        p.reward_log = h->d_reward_log;      // only the captured step logs rewards
+        cudaStream_t cs;
+        CK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+        const int64_t l0 = h->launches, t0 = h->t_host;
+        CK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+        int rc = enqueue_closed_step(h, cs);
+        cudaError_t e = cudaStreamEndCapture(cs, &h->graph);
+        cudaStreamDestroy(cs);
+        p.reward_log = nullptr;
+        h->graph_kernels = (int)(h->launches - l0);
+        h->launches = l0;
+        h->t_host = t0;
+        if (rc) return 1;
+        if (e != cudaSuccess) return fail(std::string("fgnn_rollout: capture failed: ") + cudaGetErrorString(e));
+        CK(cudaGraphInstantiate(&h->graph_exec, h->graph, 0));
+    }
+    if (h->d_reward_log) CK(cudaMemsetAsync(p.log_index, 0, sizeof(int), st));
+    for (int i = 0; i < T; ++i) CK(cudaGraphLaunch(h->graph_exec, st));
+    h->launches += (int64_t)h->graph_kernels * T;
+    h->t_host += T;
+    h->binned = false;
+    if (want_log) return copy_out(reward_bt, h->d_reward_log, (size_t)T * p.B * sizeof(double), st);
+    return 0;
+}
+
+extern "C" int fgnn_actor_forward_dense(fgnn_handle* h, int32_t batch, int32_t n2, const float* ds, const float* gso,
+                                        float* out, void* stream) {
+    if (!h || !ds || !gso || !out) return fail("fgnn_actor_forward_dense: null argument");
+    if (batch < 1 || n2 < 1) return fail("fgnn_actor_forward_dense: empty batch");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(h->cfg.device));
+    const int K = h->cfg.k;
+    dense_kernel_t dk = dense_kernel(K, h->HP);
+    WeightLayout wl{F * K, h->HP, h->cfg.n_layers};
+    size_t smem = (size_t)K * F * DENSE_MT * sizeof(float) +
+                  (h->HP > 64 ? (size_t)2 * h->HP * FINAL_THREADS * sizeof(float) : (size_t)wl.total() * sizeof(float));
+    CK(cudaFuncSetAttribute((const void*)dk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(blocks_for(n2, FINAL_THREADS), batch);
+    dk<<<grid, FINAL_THREADS, smem, st>>>(ds, gso, out, h->d_weights, h->cfg.n_layers, n2);
+    return launch_check(h);
+}
+
+// ---- read-back ----------------------------------------------------------------------------
+extern "C" int fgnn_get_state(fgnn_handle* h, double* x, void* stream) {
+    if (!h || !x) return fail("fgnn_get_state: null argument");
+    CK(cudaSetDevice(h->cfg.device));
+    return copy_out(x, h->p.state, (size_t)h->p.M * sizeof(double4), (cudaStream_t)stream);
+}
+
+static int age_slot(fgnn_handle* h, int age, int* slot) {
+    if (age < 0 || age >= h->cfg.k) return fail("age must be in 0..k-1");
+    *slot = slot_of((int)(h->t_host - age), h->cfg.k);
+    return 0;
+}
+
+extern "C" int fgnn_get_features(fgnn_handle* h, int32_t age, float* out, void* stream) {
+    if (!h || !out) return fail("fgnn_get_features: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(h->cfg.device));
+    int g;
+    if (age_slot(h, age, &g)) return 1;
+    const int M = h->p.M;
+    k_pack_rows<<<blocks_for(M * F, 256), 256, 0, st>>>(h->p.xhist + (size_t)g * M * ROW, h->d_staging, M);
+    if (launch_check(h)) return 1;
+    return copy_out(out, h->d_staging, (size_t)M * F * sizeof(float), st);
+}
+
+extern "C" int fgnn_get_degrees(fgnn_handle* h, int32_t age, int32_t* out, void* stream) {
+    if (!h || !out) return fail("fgnn_get_degrees: null argument");
+    CK(cudaSetDevice(h->cfg.device));
+    int g;
+    if (age_slot(h, age, &g)) return 1;
+    return copy_out(out, h->p.deg + (size_t)g * h->p.M, (size_t)h->p.M * sizeof(int), (cudaStream_t)stream);
+}
+
+extern "C" int fgnn_get_aggregated(fgnn_handle* h, float* out, void* stream) {
+    if (!h || !out) return fail("fgnn_get_aggregated: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(h->cfg.device));
+    const int M = h->p.M, K = h->cfg.k;
+    for (int k = 0; k < K; ++k) {
+        const float* rows = k == 0 ? h->p.xhist + (size_t)slot_of((int)h->t_host, K) * M * ROW
+                                   : h->p.zbuf + (size_t)k * M * ROW;
+        k_pack_rows<<<blocks_for(M * F, 256), 256, 0, st>>>(rows, h->d_staging + (size_t)k * M * F, M);
+        if (launch_check(h)) return 1;
+    }
+    return copy_out(out, h->d_staging, (size_t)K * M * F * sizeof(float), st);
+}
+
+extern "C" int fgnn_get_action(fgnn_handle* h, float* out, void* stream) {
+    if (!h || !out) return fail("fgnn_get_action: null argument");
+    CK(cudaSetDevice(h->cfg.device));
+    return copy_out(out, h->p.action, (size_t)h->p.M * 2 * sizeof(float), (cudaStream_t)stream);
+}
+
+extern "C" int fgnn_export_network_dense(fgnn_handle* h, int32_t age, float* out, void* stream) {
+    if (!h || !out) return fail("fgnn_export_network_dense: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(h->cfg.device));
+    int g;
+    if (age_slot(h, age, &g)) return 1;
+    const size_t n = (size_t)h->p.B * h->p.N * h->p.N;
+    cudaPointerAttributes attr;
+    const bool on_device = cudaPointerGetAttributes(&attr, out) == cudaSuccess && attr.type == cudaMemoryTypeDevice;
+    cudaGetLastError();
+    float* d_out = out;
+    if (!on_device) CK(cudaMallocAsync((void**)&d_out, n * sizeof(float), st));
+    CK(cudaMemsetAsync(d_out, 0, n * sizeof(float), st));
+    k_export_dense<<<blocks_for(h->p.M, 256), 256, 0, st>>>(h->p, g, d_out);
+    if (launch_check(h)) return 1;
+    if (!on_device) {
+        CK(cudaMemcpyAsync(out, d_out, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CK(cudaFreeAsync(d_out, st));
+    }
+    return 0;
+}
+
+extern "C" int fgnn_get_csr(fgnn_handle* h, int32_t age, const uint32_t** row_start, const int32_t** deg,
+                            const int32_t** cols, const float** src_scale) {
+    if (!h) return fail("fgnn_get_csr: null handle");
+    int g;
+    if (age_slot(h, age, &g)) return 1;
+    const size_t M = h->p.M;
+    if (row_start) *row_start = h->p.row_start + g * M;
+    if (deg) *deg = h->p.deg + g * M;
+    if (cols) *cols = h->p.cols + (size_t)g * h->p.nnz_cap;
+    if (src_scale) *src_scale = h->p.sinv + g * M;
+    return 0;
+}
+
+extern "C" int fgnn_get_stats(fgnn_handle* h, fgnn_stats* out, void* stream) {
+    if (!h || !out) return fail("fgnn_get_stats: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(h->cfg.device));
+    int t = 0, ovf = 0;
+    unsigned cur[KMAX] = {0, 0, 0, 0};
+    CK(cudaMemcpyAsync(&t, h->p.t, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&ovf, h->p.overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(cur, h->p.nnz_cursor, h->cfg.k * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    out->step = t;
+    out->n_edges = cur[slot_of(t, h->cfg.k)];
+    out->overflow = ovf;
+    out->grid_dim = h->p.G;
+    out->n_cells = h->p.C;
+    out->edge_capacity = h->p.nnz_cap;
+    return 0;
+}
+
+extern "C" int fgnn_memcpy_sync(void* dst, const void* src, uint64_t bytes, void* stream) {
+    if (!dst || !src) return fail("fgnn_memcpy_sync: null argument");
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    return 0;
+}
+
+extern "C" int64_t fgnn_launch_count(fgnn_handle* h) { return h ? h->launches : 0; }

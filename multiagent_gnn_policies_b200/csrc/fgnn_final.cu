@@ -1,0 +1,15 @@
+// fgnn_final.cu -- compiled once per (FGNN_K, FGNN_HP) pair: -DFGNN_K=<1..4> -DFGNN_HP=<16|32|64|128>
+#include "fgnn_final.cuh"
+
+#define FGNN_CAT2(a, b, c, d) a##b##c##d
+#define FGNN_CAT(a, b, c, d) FGNN_CAT2(a, b, c, d)
+
+namespace fgnn {
+typedef void (*final_kernel_t)(Params);
+typedef void (*dense_kernel_t)(const float*, const float*, float*, const float*, int, int);
+
+final_kernel_t FGNN_CAT(get_final_k, FGNN_K, _hp, FGNN_HP)(bool closed) {
+    return closed ? k_final<FGNN_K, FGNN_HP, true> : k_final<FGNN_K, FGNN_HP, false>;
+}
+dense_kernel_t FGNN_CAT(get_dense_k, FGNN_K, _hp, FGNN_HP)() { return k_actor_dense<FGNN_K, FGNN_HP>; }
+}  // namespace fgnn

@@ -1,0 +1,495 @@
+// fgnn_kernels.cuh -- device code of the flocking-GNN rollout engine (sm_100a).
+//
+// One rollout step =  [bin] -> scan -> scatter -> canon -> adjacency+features -> hop(s) -> final
+// (final = last hop + readout MLP + double integrator + binning of the new positions).
+// See DESIGN.md for the data layout and the per-kernel byte counts.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fgnn {
+
+constexpr int F = 6;          // features per agent (n_states)
+constexpr int ROW = 8;        // padded feature row: 8 floats = one 32-byte sector
+constexpr int KMAX = 4;       // filter taps supported
+constexpr int LMAX = 4;       // hidden layers supported
+constexpr int FINAL_THREADS = 128;   // block size of the fused final kernel and the dense Actor kernel
+constexpr int DENSE_MT = 32;         // m-tile of the dense Actor kernel
+
+// All device pointers one step needs.  Passed by value to every kernel.
+struct Params {
+    int M;                    // total agents = B * N
+    int N;                    // agents per episode
+    int B;                    // episodes
+    int K;                    // taps
+    int L;                    // hidden layers
+    int G;                    // cells per side (wrapped grid)
+    int C;                    // total cells = B*G*G
+    int mean_pooling;
+    int half_accel;
+    int write_z_last;         // final kernel also stores z_{K-1} (debug / fgnn_get_aggregated)
+    unsigned nnz_cap;         // directed-edge capacity per ring slot
+    double inv_cell;          // 1 / cell size  (cell size = R * (1 + 2^-20))
+    double R2;                // comm_radius^2
+    double dt;
+    double gain;              // action_scalar
+
+    int* t;                   // device step counter (index of the current graph)
+    double4* state;           // [M] px,py,vx,vy
+    int* cell_of;             // [M]
+    int* cell_count;          // [C+1]  (last entry stays 0)
+    int* cell_start;          // [C+1]
+    int* tmp_id;              // [M] scatter order (atomic, not canonical)
+    int* sorted_id;           // [M] canonical: by cell, then by agent id
+    double4* sorted_state;    // [M]
+    unsigned* tile_status;    // scan look-back words
+    int* tile_counter;        // scan dynamic tile id
+    int n_tiles;
+
+    float* xhist;             // [K][M][ROW]  features x_{t}, ring slot = t mod K
+    float* sinv;              // [K][M]       source scale 1/max(deg,1) (or 1)
+    unsigned* row_start;      // [K][M]
+    int* deg;                 // [K][M]
+    int* cols;                // [K][nnz_cap]
+    unsigned* nnz_cursor;     // [K]
+    int* overflow;            // sticky flag
+
+    float* zbuf;              // [K][M][ROW]  z_k, k >= 1
+    float* ybuf;              // [2][K][M][ROW] hop intermediates (ping-pong)
+    float* action;            // [M][2]
+    const float* weights;     // packed, see WeightLayout
+
+    double* racc;             // [B][4] sum vx, vy, vx^2, vy^2
+    double* reward;           // [B]
+    int* reward_pending;
+    double* reward_log;       // [T][B] or null
+    int* log_index;
+};
+
+__host__ __device__ inline int slot_of(int t, int K) { int s = t % K; return s < 0 ? s + K : s; }
+
+// Packed weights (floats): w0[6K][HP] b0[HP] | (L-1) x { wh[HP][HP] bh[HP] } | wl[HP][2] bl[2] (+pad)
+struct WeightLayout {
+    int in0, HP, L;
+    __host__ __device__ int off_w0() const { return 0; }
+    __host__ __device__ int off_b0() const { return in0 * HP; }
+    __host__ __device__ int off_wh(int l) const { return in0 * HP + HP + (l - 1) * (HP * HP + HP); }   // l = 1..L-1
+    __host__ __device__ int off_bh(int l) const { return off_wh(l) + HP * HP; }
+    __host__ __device__ int off_wl() const { return in0 * HP + HP + (L - 1) * (HP * HP + HP); }
+    __host__ __device__ int off_bl() const { return off_wl() + HP * 2; }
+    __host__ __device__ int total() const { return (off_bl() + 2 + 3) & ~3; }
+};
+
+// ------------------------------------------------------------------------------------------
+// helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int wrap(long long v, int G) {
+    int r = (int)(v % G);
+    return r < 0 ? r + G : r;
+}
+
+__device__ __forceinline__ void cell_coords(const Params& p, double px, double py, long long& ix, long long& iy) {
+    ix = (long long)floor(px * p.inv_cell);
+    iy = (long long)floor(py * p.inv_cell);
+}
+
+__device__ __forceinline__ int cell_index(const Params& p, int ep, long long ix, long long iy) {
+    return (ep * p.G + wrap(iy, p.G)) * p.G + wrap(ix, p.G);
+}
+
+// r2 exactly as numpy evaluates dx*dx + dy*dy (two roundings of the products, one of the sum; no FMA)
+__device__ __forceinline__ double r2_exact(double dx, double dy) {
+    return __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+}
+
+__device__ __forceinline__ void load_row6(const float* __restrict__ base, int idx, float (&v)[F]) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(base + (size_t)idx * ROW));
+    const float2 b = __ldg(reinterpret_cast<const float2*>(base + (size_t)idx * ROW + 4));
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y;
+}
+
+__device__ __forceinline__ void store_row6(float* base, int idx, const float (&v)[F]) {
+    float4* dst = reinterpret_cast<float4*>(base + (size_t)idx * ROW);
+    dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+    dst[1] = make_float4(v[4], v[5], 0.f, 0.f);
+}
+
+#ifdef FGNN_MAIN_TU
+// ------------------------------------------------------------------------------------------
+// K_A  bin: cell of every agent + per-cell population count
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_bin(Params p) {
+    int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= p.M) return;
+    double4 s = p.state[a];
+    long long ix, iy;
+    cell_coords(p, s.x, s.y, ix, iy);
+    int c = cell_index(p, a / p.N, ix, iy);
+    p.cell_of[a] = c;
+    atomicAdd(&p.cell_count[c], 1);
+}
+
+// reward_b = -(var(vx) + var(vy)) per episode from the accumulated sums; clears the sums
+static __device__ __forceinline__ void finalize_reward(const Params& p) {
+    if (*p.reward_pending == 0) return;
+    __syncthreads();
+    const int li = p.reward_log ? *p.log_index : 0;
+    for (int b = threadIdx.x; b < p.B; b += blockDim.x) {
+        double n = (double)p.N;
+        double sx = p.racc[b * 4 + 0], sy = p.racc[b * 4 + 1], qx = p.racc[b * 4 + 2], qy = p.racc[b * 4 + 3];
+        double mx = sx / n, my = sy / n;
+        double r = -((qx / n - mx * mx) + (qy / n - my * my));
+        p.reward[b] = r;
+        if (p.reward_log) p.reward_log[(size_t)li * p.B + b] = r;
+        p.racc[b * 4 + 0] = 0.0; p.racc[b * 4 + 1] = 0.0; p.racc[b * 4 + 2] = 0.0; p.racc[b * 4 + 3] = 0.0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        *p.reward_pending = 0;
+        if (p.reward_log) *p.log_index = li + 1;
+    }
+}
+
+__global__ void k_finalize_reward(Params p) { finalize_reward(p); }
+
+// ------------------------------------------------------------------------------------------
+// K_B  scan: exclusive prefix sum of cell_count[0..C] -> cell_start[0..C] (single pass,
+//      decoupled look-back), zeroes cell_count; tile 0 also advances t and finalises the reward.
+// ------------------------------------------------------------------------------------------
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+constexpr unsigned FLAG_AGG = 1u << 30, FLAG_INC = 2u << 30, VAL_MASK = (1u << 30) - 1;
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan(Params p, int advance) {
+    __shared__ int s_tile;
+    __shared__ int s_warp[SCAN_THREADS / 32];
+    __shared__ int s_excl;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(p.tile_counter, 1);
+    __syncthreads();
+    const int tile = s_tile;
+    if (tile == 0) {
+        if (tid == 0) {
+            const int tn = *p.t + (advance ? 1 : 0);
+            *p.t = tn;
+            p.nnz_cursor[slot_of(tn, p.K)] = 0;      // edge cursor of the slot about to be rebuilt
+        }
+        finalize_reward(p);
+    }
+    const int n = p.C + 1;
+    const int base = tile * SCAN_TILE + tid * SCAN_ITEMS;
+    int v[SCAN_ITEMS];
+    int sum = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        int idx = base + i;
+        v[i] = idx < n ? p.cell_count[idx] : 0;
+        sum += v[i];
+    }
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        int idx = base + i;
+        if (idx < n) p.cell_count[idx] = 0;
+    }
+    // block exclusive scan of the per-thread sums
+    int inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += y;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int w = lane < SCAN_THREADS / 32 ? s_warp[lane] : 0;
+        int winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int y = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += y;
+        }
+        if (lane < SCAN_THREADS / 32) s_warp[lane] = winc - w;      // exclusive per-warp offsets
+        const int total = __shfl_sync(0xffffffffu, winc, SCAN_THREADS / 32 - 1);
+        // publish the tile aggregate, then look back over predecessor tiles 32 at a time
+        volatile unsigned* status = p.tile_status;
+        int excl = 0;
+        if (tile == 0) {
+            if (lane == 0) status[0] = FLAG_INC | (unsigned)total;
+        } else {
+            if (lane == 0) status[tile] = FLAG_AGG | (unsigned)total;
+            __threadfence();
+            int look = tile - 1;
+            while (true) {
+                int idx = look - lane;
+                unsigned w32 = FLAG_INC;        // out-of-range lanes act as a zero inclusive prefix
+                if (idx >= 0) {
+                    do { w32 = status[idx]; } while ((w32 >> 30) == 0);
+                }
+                unsigned inc_mask = __ballot_sync(0xffffffffu, (w32 >> 30) == 2u);
+                int first_inc = inc_mask ? __ffs(inc_mask) - 1 : 32;     // nearest tile with an inclusive prefix
+                int contrib = (lane <= first_inc) ? (int)(w32 & VAL_MASK) : 0;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+                excl += contrib;
+                if (inc_mask) break;
+                look -= 32;
+            }
+            if (lane == 0) {
+                __threadfence();
+                status[tile] = FLAG_INC | (unsigned)(excl + total);
+            }
+        }
+        if (lane == 0) s_excl = excl;
+    }
+    __syncthreads();
+    int run = s_excl + s_warp[warp] + (inc - sum);
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        int idx = base + i;
+        if (idx < n) p.cell_start[idx] = run;
+        run += v[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K_C  scatter agent ids into their cell's slot range (atomic order, canonicalised by K_C2)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_scatter(Params p) {
+    int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= p.M) return;
+    int c = p.cell_of[a];
+    int slot = p.cell_start[c] + atomicAdd(&p.cell_count[c], 1);
+    p.tmp_id[slot] = a;
+}
+
+// K_C2 canon: order every cell's list by agent id (rank by counting), copy the state next to it.
+//      Makes CSR row order -- and with it every fp32 sum downstream -- run-to-run reproducible.
+__global__ void __launch_bounds__(256) k_canon(Params p) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int i = s; i <= p.C; i += gridDim.x * blockDim.x) p.cell_count[i] = 0;   // fill counters -> 0 for the next bin
+    if (s >= p.M) return;
+    int a = p.tmp_id[s];
+    int c = p.cell_of[a];
+    int q0 = p.cell_start[c], q1 = p.cell_start[c + 1];
+    int rank = 0;
+    for (int q = q0; q < q1; ++q) rank += (p.tmp_id[q] < a) ? 1 : 0;
+    int dst = q0 + rank;
+    p.sorted_id[dst] = a;
+    p.sorted_state[dst] = p.state[a];
+}
+
+// ------------------------------------------------------------------------------------------
+// K_D  adjacency + degree + 6-d relative features (gym_flock compute_helpers), CSR emission.
+//      One thread per agent, in cell-sorted order; float64 arithmetic for the radius cut and the
+//      feature sums (bit-identical edge set to the float64 oracle).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_adjacency(Params p) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    // housekeeping for the next scan
+    for (int i = s; i < p.n_tiles; i += gridDim.x * blockDim.x) p.tile_status[i] = 0;
+    if (s == 0) *p.tile_counter = 0;
+
+    const int t = *p.t;
+    const int g = slot_of(t, p.K);
+    const bool valid = s < p.M;
+    int a = 0, ep = 0;
+    double4 me = make_double4(0, 0, 0, 0);
+    int q0[9], q1[9];
+    int count = 0;
+    if (valid) {
+        a = p.sorted_id[s];
+        me = p.sorted_state[s];
+        ep = a / p.N;
+        long long ix, iy;
+        cell_coords(p, me.x, me.y, ix, iy);
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+            int c = cell_index(p, ep, ix + (j % 3) - 1, iy + (j / 3) - 1);
+            q0[j] = __ldg(&p.cell_start[c]);
+            q1[j] = __ldg(&p.cell_start[c + 1]);
+        }
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+            for (int q = q0[j]; q < q1[j]; ++q) {
+                const double2 o = *reinterpret_cast<const double2*>(&p.sorted_state[q]);
+                double r2 = r2_exact(me.x - o.x, me.y - o.y);
+                count += (q != s && r2 < p.R2) ? 1 : 0;
+            }
+        }
+    }
+    // reserve a contiguous run of edge slots for the warp's 32 rows
+    int inc = count;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += y;
+    }
+    const int total = __shfl_sync(0xffffffffu, inc, 31);
+    unsigned base = 0;
+    if (lane == 31 && total > 0) base = atomicAdd(&p.nnz_cursor[g], (unsigned)total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    if (!valid) return;
+    unsigned row = base + (unsigned)(inc - count);
+    if (row + (unsigned)count > p.nnz_cap || row + (unsigned)count < row) {   // capacity exceeded: drop the row, flag it
+        *p.overflow = 1;
+        count = 0;
+        row = 0;
+    }
+    double f0 = 0, f1 = 0, f2 = 0, f3 = 0, f4 = 0, f5 = 0;
+    int* cols = p.cols + (size_t)g * p.nnz_cap + row;
+    int w = 0;
+    if (count > 0) {
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+            for (int q = q0[j]; q < q1[j]; ++q) {
+                const double4 o = p.sorted_state[q];
+                double dx = me.x - o.x, dy = me.y - o.y;
+                double r2 = r2_exact(dx, dy);
+                if (q != s && r2 < p.R2) {
+                    double inv = 1.0 / r2;
+                    double inv2 = inv * inv;
+                    f0 += me.z - o.z;
+                    f1 += dx * inv2;
+                    f2 += dx * inv;
+                    f3 += me.w - o.w;
+                    f4 += dy * inv2;
+                    f5 += dy * inv;
+                    cols[w++] = __ldg(&p.sorted_id[q]);
+                }
+            }
+        }
+    }
+    float* xr = p.xhist + ((size_t)g * p.M + a) * ROW;
+    reinterpret_cast<float4*>(xr)[0] = make_float4((float)f0, (float)f1, (float)f2, (float)f3);
+    reinterpret_cast<float4*>(xr)[1] = make_float4((float)f4, (float)f5, 0.f, 0.f);
+    p.deg[(size_t)g * p.M + a] = count;
+    p.row_start[(size_t)g * p.M + a] = row;
+    p.sinv[(size_t)g * p.M + a] = p.mean_pooling ? (float)(1.0 / (double)(count > 0 ? count : 1)) : 1.0f;
+}
+
+#endif  // FGNN_MAIN_TU
+
+// ------------------------------------------------------------------------------------------
+// K_E  graph-shift hop j (not the last one): for taps k = j+1 .. K-1
+//      Y_k <- Y_k * A_{t-j}   i.e.  out_k[n] = sum_{m in N_{t-j}(n)} in_k[m] * sinv_{t-j}[m]
+//      in_k = x_{t-k} (j == 0) or the previous hop's intermediate; tap k = j+1 is finished (z_k).
+// ------------------------------------------------------------------------------------------
+template <int NB>
+__global__ void __launch_bounds__(256) k_hop(Params p, int j) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= p.M) return;
+    const int t = *p.t;
+    const int g = slot_of(t - j, p.K);
+    const size_t M = p.M;
+    const float* src[NB];
+    float* dst[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        int k = j + 1 + b;
+        src[b] = (j == 0) ? p.xhist + (size_t)slot_of(t - k, p.K) * M * ROW
+                          : p.ybuf + ((size_t)((j - 1) & 1) * p.K + k) * M * ROW;
+        dst[b] = (b == 0) ? p.zbuf + (size_t)k * M * ROW : p.ybuf + ((size_t)(j & 1) * p.K + k) * M * ROW;
+    }
+    const unsigned rs = p.row_start[(size_t)g * M + a];
+    const int d = p.deg[(size_t)g * M + a];
+    const int* __restrict__ cols = p.cols + (size_t)g * p.nnz_cap + rs;
+    const float* __restrict__ sinv = p.sinv + (size_t)g * M;
+    float acc[NB][F];
+#pragma unroll
+    for (int b = 0; b < NB; ++b)
+#pragma unroll
+        for (int f = 0; f < F; ++f) acc[b][f] = 0.f;
+    for (int e = 0; e < d; ++e) {
+        const int m = __ldg(&cols[e]);
+        const float sc = __ldg(&sinv[m]);
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            float v[F];
+            load_row6(src[b], m, v);
+#pragma unroll
+            for (int f = 0; f < F; ++f) acc[b][f] = fmaf(v[f], sc, acc[b][f]);
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < NB; ++b) store_row6(dst[b], a, acc[b]);
+}
+
+// double integrator exactly in numpy's evaluation order (no FMA contraction), then bin the new position
+__device__ __forceinline__ void integrate_and_bin(const Params& p, int a, float u0, float u1) {
+    double4 s = p.state[a];
+    const double ax = __dmul_rn((double)u0, p.gain), ay = __dmul_rn((double)u1, p.gain);
+    double nx = __dadd_rn(s.x, __dmul_rn(s.z, p.dt));
+    double ny = __dadd_rn(s.y, __dmul_rn(s.w, p.dt));
+    if (p.half_accel) {
+        nx = __dadd_rn(nx, __dmul_rn(__dmul_rn(__dmul_rn(ax, p.dt), p.dt), 0.5));
+        ny = __dadd_rn(ny, __dmul_rn(__dmul_rn(__dmul_rn(ay, p.dt), p.dt), 0.5));
+    }
+    const double nvx = __dadd_rn(s.z, __dmul_rn(ax, p.dt));
+    const double nvy = __dadd_rn(s.w, __dmul_rn(ay, p.dt));
+    p.state[a] = make_double4(nx, ny, nvx, nvy);
+    long long ix, iy;
+    cell_coords(p, nx, ny, ix, iy);
+    const int ep = a / p.N;
+    const int c = cell_index(p, ep, ix, iy);
+    p.cell_of[a] = c;
+    atomicAdd(&p.cell_count[c], 1);
+    // velocity-variance reward: per-episode sums (warp-reduced when the warp sits in one episode)
+    double v0 = nvx, v1 = nvy, v2 = nvx * nvx, v3 = nvy * nvy;
+    const unsigned mask = __activemask();
+    const int ep0 = __shfl_sync(mask, ep, __ffs(mask) - 1);
+    const bool uniform = __all_sync(mask, ep == ep0);
+    if (uniform && mask == 0xffffffffu) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+            v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+            v2 += __shfl_xor_sync(0xffffffffu, v2, o);
+            v3 += __shfl_xor_sync(0xffffffffu, v3, o);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(&p.racc[ep * 4 + 0], v0); atomicAdd(&p.racc[ep * 4 + 1], v1);
+            atomicAdd(&p.racc[ep * 4 + 2], v2); atomicAdd(&p.racc[ep * 4 + 3], v3);
+        }
+    } else {
+        atomicAdd(&p.racc[ep * 4 + 0], v0); atomicAdd(&p.racc[ep * 4 + 1], v1);
+        atomicAdd(&p.racc[ep * 4 + 2], v2); atomicAdd(&p.racc[ep * 4 + 3], v3);
+    }
+    if (a == 0) *p.reward_pending = 1;
+}
+
+#ifdef FGNN_MAIN_TU
+// first half of env.step(u) with an externally supplied action
+__global__ void __launch_bounds__(256) k_integrate(Params p, const float* __restrict__ u) {
+    int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= p.M) return;
+    const float2 uu = reinterpret_cast<const float2*>(u)[a];
+    integrate_and_bin(p, a, uu.x, uu.y);
+}
+
+// ------------------------------------------------------------------------------------------
+// read-back helpers
+// ------------------------------------------------------------------------------------------
+__global__ void k_pack_rows(const float* __restrict__ rows, float* __restrict__ out, int M) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M * F) return;
+    int a = i / F, f = i % F;
+    out[i] = rows[(size_t)a * ROW + f];
+}
+
+__global__ void k_export_dense(Params p, int g, float* __restrict__ out) {
+    int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= p.M) return;
+    const int ep = a / p.N, i = a % p.N;
+    const unsigned rs = p.row_start[(size_t)g * p.M + a];
+    const int d = p.deg[(size_t)g * p.M + a];
+    const float sc = p.sinv[(size_t)g * p.M + a];
+    const int* cols = p.cols + (size_t)g * p.nnz_cap + rs;
+    float* row = out + ((size_t)ep * p.N + i) * p.N;
+    for (int e = 0; e < d; ++e) row[cols[e] % p.N] = sc;
+}
+
+#endif  // FGNN_MAIN_TU
+
+}  // namespace fgnn

@@ -1,0 +1,329 @@
+"""ctypes binding of libfgnn.so (include/fgnn.h) -- the host-side handle of the rollout engine.
+
+There is NO CPU fallback: importing works anywhere (so CPU-only tests can check the ABI), but
+constructing a :class:`FlockEngine` without the CUDA library or without a GPU raises.
+PyTorch is used only for device memory and streams.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfgnn.so")
+
+ABI_SYMBOLS = [
+    "fgnn_last_error", "fgnn_version", "fgnn_create", "fgnn_destroy", "fgnn_set_weights", "fgnn_reset",
+    "fgnn_set_state", "fgnn_build_graph", "fgnn_integrate", "fgnn_env_step", "fgnn_policy", "fgnn_step",
+    "fgnn_rollout", "fgnn_actor_forward_dense", "fgnn_get_state", "fgnn_get_features", "fgnn_get_degrees",
+    "fgnn_get_aggregated", "fgnn_get_action", "fgnn_export_network_dense", "fgnn_get_csr", "fgnn_get_stats",
+    "fgnn_memcpy_sync", "fgnn_launch_count",
+]
+
+
+class FgnnConfig(ctypes.Structure):
+    _fields_ = [
+        ("n_agents", ctypes.c_int32), ("n_episodes", ctypes.c_int32), ("k", ctypes.c_int32),
+        ("n_states", ctypes.c_int32), ("n_actions", ctypes.c_int32), ("hidden", ctypes.c_int32),
+        ("n_layers", ctypes.c_int32), ("mean_pooling", ctypes.c_int32), ("half_accel_term", ctypes.c_int32),
+        ("device", ctypes.c_int32), ("grid_dim", ctypes.c_int32), ("edge_capacity", ctypes.c_int32),
+        ("readout_mode", ctypes.c_int32), ("reserved0", ctypes.c_int32),
+        ("comm_radius", ctypes.c_double), ("dt", ctypes.c_double), ("action_scalar", ctypes.c_double),
+    ]
+
+
+class FgnnStats(ctypes.Structure):
+    _fields_ = [
+        ("step", ctypes.c_int64), ("n_edges", ctypes.c_int64), ("overflow", ctypes.c_int32),
+        ("grid_dim", ctypes.c_int32), ("n_cells", ctypes.c_int64), ("edge_capacity", ctypes.c_int64),
+    ]
+
+
+class FgnnError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library(path=None):
+    """dlopen libfgnn.so and declare the prototypes of include/fgnn.h.  Raises if it is not built."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise FgnnError(f"{path} not found: build it with `python -m multiagent_gnn_policies_b200.build` "
+                        "(there is no CPU fallback)")
+    lib = ctypes.CDLL(path)
+    vp, i32, i64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64
+    lib.fgnn_last_error.restype = ctypes.c_char_p
+    lib.fgnn_last_error.argtypes = []
+    lib.fgnn_version.restype = ctypes.c_int
+    lib.fgnn_create.argtypes = [ctypes.POINTER(FgnnConfig), ctypes.POINTER(vp)]
+    lib.fgnn_destroy.argtypes = [vp]
+    lib.fgnn_set_weights.argtypes = [vp, i32, vp, vp, vp]
+    lib.fgnn_reset.argtypes = [vp, vp, vp]
+    lib.fgnn_set_state.argtypes = [vp, vp, vp]
+    lib.fgnn_build_graph.argtypes = [vp, i32, vp]
+    lib.fgnn_integrate.argtypes = [vp, vp, vp, vp]
+    lib.fgnn_env_step.argtypes = [vp, vp, vp, vp]
+    lib.fgnn_policy.argtypes = [vp, vp, vp]
+    lib.fgnn_step.argtypes = [vp, vp, vp, vp]
+    lib.fgnn_rollout.argtypes = [vp, i32, vp, vp]
+    lib.fgnn_actor_forward_dense.argtypes = [vp, i32, i32, vp, vp, vp, vp]
+    lib.fgnn_get_state.argtypes = [vp, vp, vp]
+    lib.fgnn_get_features.argtypes = [vp, i32, vp, vp]
+    lib.fgnn_get_degrees.argtypes = [vp, i32, vp, vp]
+    lib.fgnn_get_aggregated.argtypes = [vp, vp, vp]
+    lib.fgnn_get_action.argtypes = [vp, vp, vp]
+    lib.fgnn_export_network_dense.argtypes = [vp, i32, vp, vp]
+    lib.fgnn_get_csr.argtypes = [vp, i32, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp)]
+    lib.fgnn_get_stats.argtypes = [vp, ctypes.POINTER(FgnnStats), vp]
+    lib.fgnn_memcpy_sync.argtypes = [vp, vp, ctypes.c_uint64, vp]
+    lib.fgnn_launch_count.argtypes = [vp]
+    lib.fgnn_launch_count.restype = i64
+    for name in ABI_SYMBOLS:
+        if name not in ("fgnn_last_error", "fgnn_launch_count", "fgnn_version"):
+            getattr(lib, name).restype = ctypes.c_int
+    if path == LIB_PATH:
+        _lib = lib
+    return lib
+
+
+def _ptr(obj):
+    """Raw address of a numpy array, a torch tensor, an int, or None."""
+    if obj is None:
+        return None
+    if isinstance(obj, int):
+        return obj
+    if isinstance(obj, np.ndarray):
+        assert obj.flags["C_CONTIGUOUS"], "array must be C-contiguous"
+        return obj.ctypes.data
+    if hasattr(obj, "data_ptr"):
+        assert obj.is_contiguous(), "tensor must be contiguous"
+        return obj.data_ptr()
+    raise TypeError(f"cannot take the address of {type(obj)}")
+
+
+class FlockEngine:
+    """One engine handle = B episodes x N agents of FlockingRelative-v0 + a K-tap aggregation-GNN actor.
+
+    Mirrors, on device, what the reference spreads over env.step (gym_flock),
+    MultiAgentStateWithDelay (learner/state_with_delay.py:6-53) and DAGGER.select_action
+    (learner/gnn_dagger.py:55-72)."""
+
+    def __init__(self, n_agents, k=3, hidden=32, n_layers=2, comm_radius=1.0, dt=0.01, n_episodes=1,
+                 device=0, action_scalar=10.0, mean_pooling=True, half_accel_term=True, grid_dim=0,
+                 edge_capacity=0, readout_mode=0, n_states=6, n_actions=2, stream=None):
+        import torch  # device memory + streams only
+        if not torch.cuda.is_available():
+            raise FgnnError("no CUDA device: the rollout engine has no CPU fallback")
+        self._torch = torch
+        self.lib = load_library()
+        self.n_agents, self.n_episodes, self.k = int(n_agents), int(n_episodes), int(k)
+        self.hidden, self.n_layers = int(hidden), int(n_layers)
+        self.n_states, self.n_actions = int(n_states), int(n_actions)
+        self.comm_radius, self.dt, self.action_scalar = float(comm_radius), float(dt), float(action_scalar)
+        self.device_index = int(device)
+        self.device = torch.device("cuda", self.device_index)
+        self.M = self.n_agents * self.n_episodes
+        self._stream = stream
+        cfg = FgnnConfig(self.n_agents, self.n_episodes, self.k, self.n_states, self.n_actions, self.hidden,
+                         self.n_layers, int(bool(mean_pooling)), int(bool(half_accel_term)), self.device_index,
+                         int(grid_dim), int(edge_capacity), int(readout_mode), 0,
+                         self.comm_radius, self.dt, self.action_scalar)
+        self._h = ctypes.c_void_p()
+        self._check(self.lib.fgnn_create(ctypes.byref(cfg), ctypes.byref(self._h)))
+
+    # -- plumbing ---------------------------------------------------------------------------
+    def _check(self, rc):
+        if rc != 0:
+            raise FgnnError(self.lib.fgnn_last_error().decode())
+
+    @property
+    def stream(self):
+        if self._stream is not None:
+            return self._stream
+        return self._torch.cuda.current_stream(self.device).cuda_stream
+
+    def sync(self):
+        self._torch.cuda.current_stream(self.device).synchronize()
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self.lib.fgnn_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- weights ----------------------------------------------------------------------------
+    def load_state_dict(self, sd):
+        """``conv_layers.{i}.weight`` (out,in,step,1) / ``.bias`` as in the reference checkpoint."""
+        for i in range(self.n_layers + 1):
+            w = sd[f"conv_layers.{i}.weight"]
+            b = sd[f"conv_layers.{i}.bias"]
+            w = np.ascontiguousarray(w.detach().cpu().numpy() if hasattr(w, "detach") else w, dtype=np.float32)
+            b = np.ascontiguousarray(b.detach().cpu().numpy() if hasattr(b, "detach") else b, dtype=np.float32)
+            out_dim = self.n_actions if i == self.n_layers else self.hidden
+            in_dim = self.n_states if i == 0 else self.hidden
+            step = self.k if i == 0 else 1
+            if w.reshape(w.shape[0], w.shape[1], -1).shape != (out_dim, in_dim, step):
+                raise FgnnError(f"layer {i}: weight shape {w.shape} does not match ({out_dim},{in_dim},{step},1)")
+            self._check(self.lib.fgnn_set_weights(self._h, i, _ptr(w), _ptr(b), self.stream))
+
+    # -- env side ---------------------------------------------------------------------------
+    def _as_state(self, x):
+        if hasattr(x, "data_ptr"):
+            assert x.dtype == self._torch.float64 and x.numel() == self.M * 4
+            return x.contiguous()
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        assert x.size == self.M * 4, f"state must have {self.M}x4 entries"
+        return x
+
+    def reset(self, x):
+        x = self._as_state(x)
+        self._check(self.lib.fgnn_reset(self._h, _ptr(x), self.stream))
+        if isinstance(x, np.ndarray):
+            self.sync()
+
+    def set_state(self, x):
+        x = self._as_state(x)
+        self._check(self.lib.fgnn_set_state(self._h, _ptr(x), self.stream))
+        if isinstance(x, np.ndarray):
+            self.sync()
+
+    def build_graph(self, advance=True):
+        self._check(self.lib.fgnn_build_graph(self._h, int(bool(advance)), self.stream))
+
+    def _as_action(self, u):
+        if hasattr(u, "data_ptr"):
+            assert u.dtype == self._torch.float32 and u.numel() == self.M * 2
+            return u.contiguous()
+        u = np.ascontiguousarray(u, dtype=np.float32)
+        assert u.size == self.M * 2
+        return u
+
+    def integrate(self, u, want_reward=False):
+        u = self._as_action(u)
+        r = np.empty(self.n_episodes, dtype=np.float64) if want_reward else None
+        self._check(self.lib.fgnn_integrate(self._h, _ptr(u), _ptr(r), self.stream))
+        if isinstance(u, np.ndarray) or want_reward:
+            self.sync()
+        return r
+
+    def env_step(self, u):
+        """env.step(u): integrate + rebuild graph/features; returns the per-episode reward (B,) f64."""
+        u = self._as_action(u)
+        r = np.empty(self.n_episodes, dtype=np.float64)
+        self._check(self.lib.fgnn_env_step(self._h, _ptr(u), _ptr(r), self.stream))
+        self.sync()
+        return r
+
+    # -- learner side -----------------------------------------------------------------------
+    def policy(self, out=None):
+        """select_action: (B*N, 2) fp32.  ``out`` may be a torch CUDA tensor or a (pinned) numpy array;
+        default is a fresh CUDA tensor."""
+        if out is None:
+            out = self._torch.empty((self.M, 2), dtype=self._torch.float32, device=self.device)
+        self._check(self.lib.fgnn_policy(self._h, _ptr(out), self.stream))
+        if isinstance(out, np.ndarray):
+            self.sync()
+        return out
+
+    def step(self, action_out=None, reward_out=None):
+        """One closed-loop step (select_action -> env.step).  Outputs optional, see ``policy``."""
+        self._check(self.lib.fgnn_step(self._h, _ptr(action_out), _ptr(reward_out), self.stream))
+        if isinstance(action_out, np.ndarray) or isinstance(reward_out, np.ndarray):
+            self.sync()
+
+    def rollout(self, steps, want_reward=False):
+        r = np.empty((steps, self.n_episodes), dtype=np.float64) if want_reward else None
+        self._check(self.lib.fgnn_rollout(self._h, int(steps), _ptr(r), self.stream))
+        if want_reward:
+            self.sync()
+        return r
+
+    def actor_forward_dense(self, delay_state, delay_gso):
+        """Actor.forward on dense CUDA tensors: (B,K,F,N), (B,K,N,N) -> (B,1,A,N)."""
+        torch = self._torch
+        ds = delay_state.to(self.device, torch.float32).contiguous()
+        gso = delay_gso.to(self.device, torch.float32).contiguous()
+        B, K, Fdim, N = ds.shape
+        assert K == self.k and Fdim == self.n_states and tuple(gso.shape) == (B, K, N, N)
+        out = torch.empty((B, 1, self.n_actions, N), dtype=torch.float32, device=self.device)
+        self._check(self.lib.fgnn_actor_forward_dense(self._h, B, N, _ptr(ds), _ptr(gso), _ptr(out), self.stream))
+        return out
+
+    # -- read-back --------------------------------------------------------------------------
+    def get_state(self):
+        x = np.empty((self.M, 4), dtype=np.float64)
+        self._check(self.lib.fgnn_get_state(self._h, _ptr(x), self.stream))
+        self.sync()
+        return x
+
+    def get_features(self, age=0):
+        v = np.empty((self.M, 6), dtype=np.float32)
+        self._check(self.lib.fgnn_get_features(self._h, age, _ptr(v), self.stream))
+        self.sync()
+        return v
+
+    def get_degrees(self, age=0):
+        d = np.empty(self.M, dtype=np.int32)
+        self._check(self.lib.fgnn_get_degrees(self._h, age, _ptr(d), self.stream))
+        self.sync()
+        return d
+
+    def get_aggregated(self):
+        z = np.empty((self.k, self.M, 6), dtype=np.float32)
+        self._check(self.lib.fgnn_get_aggregated(self._h, _ptr(z), self.stream))
+        self.sync()
+        return z
+
+    def get_action(self):
+        a = np.empty((self.M, 2), dtype=np.float32)
+        self._check(self.lib.fgnn_get_action(self._h, _ptr(a), self.stream))
+        self.sync()
+        return a
+
+    def network_dense(self, age=0, device=False):
+        """Row-normalised state_network of graph t-age as (B,N,N) fp32 (numpy, or CUDA tensor)."""
+        shape = (self.n_episodes, self.n_agents, self.n_agents)
+        if device:
+            out = self._torch.empty(shape, dtype=self._torch.float32, device=self.device)
+            self._check(self.lib.fgnn_export_network_dense(self._h, age, _ptr(out), self.stream))
+            return out
+        out = np.empty(shape, dtype=np.float32)
+        self._check(self.lib.fgnn_export_network_dense(self._h, age, _ptr(out), self.stream))
+        self.sync()
+        return out
+
+    def csr(self, age=0):
+        """(row_start uint32 (M,), deg int32 (M,), cols int32 (nnz_cap,), scale fp32 (M,)) as numpy copies."""
+        rs, dg, cl, sc = (ctypes.c_void_p() for _ in range(4))
+        self._check(self.lib.fgnn_get_csr(self._h, age, ctypes.byref(rs), ctypes.byref(dg), ctypes.byref(cl),
+                                          ctypes.byref(sc)))
+
+        def fetch(ptr, n, dtype):
+            host = np.empty(n, dtype=dtype)
+            self._check(self.lib.fgnn_memcpy_sync(host.ctypes.data, ptr, host.nbytes, self.stream))
+            return host
+        deg = fetch(dg, self.M, np.int32)
+        row_start = fetch(rs, self.M, np.uint32)
+        n_used = int((row_start.astype(np.int64) + deg).max()) if self.M else 0
+        cols = fetch(cl, max(n_used, 1), np.int32)[:n_used]
+        scale = fetch(sc, self.M, np.float32)
+        return row_start, deg, cols, scale
+
+    def stats(self):
+        s = FgnnStats()
+        self._check(self.lib.fgnn_get_stats(self._h, ctypes.byref(s), self.stream))
+        return {"step": s.step, "n_edges": s.n_edges, "overflow": bool(s.overflow), "grid_dim": s.grid_dim,
+                "n_cells": s.n_cells, "edge_capacity": s.edge_capacity}
+
+    def launch_count(self):
+        return int(self.lib.fgnn_launch_count(self._h))

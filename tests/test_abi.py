@@ -1,0 +1,43 @@
+"""CPU-side checks of the C-ABI boundary: the library loads and exports every symbol include/fgnn.h
+declares; the host wrapper refuses to run without a GPU (no CPU fallback)."""
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+from multiagent_gnn_policies_b200 import engine
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "fgnn.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(fgnn_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_header_and_binding_agree():
+    assert declared_symbols() == sorted(engine.ABI_SYMBOLS)
+
+
+def test_library_exports_every_declared_symbol():
+    if not os.path.exists(engine.LIB_PATH):
+        from multiagent_gnn_policies_b200 import build
+        build.build()
+    lib = engine.load_library()
+    for name in declared_symbols():
+        assert hasattr(lib, name), name
+    assert lib.fgnn_version() >= 100
+
+
+def test_config_struct_layout_matches_header():
+    import ctypes
+    assert ctypes.sizeof(engine.FgnnConfig) == 14 * 4 + 3 * 8
+    assert ctypes.sizeof(engine.FgnnStats) == 8 + 8 + 4 + 4 + 8 + 8
+
+
+def test_engine_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(engine.FgnnError):
+        engine.FlockEngine(n_agents=10)

@@ -1,0 +1,269 @@
+"""Parity of the CUDA path (through the C ABI) against the golden vectors made by the reference's own
+learner code, and against the CPU oracle.  Run on the B200 box: pytest -m gpu."""
+import numpy as np
+import pytest
+
+from conftest import rel_inf, load_golden, golden_names
+from oracle import flock_env, learner, sparse
+
+pytestmark = pytest.mark.gpu
+
+TOL_ACTION = 1e-5       # north_star: actions within 1e-5 relative (inf-norm) fp32
+TOL_FEATURE = 2e-7      # fp32 rounding of a float64-accurate sum
+
+
+def make_engine(g, **kw):
+    from multiagent_gnn_policies_b200.engine import FlockEngine
+    eng = FlockEngine(n_agents=g["n_agents"], k=g["k"], hidden=g["hidden"], n_layers=g["n_layers"],
+                      comm_radius=g["comm_radius"], dt=g["dt"], **kw)
+    eng.load_state_dict(g["state_dict"])
+    return eng
+
+
+@pytest.mark.parametrize("name", golden_names())
+@pytest.mark.parametrize("mode", ["env_step", "teacher_forced"])
+def test_golden_trajectory(name, mode):
+    g = load_golden(name)
+    eng = make_engine(g)
+    eng.reset(g["x"][0])
+    for t in range(g["steps"]):
+        if t > 0:
+            if mode == "env_step":
+                r = eng.env_step(g["action"][t - 1])
+                assert r[0] == pytest.approx(float(g["reward"][t - 1]), rel=1e-9, abs=1e-12)
+                np.testing.assert_array_equal(eng.get_state(), g["x"][t])     # integrator is bit-exact
+            else:
+                eng.set_state(g["x"][t])
+                eng.build_graph(advance=True)
+        assert np.array_equal(eng.get_degrees(), g["deg"][t])                 # adjacency: exact
+        feats = eng.get_features()
+        assert rel_inf(feats, g["values"][t].astype(np.float32)) <= TOL_FEATURE
+        act = eng.policy().cpu().numpy()
+        assert rel_inf(act, g["action"][t]) <= TOL_ACTION
+        z = eng.get_aggregated()                                              # (K, N, 6)
+        assert rel_inf(z.transpose(0, 2, 1), g["z"][t]) <= 2e-6
+    assert not eng.stats()["overflow"]
+    eng.close()
+
+
+@pytest.mark.parametrize("name", ["ckpt_n100_k3", "rand_n100_k4_h64_l2", "rand_n50_k2_h16_l3", "rand_n12_k1_h4_l1"])
+def test_network_export_equals_oracle(name):
+    g = load_golden(name)
+    eng = make_engine(g)
+    eng.reset(g["x"][0])
+    for t in range(min(3, g["steps"])):
+        if t > 0:
+            eng.env_step(g["action"][t - 1])
+        _, sn, _, _ = flock_env.compute_helpers(g["x"][t], g["comm_radius"] ** 2)
+        np.testing.assert_array_equal(eng.network_dense()[0], sn.astype(np.float32))
+    if g["k"] > 1 and g["steps"] > 1:
+        _, sn_prev, _, _ = flock_env.compute_helpers(g["x"][t - 1], g["comm_radius"] ** 2)
+        np.testing.assert_array_equal(eng.network_dense(age=1)[0], sn_prev.astype(np.float32))
+    eng.close()
+
+
+def oracle_closed_loop(g, steps):
+    """Closed-loop rollout of the numpy oracle from g['x'][0]."""
+    layers = learner.weights_from_state_dict(g["state_dict"])
+    x = g["x"][0].copy()
+    R2 = g["comm_radius"] ** 2
+    state, acts, rewards = None, [], []
+    for t in range(steps):
+        sv, sn, _, _ = flock_env.compute_helpers(x, R2)
+        state = learner.DelayState((sv, sn), prev_state=state, k=g["k"])
+        a = learner.select_action(layers, state)
+        acts.append(a)
+        x = flock_env.integrate(x, a, g["dt"])
+        rewards.append(flock_env.instant_cost(x))
+    return np.stack(acts), np.array(rewards), x
+
+
+@pytest.mark.parametrize("name", ["ckpt_n100_k3", "rand_n100_k4_h64_l2", "rand_n64_k3_h128_l4", "rand_n50_k2_h16_l3"])
+def test_closed_loop_step_and_graph_rollout(name):
+    g = load_golden(name)
+    T = 6
+    acts_o, rew_o, x_o = oracle_closed_loop(g, T)
+    # stepwise fused kernel
+    eng = make_engine(g)
+    eng.reset(g["x"][0])
+    acts, rews = [], []
+    for t in range(T):
+        a = np.empty((g["n_agents"], 2), np.float32)
+        r = np.empty(1, np.float64)
+        eng.step(a, r)
+        acts.append(a)
+        rews.append(r[0])
+    acts = np.stack(acts)
+    # free-running rollouts drift apart slowly (fp32 action differences feed back): looser bound
+    assert rel_inf(acts, acts_o) <= 2e-4
+    np.testing.assert_allclose(rews, rew_o, rtol=1e-5)
+    x_step = eng.get_state()
+    # CUDA-graph rollout must reproduce the stepwise path bit for bit
+    eng2 = make_engine(g)
+    eng2.reset(g["x"][0])
+    rew2 = eng2.rollout(T, want_reward=True)
+    np.testing.assert_array_equal(eng2.get_state(), x_step)
+    np.testing.assert_array_equal(eng2.get_action(), acts[-1])
+    np.testing.assert_allclose(rew2[:, 0], rews, rtol=1e-12)
+    # API-split path (policy + env_step) is the same arithmetic as the fused kernel
+    eng3 = make_engine(g)
+    eng3.reset(g["x"][0])
+    for t in range(T):
+        a = eng3.policy().cpu().numpy()
+        np.testing.assert_array_equal(a, acts[t])
+        eng3.env_step(a)
+    np.testing.assert_array_equal(eng3.get_state(), x_step)
+    for e in (eng, eng2, eng3):
+        e.close()
+
+
+def test_run_to_run_reproducible():
+    g = load_golden("ckpt_n400_k3_uniform")
+    outs = []
+    for _ in range(2):
+        eng = make_engine(g)
+        eng.reset(g["x"][0])
+        eng.rollout(12)
+        outs.append((eng.get_state(), eng.get_action(), eng.csr()))
+        eng.close()
+    np.testing.assert_array_equal(outs[0][0], outs[1][0])
+    np.testing.assert_array_equal(outs[0][1], outs[1][1])
+    for a, b in zip(outs[0][2][1:], outs[1][2][1:]):      # deg, cols, scale (row_start may differ)
+        pass
+    rs0, d0, c0, _ = outs[0][2]
+    rs1, d1, c1, _ = outs[1][2]
+    np.testing.assert_array_equal(d0, d1)
+    for a in range(len(d0)):
+        np.testing.assert_array_equal(c0[rs0[a]:rs0[a] + d0[a]], c1[rs1[a]:rs1[a] + d1[a]])
+
+
+def test_batched_episodes_equal_separate_runs():
+    g = load_golden("ckpt_n100_k3")
+    from multiagent_gnn_policies_b200.engine import FlockEngine
+    B, N, T = 5, g["n_agents"], 5
+    rng = np.random.RandomState(0)
+    xs = []
+    for b in range(B):
+        env = flock_env.FlockingRelativeOracle(n_agents=N, rng=rng)
+        xs.append(env.sample_initial_state().copy())
+    xs = np.stack(xs)
+    # offsets in space must not matter, nor may episodes see each other even when they overlap
+    big = FlockEngine(n_agents=N, n_episodes=B, k=3, hidden=32, n_layers=2)
+    big.load_state_dict(g["state_dict"])
+    big.reset(xs.reshape(B * N, 4))
+    rew = big.rollout(T, want_reward=True)
+    xb = big.get_state().reshape(B, N, 4)
+    ab = big.get_action().reshape(B, N, 2)
+    for b in range(B):
+        one = make_engine(g)
+        one.reset(xs[b])
+        r1 = one.rollout(T, want_reward=True)
+        np.testing.assert_array_equal(one.get_state(), xb[b])
+        np.testing.assert_array_equal(one.get_action(), ab[b])
+        np.testing.assert_allclose(r1[:, 0], rew[:, b], rtol=1e-12)
+        one.close()
+    big.close()
+
+
+@pytest.mark.parametrize("n,R,hidden", [(20000, 1.0, 32), (30000, 2.0, 64)])
+def test_large_n_against_sparse_oracle(n, R, hidden):
+    """Sizes the dense reference cannot hold: compare with the edge-list oracle."""
+    import torch
+    from multiagent_gnn_policies_b200.engine import FlockEngine
+    g = load_golden("ckpt_n100_k3")
+    if hidden == 32:
+        sd = g["state_dict"]
+    else:
+        torch.manual_seed(11)
+        sd = {"conv_layers.0.weight": torch.randn(hidden, 6, 3, 1) * 0.2, "conv_layers.0.bias": torch.randn(hidden) * 0.1,
+              "conv_layers.1.weight": torch.randn(hidden, hidden, 1, 1) * 0.1, "conv_layers.1.bias": torch.randn(hidden) * 0.1,
+              "conv_layers.2.weight": torch.randn(2, hidden, 1, 1) * 0.1, "conv_layers.2.bias": torch.randn(2) * 0.1}
+        sd = {k: v.numpy() for k, v in sd.items()}
+    layers = learner.weights_from_state_dict(sd)
+    x = flock_env.synthetic_state(n, seed=n, density=1.6)
+    eng = FlockEngine(n_agents=n, k=3, hidden=hidden, n_layers=2, comm_radius=R, dt=0.01, edge_capacity=64)
+    eng.load_state_dict(sd)
+    eng.reset(x)
+    sstate = None
+    for t in range(4):
+        sv, deg, i, j = sparse.compute_helpers_sparse(x, R)
+        assert np.array_equal(eng.get_degrees(), deg)
+        rs, dg, cols, scale = eng.csr()
+        # identical edge SET per row (row order is the engine's cell order)
+        order = np.argsort(rs, kind="stable")
+        got = np.concatenate([np.sort(cols[rs[a]:rs[a] + dg[a]]) for a in range(n)]) if n <= 50000 else None
+        assert np.array_equal(got, j)
+        assert rel_inf(eng.get_features(), sv.astype(np.float32)) <= TOL_FEATURE
+        a_net = sparse.network_csr(n, deg, i, j)
+        sstate = sparse.SparseDelayState(sv, a_net, prev_state=sstate, k=3)
+        act_o = sparse.readout(layers, sstate.aggregate())
+        act = eng.policy().cpu().numpy()
+        assert rel_inf(act, act_o) <= TOL_ACTION
+        x = flock_env.integrate(x, act_o, 0.01)
+        eng.env_step(act_o)
+        np.testing.assert_array_equal(eng.get_state(), x)
+    assert not eng.stats()["overflow"]
+    eng.close()
+
+
+@pytest.mark.parametrize("name", ["ckpt_n100_k3", "rand_n100_k4_h64_l2", "rand_n64_k3_h128_l4", "rand_n12_k1_h4_l1"])
+def test_dense_actor_forward_matches_reference(name):
+    """Actor.forward(delay_state, delay_gso) on dense tensors, batch of consecutive states."""
+    import torch
+    g = load_golden(name)
+    eng = make_engine(g)
+    R2 = g["comm_radius"] ** 2
+    state, ds, gso = None, [], []
+    for t in range(g["steps"]):
+        sv, sn, _, _ = flock_env.compute_helpers(g["x"][t], R2)
+        state = learner.DelayState((sv, sn), prev_state=state, k=g["k"])
+        ds.append(state.delay_state[0])
+        gso.append(state.delay_gso[0])
+    ds = torch.from_numpy(np.stack(ds)).cuda()
+    gso = torch.from_numpy(np.stack(gso)).cuda()
+    out = eng.actor_forward_dense(ds, gso).cpu().numpy()          # (B,1,2,N)
+    assert out.shape == (g["steps"], 1, 2, g["n_agents"])
+    ref = g["action"].transpose(0, 2, 1)[:, None]                 # (T,1,2,N)
+    assert rel_inf(out, ref) <= TOL_ACTION
+    eng.close()
+
+
+def test_edge_cases():
+    from multiagent_gnn_policies_b200.engine import FlockEngine, FgnnError
+    g = load_golden("ckpt_n100_k3")
+    layers = learner.weights_from_state_dict(g["state_dict"])
+    # a single agent, and agents that never see each other: empty graph, action = MLP(0-features)
+    for n, spread in ((1, 1.0), (7, 50.0)):
+        eng = FlockEngine(n_agents=n, k=3, hidden=32, n_layers=2)
+        eng.load_state_dict(g["state_dict"])
+        x = np.zeros((n, 4))
+        x[:, 0] = np.arange(n) * spread
+        x[:, 2] = 1.0
+        eng.reset(x)
+        assert eng.get_degrees().sum() == 0 and eng.stats()["n_edges"] == 0
+        a = eng.policy().cpu().numpy()
+        exp = sparse.readout(layers, np.zeros((3, n, 6), np.float32))
+        assert rel_inf(a, exp) <= TOL_ACTION
+        r = eng.env_step(a)
+        assert r[0] == pytest.approx(flock_env.instant_cost(flock_env.integrate(x, a, 0.01)), abs=1e-12)
+        eng.close()
+    # negative coordinates / wrapped cell grid / N not a multiple of any block size
+    n = 333
+    x = flock_env.synthetic_state(n, seed=2, density=1.6)
+    x[:, 0:2] -= 1000.25
+    eng = FlockEngine(n_agents=n, k=3, hidden=32, n_layers=2, grid_dim=3)
+    eng.load_state_dict(g["state_dict"])
+    eng.reset(x)
+    sv, sn, adj, deg = flock_env.compute_helpers(x, 1.0)
+    assert np.array_equal(eng.get_degrees(), deg)
+    np.testing.assert_array_equal(eng.network_dense()[0], sn.astype(np.float32))
+    eng.close()
+    # edge capacity exceeded -> sticky overflow flag, no crash
+    eng = FlockEngine(n_agents=2000, k=3, hidden=32, n_layers=2, comm_radius=4.0, edge_capacity=1)
+    eng.load_state_dict(g["state_dict"])
+    eng.reset(flock_env.synthetic_state(2000, seed=4, density=1.6))
+    assert eng.stats()["overflow"]
+    eng.close()
+    # bad configuration is rejected with a message
+    with pytest.raises(FgnnError):
+        FlockEngine(n_agents=10, k=9)
