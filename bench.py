@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""Benchmark of the flocking-GNN rollout hot path (BASELINE.json metric: agent-steps/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one closed-loop rollout step over every agent: radius adjacency + 6-d features ->
+K-hop aggregation -> MLP readout -> double-integrator update.
+Workload (config.workload): N agents PER GPU, K=3, uniform density 1.6 agents/unit^2 (mean degree ~5
+at comm_radius 1), cell-major agent order, shipped-checkpoint-shaped actor (H=32, L=2), fp32 learner
+arithmetic / fp64 environment arithmetic, synthetic data, random-init or shipped weights.
+
+Prints ONE JSON line (rank 0).  `value` = device-resident throughput (CUDA-graph rollout);
+`e2e` = the same metric through the reference-facing calls with HOST buffers every step
+(select_action -> host, env.step(action from host)); `roofline` = dominant kernel vs measured HBM
+peak; `cpu_baseline` = the reference algorithm (dense numpy/oracle port) timed on this box's cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "agent-steps/sec"
+UNIT = "agent-steps/s"
+DENSITY = 1.6
+FALLBACK_HBM_GBS = 6650.0      # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def make_workload(n_agents, seed=11, density=DENSITY, v_max=3.0, min_dist=0.1, x_offset=0.0):
+    """SURVEY.md 8(d) synthetic state: uniform square of side sqrt(N/density), cell-major order,
+    no pair closer than min_dist (gym_flock's reset threshold)."""
+    from scipy.spatial import cKDTree
+    rng = np.random.default_rng(seed)
+    side = np.sqrt(n_agents / density)
+    x = np.empty((n_agents, 4))
+    x[:, 0:2] = rng.uniform(0.0, side, size=(n_agents, 2))
+    for _ in range(200):
+        pairs = cKDTree(x[:, 0:2]).query_pairs(min_dist, output_type="ndarray")
+        if pairs.size == 0:
+            break
+        bad = np.unique(pairs[:, 1])
+        x[bad, 0:2] = rng.uniform(0.0, side, size=(bad.size, 2))
+    bias = rng.uniform(-v_max, v_max, size=(2,))
+    x[:, 2:4] = rng.uniform(-v_max, v_max, size=(n_agents, 2)) + bias
+    order = np.lexsort((np.floor(x[:, 0]).astype(np.int64), np.floor(x[:, 1]).astype(np.int64)))
+    x = x[order]
+    x[:, 0] += x_offset
+    return np.ascontiguousarray(x)
+
+
+def make_weights(hidden, k, n_layers, seed=11):
+    """Shipped checkpoint shape when available in the golden fixtures (H=32,K=3,L=2), else random init of the
+    reference architecture (nn.Conv2d default init, torch.manual_seed(seed))."""
+    if hidden == 32 and k == 3 and n_layers == 2:
+        path = os.path.join(ROOT, "tests", "golden", "ckpt_n100_k3.npz")
+        if os.path.exists(path):
+            g = np.load(path)
+            return {key[3:]: g[key] for key in g.files if key.startswith("sd.")}, "shipped checkpoint (via tests/golden)"
+    import torch
+    torch.manual_seed(seed)
+    dims = [6] + [hidden] * n_layers + [2]
+    sd = {}
+    for i in range(len(dims) - 1):
+        conv = torch.nn.Conv2d(dims[i], dims[i + 1], (k if i == 0 else 1, 1))
+        sd[f"conv_layers.{i}.weight"] = conv.weight.detach().numpy()
+        sd[f"conv_layers.{i}.bias"] = conv.bias.detach().numpy()
+    return sd, "random init"
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason sampling during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [q.strip() for q in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference ALGORITHM (dense N x N GSO products + dense all-pairs
+# env) restated in numpy (oracle/), timed on the host cores over a bounded sample of the workload.
+# ---------------------------------------------------------------------------------------------
+def run_cpu_reference(n_sample, steps, warmup, hidden, k, n_layers, seed=11):
+    from oracle import flock_env, learner
+    sd, _ = make_weights(hidden, k, n_layers)
+    layers = learner.weights_from_state_dict(sd)
+    x = make_workload(n_sample, seed=seed)
+    state = None
+    R2 = 1.0
+
+    def one_step(x, state):
+        sv, sn, _, _ = flock_env.compute_helpers(x, R2)
+        state = learner.DelayState((sv, sn), prev_state=state, k=k, with_curr_gso=True)   # reference builds curr_gso too
+        a = learner.select_action(layers, state)
+        return flock_env.integrate(x, a, 0.01), state
+
+    for _ in range(warmup):
+        x, state = one_step(x, state)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        x, state = one_step(x, state)
+    dt = time.perf_counter() - t0
+    try:
+        from threadpoolctl import threadpool_info
+        cores = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+    except Exception:
+        cores = os.cpu_count() or 1
+    return {"value": n_sample * steps / dt, "unit": UNIT, "cores": int(cores), "kind": "port",
+            "sample": f"dense oracle port of the reference algorithm (all-pairs float64 env + dense NxN GSO products, "
+                      f"numpy), N={n_sample} of the same density, {steps} steps after {warmup} warm-up; "
+                      f"{dt / steps * 1e3:.1f} ms/step; host has {os.cpu_count()} cpus"}, dt / steps
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n-agents", type=int, default=1_000_000, help="agents per GPU")
+    ap.add_argument("--hidden", type=int, default=32)
+    ap.add_argument("--k", type=int, default=3)
+    ap.add_argument("--n-layers", type=int, default=2)
+    ap.add_argument("--radius", type=float, default=1.0)
+    ap.add_argument("--cpu-sample", type=int, default=1500, help="N of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer e2e loop (default: min(steps, 50))")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    workload = (f"FlockingRelative closed-loop rollout, N={args.n_agents} agents per GPU, K={args.k}, H={args.hidden}, "
+                f"L={args.n_layers}, R={args.radius}, density {DENSITY}/unit^2, dt=0.01, cell-major order")
+    config = {"workload": workload, "n_agents_per_gpu": args.n_agents, "k": args.k, "hidden": args.hidden,
+              "n_layers": args.n_layers, "comm_radius": args.radius,
+              "l2_policy": "working set per step (~0.5 GB at N=1M) exceeds the 126 MB L2; no explicit flush"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps = max(1, min(args.steps, 5))
+        warm = max(1, min(args.warmup, 2))
+        cb, sec = run_cpu_reference(args.cpu_sample, steps, warm, args.hidden, args.k, args.n_layers)
+        line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+                "steps": steps, "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32 learner / f64 env", "data": "synthetic", "config": config,
+                "cpu_baseline": cb, "gpu_launches": 0,
+                "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from multiagent_gnn_policies_b200.engine import FlockEngine
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    N = args.n_agents
+    side = np.sqrt(N / DENSITY)
+    x0 = make_workload(N, seed=11 + rank, x_offset=rank * side)
+    sd, weights_note = make_weights(args.hidden, args.k, args.n_layers)
+    cap = int(max(24, 3.2 * np.pi * args.radius ** 2 * DENSITY + 16))
+    eng = FlockEngine(n_agents=N, k=args.k, hidden=args.hidden, n_layers=args.n_layers, comm_radius=args.radius,
+                      dt=0.01, device=local_rank, edge_capacity=cap)
+    eng.load_state_dict(sd)
+    eng.reset(x0)
+    st0 = eng.stats()
+    deg_start = st0["n_edges"] / N
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput: CUDA-graph rollout ------------------------------------
+    eng.rollout(args.warmup)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = eng.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    eng.rollout(args.steps)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = eng.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        tms = torch.tensor([ms], device="cuda")
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+    st1 = eng.stats()
+    deg_end = st1["n_edges"] / N
+    if st1["overflow"]:
+        raise RuntimeError("edge capacity overflow during the timed region: results void")
+    value = world * N * args.steps / (ms * 1e-3)
+
+    # ---- per-kernel device times (CUDA events between launches), for the roofline ----------
+    prof = {}
+    nprof = 10
+    for _ in range(nprof):
+        for name, kms in eng.profile_step():
+            prof[name] = prof.get(name, 0.0) + kms / nprof
+    deg_prof = eng.stats()["n_edges"] / N
+
+    # ---- e2e: reference-facing calls with HOST buffers every step ---------------------------
+    e2e_steps = args.e2e_steps or min(args.steps, 50)
+    act_host = torch.empty((N, 2), dtype=torch.float32, pin_memory=True)
+    rew_host = torch.empty((1,), dtype=torch.float64, pin_memory=True)
+    act_np, rew_np = act_host.numpy(), rew_host.numpy()
+    lib, h, stream = eng.lib, eng._h, eng.stream
+    for _ in range(3):
+        eng.policy(out=act_np)
+        lib.fgnn_env_step(h, act_np.ctypes.data, rew_np.ctypes.data, stream)
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(e2e_steps):
+        eng.policy(out=act_np)                       # select_action(state) -> host action (D2H, sync)
+        rc = lib.fgnn_env_step(h, act_np.ctypes.data, rew_np.ctypes.data, stream)    # env.step(host action) (H2D) -> reward (D2H)
+        assert rc == 0
+        torch.cuda.current_stream().synchronize()    # the caller reads the reward
+    t1.record()
+    barrier()
+    e2e_ms = t0.elapsed_time(t1)
+    if world > 1:
+        tms = torch.tensor([e2e_ms], device="cuda")
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        e2e_ms = float(tms.item())
+    e2e_value = world * N * e2e_steps / (e2e_ms * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ---------------------------------------------------
+    peak, peak_src = measured_peaks()
+    # SURVEY.md 8(d) algorithmic bytes per agent per launch (K=3; fp32 values, int32 CSR, 16 B state)
+    d = deg_prof
+    alg_bytes = {"adjacency": 44 + 4 * d, "hop0": 104 + 4 * d, "final": 120 + 4 * d}
+    dom = max(prof, key=prof.get)
+    step_ms_prof = sum(prof.values())
+    roof = {"bound": "hbm", "kernel": dom, "unit": "GB/s", "peak": peak, "peak_source": peak_src, "traffic": None,
+            "kernel_ms": prof[dom], "kernel_share_of_step": prof[dom] / step_ms_prof,
+            "per_kernel_ms": {k_: round(v, 5) for k_, v in prof.items()}}
+    if dom in alg_bytes and args.k == 3:
+        ach = alg_bytes[dom] * N / (prof[dom] * 1e-3) / 1e9
+        roof.update({"achieved": ach, "frac": ach / peak, "algorithmic_bytes_per_agent": alg_bytes[dom]})
+    else:
+        roof.update({"achieved": None, "frac": None})
+    step_bytes = 268 + 12 * d
+    roof["whole_step"] = {"algorithmic_bytes_per_agent_step": step_bytes,
+                          "achieved": step_bytes * value / world / 1e9, "frac": step_bytes * value / world / 1e9 / peak}
+
+    cb = None
+    if not args.no_cpu_baseline:
+        cb, _ = run_cpu_reference(args.cpu_sample, 3, 1, args.hidden, args.k, args.n_layers)
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 learner / f64 env", "data": f"synthetic ({weights_note})", "config": config,
+            "mean_degree": {"start": deg_start, "end": deg_end},
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": e2e_value, "unit": UNIT, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
+                    "h2d_bytes_per_step": int(N * 2 * 4), "d2h_bytes_per_step": int(N * 2 * 4 + 8)},
+            "roofline": roof, "cpu_baseline": cb}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

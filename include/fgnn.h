@@ -116,6 +116,11 @@ int fgnn_get_csr(fgnn_handle* h, int32_t age, const uint32_t** row_start, const 
                  const int32_t** cols, const float** src_scale);
 int fgnn_get_stats(fgnn_handle* h, fgnn_stats* out, void* stream);   /* synchronises the stream */
 
+/* One closed-loop step (same work as fgnn_step) with a CUDA event after every kernel: ms_out[i] is the
+ * device time of kernel i, names_out (16 bytes each, may be NULL) its name.  For bench.py's roofline. */
+int fgnn_profile_step(fgnn_handle* h, int32_t max_kernels, float* ms_out, char* names_out, int32_t* n_out,
+                      void* stream);
+
 /* Stream-ordered copy between any two host/device buffers (cudaMemcpyDefault) + stream sync; lets a
  * ctypes host read the device arrays fgnn_get_csr points at without binding the CUDA runtime. */
 int fgnn_memcpy_sync(void* dst, const void* src, uint64_t bytes, void* stream);

@@ -48,6 +48,11 @@ struct fgnn_handle {
     int graph_kernels = 0;
     int final_grid_closed = 0, final_grid_open = 0;
     size_t final_smem = 0;
+    // per-kernel profiling of one step (fgnn_profile_step)
+    bool profiling = false;
+    cudaStream_t prof_stream = nullptr;
+    std::vector<cudaEvent_t> prof_events;
+    std::vector<std::string> prof_names;
 };
 
 template <typename T>
@@ -241,9 +246,16 @@ extern "C" int fgnn_set_weights(fgnn_handle* h, int32_t layer, const float* W, c
     return 0;
 }
 
-static int launch_check(fgnn_handle* h, int n = 1) {
-    h->launches += n;
+static int launch_check(fgnn_handle* h, const char* name) {
+    h->launches += 1;
     CK(cudaGetLastError());
+    if (h->profiling) {
+        cudaEvent_t e;
+        CK(cudaEventCreate(&e));
+        CK(cudaEventRecord(e, h->prof_stream));
+        h->prof_events.push_back(e);
+        h->prof_names.push_back(name);
+    }
     return 0;
 }
 
@@ -253,13 +265,16 @@ static int enqueue_build(fgnn_handle* h, int advance, cudaStream_t st) {
     const int gb = blocks_for(p.M, 256);
     if (!h->binned) {
         k_bin<<<gb, 256, 0, st>>>(p);
-        if (launch_check(h)) return 1;
+        if (launch_check(h, "bin")) return 1;
     }
     k_scan<<<p.n_tiles, SCAN_THREADS, 0, st>>>(p, advance);
+    if (launch_check(h, "scan")) return 1;
     k_scatter<<<gb, 256, 0, st>>>(p);
+    if (launch_check(h, "scatter")) return 1;
     k_canon<<<gb, 256, 0, st>>>(p);
+    if (launch_check(h, "canon")) return 1;
     k_adjacency<<<gb, 256, 0, st>>>(p);
-    if (launch_check(h, 4)) return 1;
+    if (launch_check(h, "adjacency")) return 1;
     h->binned = false;
     if (advance) h->t_host += 1;
     return 0;
@@ -273,7 +288,7 @@ static int enqueue_hops(fgnn_handle* h, cudaStream_t st) {
         if (nb == 3) k_hop<3><<<gb, 256, 0, st>>>(p, j);
         else if (nb == 2) k_hop<2><<<gb, 256, 0, st>>>(p, j);
         else k_hop<1><<<gb, 256, 0, st>>>(p, j);
-        if (launch_check(h)) return 1;
+        if (launch_check(h, j == 0 ? "hop0" : "hop1")) return 1;
     }
     return 0;
 }
@@ -284,7 +299,7 @@ static int enqueue_final(fgnn_handle* h, bool closed, int write_z, cudaStream_t 
     final_kernel_t fk = final_kernel(p.K, h->HP, closed);
     const int grid = closed ? h->final_grid_closed : h->final_grid_open;
     fk<<<grid, FINAL_THREADS, h->final_smem, st>>>(p);
-    if (launch_check(h)) return 1;
+    if (launch_check(h, "final")) return 1;
     if (closed) h->binned = true;
     return 0;
 }
@@ -353,11 +368,11 @@ extern "C" int fgnn_integrate(fgnn_handle* h, const float* u, double* reward_b, 
     }
     CK(cudaMemcpyAsync(h->d_u_in, u, (size_t)p.M * 2 * sizeof(float), cudaMemcpyDefault, st));
     k_integrate<<<blocks_for(p.M, 256), 256, 0, st>>>(p, h->d_u_in);
-    if (launch_check(h)) return 1;
+    if (launch_check(h, "integrate")) return 1;
     h->binned = true;
     if (reward_b) {
         k_finalize_reward<<<1, 256, 0, st>>>(p);
-        if (launch_check(h)) return 1;
+        if (launch_check(h, "finalize_reward")) return 1;
         return copy_out(reward_b, p.reward, (size_t)p.B * sizeof(double), st);
     }
     return 0;
@@ -452,7 +467,7 @@ extern "C" int fgnn_actor_forward_dense(fgnn_handle* h, int32_t batch, int32_t n
     CK(cudaFuncSetAttribute((const void*)dk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(blocks_for(n2, FINAL_THREADS), batch);
     dk<<<grid, FINAL_THREADS, smem, st>>>(ds, gso, out, h->d_weights, h->cfg.n_layers, n2);
-    return launch_check(h);
+    return launch_check(h, "actor_dense");
 }
 
 // ---- read-back ----------------------------------------------------------------------------
@@ -476,7 +491,7 @@ extern "C" int fgnn_get_features(fgnn_handle* h, int32_t age, float* out, void* 
     if (age_slot(h, age, &g)) return 1;
     const int M = h->p.M;
     k_pack_rows<<<blocks_for(M * F, 256), 256, 0, st>>>(h->p.xhist + (size_t)g * M * ROW, h->d_staging, M);
-    if (launch_check(h)) return 1;
+    if (launch_check(h, "pack_rows")) return 1;
     return copy_out(out, h->d_staging, (size_t)M * F * sizeof(float), st);
 }
 
@@ -497,7 +512,7 @@ extern "C" int fgnn_get_aggregated(fgnn_handle* h, float* out, void* stream) {
         const float* rows = k == 0 ? h->p.xhist + (size_t)slot_of((int)h->t_host, K) * M * ROW
                                    : h->p.zbuf + (size_t)k * M * ROW;
         k_pack_rows<<<blocks_for(M * F, 256), 256, 0, st>>>(rows, h->d_staging + (size_t)k * M * F, M);
-        if (launch_check(h)) return 1;
+        if (launch_check(h, "pack_rows")) return 1;
     }
     return copy_out(out, h->d_staging, (size_t)K * M * F * sizeof(float), st);
 }
@@ -522,7 +537,7 @@ extern "C" int fgnn_export_network_dense(fgnn_handle* h, int32_t age, float* out
     if (!on_device) CK(cudaMallocAsync((void**)&d_out, n * sizeof(float), st));
     CK(cudaMemsetAsync(d_out, 0, n * sizeof(float), st));
     k_export_dense<<<blocks_for(h->p.M, 256), 256, 0, st>>>(h->p, g, d_out);
-    if (launch_check(h)) return 1;
+    if (launch_check(h, "export_dense")) return 1;
     if (!on_device) {
         CK(cudaMemcpyAsync(out, d_out, n * sizeof(float), cudaMemcpyDeviceToHost, st));
         CK(cudaFreeAsync(d_out, st));
@@ -559,6 +574,44 @@ extern "C" int fgnn_get_stats(fgnn_handle* h, fgnn_stats* out, void* stream) {
     out->grid_dim = h->p.G;
     out->n_cells = h->p.C;
     out->edge_capacity = h->p.nnz_cap;
+    return 0;
+}
+
+extern "C" int fgnn_profile_step(fgnn_handle* h, int32_t max_kernels, float* ms_out, char* names_out, int32_t* n_out,
+                                 void* stream) {
+    if (!h || !ms_out || !n_out) return fail("fgnn_profile_step: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(h->cfg.device));
+    if (h->binned) return fail("fgnn_profile_step: state was integrated but the graph not rebuilt");
+    h->prof_events.clear();
+    h->prof_names.clear();
+    cudaEvent_t e0;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventRecord(e0, st));
+    h->profiling = true;
+    h->prof_stream = st;
+    int rc = enqueue_closed_step(h, st);
+    h->profiling = false;
+    if (rc) return 1;
+    CK(cudaStreamSynchronize(st));
+    const int n = (int)h->prof_events.size();
+    *n_out = n < max_kernels ? n : max_kernels;
+    cudaEvent_t prev = e0;
+    for (int i = 0; i < n; ++i) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, prev, h->prof_events[i]));
+        if (i < max_kernels) {
+            ms_out[i] = ms;
+            if (names_out) {
+                strncpy(names_out + 16 * i, h->prof_names[i].c_str(), 15);
+                names_out[16 * i + 15] = 0;
+            }
+        }
+        prev = h->prof_events[i];
+    }
+    CK(cudaEventDestroy(e0));
+    for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
+    h->prof_events.clear();
     return 0;
 }
 

@@ -17,7 +17,7 @@ ABI_SYMBOLS = [
     "fgnn_set_state", "fgnn_build_graph", "fgnn_integrate", "fgnn_env_step", "fgnn_policy", "fgnn_step",
     "fgnn_rollout", "fgnn_actor_forward_dense", "fgnn_get_state", "fgnn_get_features", "fgnn_get_degrees",
     "fgnn_get_aggregated", "fgnn_get_action", "fgnn_export_network_dense", "fgnn_get_csr", "fgnn_get_stats",
-    "fgnn_memcpy_sync", "fgnn_launch_count",
+    "fgnn_profile_step", "fgnn_memcpy_sync", "fgnn_launch_count",
 ]
 
 
@@ -80,6 +80,7 @@ def load_library(path=None):
     lib.fgnn_export_network_dense.argtypes = [vp, i32, vp, vp]
     lib.fgnn_get_csr.argtypes = [vp, i32, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp)]
     lib.fgnn_get_stats.argtypes = [vp, ctypes.POINTER(FgnnStats), vp]
+    lib.fgnn_profile_step.argtypes = [vp, i32, vp, vp, ctypes.POINTER(i32), vp]
     lib.fgnn_memcpy_sync.argtypes = [vp, vp, ctypes.c_uint64, vp]
     lib.fgnn_launch_count.argtypes = [vp]
     lib.fgnn_launch_count.restype = i64
@@ -324,6 +325,15 @@ class FlockEngine:
         self._check(self.lib.fgnn_get_stats(self._h, ctypes.byref(s), self.stream))
         return {"step": s.step, "n_edges": s.n_edges, "overflow": bool(s.overflow), "grid_dim": s.grid_dim,
                 "n_cells": s.n_cells, "edge_capacity": s.edge_capacity}
+
+    def profile_step(self):
+        """One closed-loop step with per-kernel CUDA-event timing: [(kernel name, ms), ...]."""
+        ms = (ctypes.c_float * 16)()
+        names = ctypes.create_string_buffer(16 * 16)
+        n = ctypes.c_int32(0)
+        self._check(self.lib.fgnn_profile_step(self._h, 16, ctypes.addressof(ms), ctypes.addressof(names),
+                                               ctypes.byref(n), self.stream))
+        return [(names.raw[16 * i:16 * i + 16].split(b"\0")[0].decode(), float(ms[i])) for i in range(n.value)]
 
     def launch_count(self):
         return int(self.lib.fgnn_launch_count(self._h))

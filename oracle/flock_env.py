@@ -166,13 +166,27 @@ class FlockingRelativeOracle:
                           self.max_accel, self.action_scalar)
 
 
-def synthetic_state(n_agents, seed=11, density=1.6, v_max=3.0, sort_cells=True, cell=1.0, dtype=np.float64):
+def synthetic_state(n_agents, seed=11, density=1.6, v_max=3.0, sort_cells=True, cell=1.0, min_dist=0.1,
+                    dtype=np.float64):
     """Benchmark workload of SURVEY.md section 8(d): uniform positions in a square of side
-    sqrt(N/density), velocities U(-v_max,v_max)+bias, optionally in cell-major order."""
+    sqrt(N/density), velocities U(-v_max,v_max)+bias, optionally in cell-major order.
+    Like gym_flock's reset (min_dist_thresh = 0.1) no two agents start closer than ``min_dist``:
+    offending points are re-drawn (near-coincident pairs make dp/r^4 ~ 1e9 and the fp32 readout
+    ill-conditioned for every implementation)."""
     rng = np.random.default_rng(seed)
     side = np.sqrt(n_agents / density)
-    x = np.empty((n_agents, NX), dtype=dtype)
+    x = np.empty((n_agents, NX), dtype=np.float64)
     x[:, 0:2] = rng.uniform(0.0, side, size=(n_agents, 2))
+    if min_dist > 0 and n_agents > 1:
+        from scipy.spatial import cKDTree
+        for _ in range(200):
+            pairs = cKDTree(x[:, 0:2]).query_pairs(min_dist, output_type='ndarray')
+            if pairs.size == 0:
+                break
+            bad = np.unique(pairs[:, 1])
+            x[bad, 0:2] = rng.uniform(0.0, side, size=(bad.size, 2))
+        else:
+            raise RuntimeError("could not separate agents by min_dist")
     bias = rng.uniform(-v_max, v_max, size=(2,))
     x[:, 2:4] = rng.uniform(-v_max, v_max, size=(n_agents, 2)) + bias
     if sort_cells:
@@ -180,4 +194,4 @@ def synthetic_state(n_agents, seed=11, density=1.6, v_max=3.0, sort_cells=True, 
         cy = np.floor(x[:, 1] / cell).astype(np.int64)
         order = np.lexsort((cx, cy))
         x = x[order]
-    return x
+    return x.astype(dtype)
