@@ -47,6 +47,23 @@ def compute_helpers_sparse(x, comm_radius):
     return sv, deg, i, j
 
 
+def controller_sparse(x, comm_radius, max_accel=1.0, action_scalar=10.0):
+    """Decentralised expert controller (flock_env.controller with centralized=False) on the edge list."""
+    n = x.shape[0]
+    i, j = radius_edges(x, comm_radius)
+    d = x[i] - x[j]
+    r2 = np.multiply(d[:, 0], d[:, 0]) + np.multiply(d[:, 1], d[:, 1])
+    gx = -2.0 * d[:, 0] / (r2 * r2) + 2.0 * d[:, 0] / r2
+    gy = -2.0 * d[:, 1] / (r2 * r2) + 2.0 * d[:, 1] / r2
+    far = r2 > comm_radius
+    gx[far] = 0.0
+    gy[far] = 0.0
+    ux = -np.bincount(i, weights=gx + d[:, 2], minlength=n)
+    uy = -np.bincount(i, weights=gy + d[:, 3], minlength=n)
+    lim = max_accel * action_scalar
+    return np.clip(np.stack((ux, uy), axis=1), -lim, lim) / action_scalar
+
+
 def network_csr(n, deg, i, j, mean_pooling=True):
     """state_network as an fp32 scipy CSR: A[i,j] = 1/max(deg_i,1) (row-normalised) or 1."""
     if mean_pooling:

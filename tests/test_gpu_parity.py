@@ -190,8 +190,7 @@ def test_large_n_against_sparse_oracle(n, R, hidden):
         assert np.array_equal(eng.get_degrees(), deg)
         rs, dg, cols, scale = eng.csr()
         # identical edge SET per row (row order is the engine's cell order)
-        order = np.argsort(rs, kind="stable")
-        got = np.concatenate([np.sort(cols[rs[a]:rs[a] + dg[a]]) for a in range(n)]) if n <= 50000 else None
+        got = np.concatenate([np.sort(cols[rs[a]:rs[a] + dg[a]]) for a in range(n)])
         assert np.array_equal(got, j)
         assert rel_inf(eng.get_features(), sv.astype(np.float32)) <= TOL_FEATURE
         a_net = sparse.network_csr(n, deg, i, j)
@@ -199,8 +198,13 @@ def test_large_n_against_sparse_oracle(n, R, hidden):
         act_o = sparse.readout(layers, sstate.aggregate())
         act = eng.policy().cpu().numpy()
         assert rel_inf(act, act_o) <= TOL_ACTION
-        x = flock_env.integrate(x, act_o, 0.01)
-        eng.env_step(act_o)
+        z = eng.get_aggregated()
+        assert rel_inf(z, sstate.aggregate()) <= 1e-6
+        # drive the env with the expert (DAGGER with beta = 1): keeps agents apart, so |features| stay
+        # O(1e3) and the fp32 readout stays well conditioned (a random policy makes agents collide)
+        u = sparse.controller_sparse(x, R).astype(np.float32)
+        x = flock_env.integrate(x, u, 0.01)
+        eng.env_step(u)
         np.testing.assert_array_equal(eng.get_state(), x)
     assert not eng.stats()["overflow"]
     eng.close()

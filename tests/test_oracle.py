@@ -66,6 +66,14 @@ def test_sparse_oracle_equals_dense(n, R):
     np.testing.assert_array_equal(a, sn.astype(np.float32))
 
 
+def test_sparse_controller_equals_dense():
+    x = flock_env.synthetic_state(200, seed=9, density=1.6)
+    for R in (1.0, 1.7):
+        u_d = flock_env.controller(x, R, R * R, centralized=False)
+        u_s = sparse.controller_sparse(x, R)
+        np.testing.assert_allclose(u_s, u_d, rtol=1e-10, atol=1e-12)
+
+
 def test_sparse_delay_state_equals_dense_path():
     g = load_golden("rand_n100_k4_h64_l2")
     layers = learner.weights_from_state_dict(g["state_dict"])
