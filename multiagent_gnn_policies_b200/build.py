@@ -35,12 +35,13 @@ def _units():
     """(object path, source, extra flags, dependency list)"""
     common_deps = [os.path.join(CSRC, "fgnn_kernels.cuh")]
     units = [(os.path.join(OBJ, "fgnn.o"), os.path.join(CSRC, "fgnn.cu"), [],
-              common_deps + [os.path.join(INCLUDE, "fgnn.h")])]
+              common_deps + [os.path.join(INCLUDE, "fgnn.h"), os.path.join(CSRC, "fgnn_final.cuh"),
+                             os.path.join(CSRC, "fgnn_final_tc.cuh")])]
     for k in KS:
         for hp in HPS:
             units.append((os.path.join(OBJ, f"fgnn_final_k{k}_hp{hp}.o"), os.path.join(CSRC, "fgnn_final.cu"),
                           [f"-DFGNN_K={k}", f"-DFGNN_HP={hp}"],
-                          common_deps + [os.path.join(CSRC, "fgnn_final.cuh")]))
+                          common_deps + [os.path.join(CSRC, "fgnn_final.cuh"), os.path.join(CSRC, "fgnn_final_tc.cuh")]))
     return units
 
 

@@ -1,6 +1,7 @@
 // fgnn.cu -- host side of libfgnn.so: handle, memory, launches, CUDA-graph rollout, C ABI (include/fgnn.h).
 #define FGNN_MAIN_TU 1
 #include "fgnn_kernels.cuh"
+#include "fgnn_final_tc.cuh"
 #include "../../include/fgnn.h"
 
 #include <cmath>
@@ -48,6 +49,14 @@ struct fgnn_handle {
     int graph_kernels = 0;
     int final_grid_closed = 0, final_grid_open = 0;
     size_t final_smem = 0;
+    int adj_stage = 16;              // neighbour ids staged per thread in k_adjacency
+    // tensor-core readout (tcgen05, 3xTF32)
+    bool use_tc = false;
+    std::vector<uint8_t> tc_host;    // TcLayout pack, host mirror
+    uint8_t* d_tc_weights = nullptr;
+    size_t tc_smem = 0;
+    int tc_grid_closed = 0, tc_grid_open = 0;
+    std::vector<std::vector<float>> raw_w, raw_b;   // per layer, reference layout
     // per-kernel profiling of one step (fgnn_profile_step)
     bool profiling = false;
     cudaStream_t prof_stream = nullptr;
@@ -74,12 +83,15 @@ typedef void (*final_kernel_t)(Params);
 typedef void (*dense_kernel_t)(const float*, const float*, float*, const float*, int, int);
 
 namespace fgnn {
-#define FGNN_DECL(K, HP) final_kernel_t get_final_k##K##_hp##HP(bool closed); dense_kernel_t get_dense_k##K##_hp##HP();
+typedef void (*final_tc_kernel_t)(Params, const uint8_t*);
+#define FGNN_DECL(K, HP) final_kernel_t get_final_k##K##_hp##HP(bool closed); dense_kernel_t get_dense_k##K##_hp##HP(); \
+    final_tc_kernel_t get_final_tc_k##K##_hp##HP(bool closed);
 #define FGNN_DECL_K(K) FGNN_DECL(K, 16) FGNN_DECL(K, 32) FGNN_DECL(K, 64) FGNN_DECL(K, 128)
 FGNN_DECL_K(1) FGNN_DECL_K(2) FGNN_DECL_K(3) FGNN_DECL_K(4)
 }
 
-#define FGNN_CASE_HP(K, HP) case HP: return closed_or_dense == 2 ? (void*)get_dense_k##K##_hp##HP() : (void*)get_final_k##K##_hp##HP(closed_or_dense == 1);
+#define FGNN_CASE_HP(K, HP) case HP: return closed_or_dense == 2 ? (void*)get_dense_k##K##_hp##HP() \
+    : closed_or_dense >= 3 ? (void*)get_final_tc_k##K##_hp##HP(closed_or_dense == 4) : (void*)get_final_k##K##_hp##HP(closed_or_dense == 1);
 #define FGNN_CASE_K(K) case K: switch (HP) { FGNN_CASE_HP(K, 16) FGNN_CASE_HP(K, 32) FGNN_CASE_HP(K, 64) default: FGNN_CASE_HP(K, 128) } break;
 static void* kernel_lookup(int K, int HP, int closed_or_dense) {
     switch (K) { FGNN_CASE_K(1) FGNN_CASE_K(2) FGNN_CASE_K(3) default: FGNN_CASE_K(4) }
@@ -87,11 +99,12 @@ static void* kernel_lookup(int K, int HP, int closed_or_dense) {
 }
 static final_kernel_t final_kernel(int K, int HP, bool closed) { return (final_kernel_t)kernel_lookup(K, HP, closed ? 1 : 0); }
 static dense_kernel_t dense_kernel(int K, int HP) { return (dense_kernel_t)kernel_lookup(K, HP, 2); }
+static final_tc_kernel_t final_tc_kernel(int K, int HP, bool closed) { return (final_tc_kernel_t)kernel_lookup(K, HP, closed ? 4 : 3); }
 
 static size_t final_smem_bytes(const fgnn_handle* h) {
     WeightLayout wl{F * h->cfg.k, h->HP, h->cfg.n_layers};
     if (h->HP > 64) return (size_t)2 * h->HP * FINAL_THREADS * sizeof(float);
-    return (size_t)wl.total() * sizeof(float);
+    return ((size_t)wl.total() + (size_t)h->HP * FINAL_THREADS) * sizeof(float);
 }
 
 static inline int blocks_for(int n, int threads) { return (n + threads - 1) / threads; }
@@ -135,6 +148,7 @@ extern "C" int fgnn_create(const fgnn_config* cfg, fgnn_handle** out) {
     if (cap > 0xfffffff0ll) cap = 0xfffffff0ll;
     if (cap < 1024) cap = 1024;
     p.nnz_cap = (unsigned)cap;
+    h->adj_stage = (int)(cap_per < 8 ? 8 : cap_per > 64 ? 64 : cap_per);
     p.inv_cell = 1.0 / (cfg->comm_radius * (1.0 + 1.0 / 1048576.0));
     p.R2 = cfg->comm_radius * cfg->comm_radius;
     p.dt = cfg->dt;
@@ -163,7 +177,9 @@ extern "C" int fgnn_create(const fgnn_config* cfg, fgnn_handle** out) {
     rc |= dalloc(h, &p.zbuf, K * M * ROW);
     rc |= dalloc(h, &p.ybuf, 2 * K * M * ROW);
     rc |= dalloc(h, &p.action, M * 2);
-    rc |= dalloc(h, &p.racc, (size_t)p.B * 4);
+    rc |= dalloc(h, &p.racc, (size_t)RSLOTS * p.B * 4);
+    rc |= dalloc(h, &p.racc_part, (size_t)(blocks_for(p.M, FINAL_THREADS) + 1) * 4);
+    rc |= dalloc(h, &p.n_partials, 1);
     rc |= dalloc(h, &p.reward, (size_t)p.B);
     rc |= dalloc(h, &p.reward_pending, 1);
     rc |= dalloc(h, &p.log_index, 1);
@@ -190,8 +206,91 @@ extern "C" int fgnn_create(const fgnn_config* cfg, fgnn_handle** out) {
         if (grid > tiles) grid = tiles;
         (closed ? h->final_grid_closed : h->final_grid_open) = grid;
     }
+    // tensor-core readout: HP <= 64 (operands must fit shared memory); readout_mode 1 forces FFMA
+    h->raw_w.resize(p.L + 1);
+    h->raw_b.resize(p.L + 1);
+    if (cfg->readout_mode == 2 && h->HP > 64) { fgnn_destroy(h); return fail("fgnn_create: tensor-core readout needs hidden <= 64"); }
+    h->use_tc = (cfg->readout_mode != 1) && h->HP <= 64;
+    if (h->use_tc) {
+        TcLayout tl;
+        tl.K0 = TcLayout::pad8(F * p.K); tl.HP = h->HP; tl.L = p.L;
+        const int KA = tl.K0 > tl.HP ? tl.K0 : tl.HP;
+        h->tc_host.assign(tl.total_bytes(), 0);
+        if (dalloc(h, &h->d_tc_weights, (size_t)tl.total_bytes())) { fgnn_destroy(h); return 1; }
+        h->tc_smem = (size_t)tl.total_bytes() + (size_t)2 * 128 * KA * 4 + 16;
+        if (h->tc_smem > 227 * 1024) {
+            if (cfg->readout_mode == 2) { fgnn_destroy(h); return fail("fgnn_create: tensor-core readout operands exceed shared memory"); }
+            h->use_tc = false;
+        }
+    }
+    if (h->use_tc) {
+        for (int closed = 0; closed < 2; ++closed) {
+            final_tc_kernel_t fk = final_tc_kernel(p.K, h->HP, closed != 0);
+            CK(cudaFuncSetAttribute((const void*)fk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->tc_smem));
+            // resident CTAs per SM from shared memory, registers and TMEM columns (the occupancy API does not
+            // account for TMEM and was observed to report 0 for this kernel)
+            cudaFuncAttributes fa;
+            CK(cudaFuncGetAttributes(&fa, (const void*)fk));
+            int occ = (int)((size_t)prop.sharedMemPerMultiprocessor / (h->tc_smem + 1024));
+            const int occ_reg = 65536 / ((fa.numRegs > 0 ? ((fa.numRegs + 7) & ~7) : 128) * FINAL_THREADS);
+            if (occ > occ_reg) occ = occ_reg;
+            if (occ > 16) occ = 16;
+            if (occ < 1) occ = 1;
+            const int max_by_tmem = 512 / tc_tmem_cols(h->HP);
+            if (occ > max_by_tmem) occ = max_by_tmem;
+            int grid = h->sm_count * occ;
+            int tiles = blocks_for(p.M, FINAL_THREADS);
+            if (grid > tiles) grid = tiles;
+            (closed ? h->tc_grid_closed : h->tc_grid_open) = grid;
+        }
+    }
     *out = h;
     return 0;
+}
+
+static uint32_t f2u(float x) { uint32_t u; memcpy(&u, &x, 4); return u; }
+static float u2f(uint32_t u) { float x; memcpy(&x, &u, 4); return x; }
+// cvt.rna.tf32.f32 on the host: round to nearest (ties away) to 10 mantissa bits
+static float tf32_rna(float x) {
+    uint32_t u = f2u(x);
+    if ((u & 0x7f800000u) == 0x7f800000u) return x;
+    u += 0x1000u;
+    u &= 0xffffe000u;
+    return u2f(u);
+}
+
+// (re)build the tensor-core weight pack from the raw per-layer weights that have been set so far
+static void pack_tc_weights(fgnn_handle* h) {
+    const int K = h->cfg.k, H = h->cfg.hidden, L = h->cfg.n_layers, HP = h->HP;
+    TcLayout tl;
+    tl.K0 = TcLayout::pad8(F * K); tl.HP = HP; tl.L = L;
+    std::fill(h->tc_host.begin(), h->tc_host.end(), 0);
+    uint8_t* base = h->tc_host.data();
+    auto put = [&](int off_hi, int off_lo, int row, int col, int Kdim, float w) {
+        const float hi = tf32_rna(w);
+        const float lo = tf32_rna(w - hi);
+        const int o = TcLayout::canon_off(row, col, Kdim);
+        memcpy(base + off_hi + o, &hi, 4);
+        memcpy(base + off_lo + o, &lo, 4);
+    };
+    if (!h->raw_w[0].empty()) {
+        for (int g = 0; g < H; ++g)
+            for (int f = 0; f < F; ++f)
+                for (int k = 0; k < K; ++k) put(tl.off_w0(0), tl.off_w0(1), g, k * F + f, tl.K0, h->raw_w[0][((size_t)g * F + f) * K + k]);
+        memcpy(base + tl.off_b(0), h->raw_b[0].data(), H * 4);
+    }
+    for (int l = 1; l < L; ++l) {
+        if (h->raw_w[l].empty()) continue;
+        for (int g = 0; g < H; ++g)
+            for (int i = 0; i < H; ++i) put(tl.off_wh(l, 0), tl.off_wh(l, 1), g, i, HP, h->raw_w[l][(size_t)g * H + i]);
+        memcpy(base + tl.off_b(l), h->raw_b[l].data(), H * 4);
+    }
+    if (!h->raw_w[L].empty()) {
+        float* wl = reinterpret_cast<float*>(base + tl.off_wl());
+        for (int a = 0; a < 2; ++a)
+            for (int i = 0; i < H; ++i) wl[i * 2 + a] = h->raw_w[L][(size_t)a * H + i];
+        memcpy(base + tl.off_bl(), h->raw_b[L].data(), 2 * 4);
+    }
 }
 
 extern "C" int fgnn_destroy(fgnn_handle* h) {
@@ -217,6 +316,12 @@ extern "C" int fgnn_set_weights(fgnn_handle* h, int32_t layer, const float* W, c
     CK(cudaMemcpyAsync(w.data(), W, w.size() * sizeof(float), cudaMemcpyDefault, st));
     CK(cudaMemcpyAsync(bb.data(), b, bb.size() * sizeof(float), cudaMemcpyDefault, st));
     CK(cudaStreamSynchronize(st));
+    h->raw_w[layer] = w;
+    h->raw_b[layer] = bb;
+    if (h->use_tc) {
+        pack_tc_weights(h);
+        CK(cudaMemcpyAsync(h->d_tc_weights, h->tc_host.data(), h->tc_host.size(), cudaMemcpyHostToDevice, st));
+    }
     float* dst = h->w_host.data();
     if (layer == 0 && L >= 1) {
         // W (H, F, K) -> w0[(k*F + f)][g]
@@ -273,7 +378,7 @@ static int enqueue_build(fgnn_handle* h, int advance, cudaStream_t st) {
     if (launch_check(h, "scatter")) return 1;
     k_canon<<<gb, 256, 0, st>>>(p);
     if (launch_check(h, "canon")) return 1;
-    k_adjacency<<<gb, 256, 0, st>>>(p);
+    k_adjacency<<<blocks_for(p.M, ADJ_THREADS), ADJ_THREADS, (size_t)h->adj_stage * ADJ_THREADS * sizeof(int), st>>>(p, h->adj_stage);
     if (launch_check(h, "adjacency")) return 1;
     h->binned = false;
     if (advance) h->t_host += 1;
@@ -296,10 +401,17 @@ static int enqueue_hops(fgnn_handle* h, cudaStream_t st) {
 static int enqueue_final(fgnn_handle* h, bool closed, int write_z, cudaStream_t st) {
     Params p = h->p;
     p.write_z_last = write_z;
-    final_kernel_t fk = final_kernel(p.K, h->HP, closed);
-    const int grid = closed ? h->final_grid_closed : h->final_grid_open;
-    fk<<<grid, FINAL_THREADS, h->final_smem, st>>>(p);
-    if (launch_check(h, "final")) return 1;
+    if (h->use_tc) {
+        final_tc_kernel_t fk = final_tc_kernel(p.K, h->HP, closed);
+        const int grid = closed ? h->tc_grid_closed : h->tc_grid_open;
+        fk<<<grid, FINAL_THREADS, h->tc_smem, st>>>(p, h->d_tc_weights);
+        if (launch_check(h, "final")) return 1;
+    } else {
+        final_kernel_t fk = final_kernel(p.K, h->HP, closed);
+        const int grid = closed ? h->final_grid_closed : h->final_grid_open;
+        fk<<<grid, FINAL_THREADS, h->final_smem, st>>>(p);
+        if (launch_check(h, "final")) return 1;
+    }
     if (closed) h->binned = true;
     return 0;
 }
@@ -317,7 +429,7 @@ extern "C" int fgnn_set_state(fgnn_handle* h, const double* x, void* stream) {
     CK(cudaMemcpyAsync(h->p.state, x, (size_t)h->p.M * sizeof(double4), cudaMemcpyDefault, st));
     if (h->binned) {
         CK(cudaMemsetAsync(h->p.cell_count, 0, ((size_t)h->p.C + 1) * sizeof(int), st));
-        CK(cudaMemsetAsync(h->p.racc, 0, (size_t)h->p.B * 4 * sizeof(double), st));
+        CK(cudaMemsetAsync(h->p.racc, 0, (size_t)RSLOTS * h->p.B * 4 * sizeof(double), st));
         CK(cudaMemsetAsync(h->p.reward_pending, 0, sizeof(int), st));
         h->binned = false;
     }
@@ -341,7 +453,7 @@ extern "C" int fgnn_reset(fgnn_handle* h, const double* x, void* stream) {
     CK(cudaMemsetAsync(p.cell_count, 0, ((size_t)p.C + 1) * sizeof(int), st));
     CK(cudaMemsetAsync(p.tile_status, 0, (size_t)p.n_tiles * sizeof(unsigned), st));
     CK(cudaMemsetAsync(p.tile_counter, 0, sizeof(int), st));
-    CK(cudaMemsetAsync(p.racc, 0, (size_t)p.B * 4 * sizeof(double), st));
+    CK(cudaMemsetAsync(p.racc, 0, (size_t)RSLOTS * p.B * 4 * sizeof(double), st));
     CK(cudaMemsetAsync(p.reward, 0, (size_t)p.B * sizeof(double), st));
     CK(cudaMemsetAsync(p.reward_pending, 0, sizeof(int), st));
     CK(cudaMemsetAsync(p.action, 0, M * 2 * sizeof(float), st));
@@ -364,7 +476,7 @@ extern "C" int fgnn_integrate(fgnn_handle* h, const float* u, double* reward_b, 
     CK(cudaSetDevice(h->cfg.device));
     if (h->binned) {      // positions were binned already (closed-loop kernel or a previous integrate): start over
         CK(cudaMemsetAsync(p.cell_count, 0, ((size_t)p.C + 1) * sizeof(int), st));
-        CK(cudaMemsetAsync(p.racc, 0, (size_t)p.B * 4 * sizeof(double), st));
+        CK(cudaMemsetAsync(p.racc, 0, (size_t)RSLOTS * p.B * 4 * sizeof(double), st));
     }
     CK(cudaMemcpyAsync(h->d_u_in, u, (size_t)p.M * 2 * sizeof(float), cudaMemcpyDefault, st));
     k_integrate<<<blocks_for(p.M, 256), 256, 0, st>>>(p, h->d_u_in);
@@ -463,7 +575,8 @@ extern "C" int fgnn_actor_forward_dense(fgnn_handle* h, int32_t batch, int32_t n
     dense_kernel_t dk = dense_kernel(K, h->HP);
     WeightLayout wl{F * K, h->HP, h->cfg.n_layers};
     size_t smem = (size_t)K * F * DENSE_MT * sizeof(float) +
-                  (h->HP > 64 ? (size_t)2 * h->HP * FINAL_THREADS * sizeof(float) : (size_t)wl.total() * sizeof(float));
+                  (h->HP > 64 ? (size_t)2 * h->HP * FINAL_THREADS * sizeof(float)
+                              : ((size_t)wl.total() + (size_t)h->HP * FINAL_THREADS) * sizeof(float));
     CK(cudaFuncSetAttribute((const void*)dk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(blocks_for(n2, FINAL_THREADS), batch);
     dk<<<grid, FINAL_THREADS, smem, st>>>(ds, gso, out, h->d_weights, h->cfg.n_layers, n2);

@@ -5,109 +5,104 @@
 
 namespace fgnn {
 
+// Activation.  tanh.approx.f32 (2^-11) breaks the 1e-5 action tolerance and libdevice tanhf costs ~25
+// instructions with a branch.  tanh_act: |x| < 0.35 -> odd Taylor polynomial x*P(x^2) (relative error
+// < 7e-8 there); otherwise sign(x) (1-e)/(1+e), e = exp(-2|x|) <= 0.5 via ex2.approx + rcp.approx
+// (absolute error < 2.5e-7, clean saturation to +-1).  Branch-free select, ~17 instructions.
+__device__ __forceinline__ float tanh_act(float x) {
+    const float x2 = x * x;
+    // tanh(x)/x = 1 - x^2/3 + 2x^4/15 - 17x^6/315 + 62x^8/2835 - 1382x^10/155925
+    float p = fmaf(x2, -0.0088632355f, 0.021869488f);
+    p = fmaf(x2, p, -0.053968254f);
+    p = fmaf(x2, p, 0.13333334f);
+    p = fmaf(x2, p, -0.33333334f);
+    const float small = fmaf(x * x2, p, x);
+    const float ax = fabsf(x);
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(ax * -2.885390081777927f));   // e^{-2|x|}
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    const float big = copysignf((1.0f - e) * r, x);
+    return ax < 0.35f ? small : big;
+}
+
 // ------------------------------------------------------------------------------------------
 // readout MLP on CUDA cores (FFMA): in (6K) -> HP -> ... -> HP -> 2, tanh between layers.
-// Weights live in shared memory (HP <= 64) and are read as warp-broadcast float4.
+// One thread per agent.  Hidden activations are staged in shared memory, one column per thread
+// (bank-conflict free), so the loops over the input index stay ROLLED: the fully unrolled form is
+// ~50 KB of SASS and stalls on instruction fetch (ncu: 41% no_instructions).  Weights are read as
+// warp-broadcast float4 from shared memory (HP <= 64) or through L1 (HP = 128).
 // ------------------------------------------------------------------------------------------
-template <int IN, int HP>
-__device__ __forceinline__ void mlp_ffma(const float (&in)[IN], const float* __restrict__ sw, const WeightLayout wl,
-                                         float& o0, float& o1) {
-    float h[HP];
-    {
-        const float* b0 = sw + wl.off_b0();
+template <int IN, int HP, int THREADS>
+__device__ __forceinline__ void mlp_ffma(const float (&in)[IN], const float* __restrict__ w, const WeightLayout wl,
+                                         float* __restrict__ sh /* [HP][THREADS] (x2 when HP > 64) */, float& o0, float& o1) {
+    constexpr int GC = HP < 64 ? HP : 64;          // output chunk held in registers
+    const int tid = threadIdx.x;
+    // layer 0: in[] lives in registers (IN <= 24), fully unrolled over the inputs
+#pragma unroll 1
+    for (int g0 = 0; g0 < HP; g0 += GC) {
+        float acc[GC];
+        const float4* b4 = reinterpret_cast<const float4*>(w + wl.off_b0() + g0);
 #pragma unroll
-        for (int g = 0; g < HP; ++g) h[g] = b0[g];
-        const float4* w0 = reinterpret_cast<const float4*>(sw + wl.off_w0());
+        for (int g4 = 0; g4 < GC / 4; ++g4) {
+            const float4 bb = b4[g4];
+            acc[4 * g4 + 0] = bb.x; acc[4 * g4 + 1] = bb.y; acc[4 * g4 + 2] = bb.z; acc[4 * g4 + 3] = bb.w;
+        }
 #pragma unroll
         for (int i = 0; i < IN; ++i) {
             const float xi = in[i];
+            const float4* w4 = reinterpret_cast<const float4*>(w + wl.off_w0() + i * HP + g0);
 #pragma unroll
-            for (int g4 = 0; g4 < HP / 4; ++g4) {
-                const float4 w = w0[i * (HP / 4) + g4];
-                h[4 * g4 + 0] = fmaf(xi, w.x, h[4 * g4 + 0]);
-                h[4 * g4 + 1] = fmaf(xi, w.y, h[4 * g4 + 1]);
-                h[4 * g4 + 2] = fmaf(xi, w.z, h[4 * g4 + 2]);
-                h[4 * g4 + 3] = fmaf(xi, w.w, h[4 * g4 + 3]);
+            for (int g4 = 0; g4 < GC / 4; ++g4) {
+                const float4 ww = w4[g4];
+                acc[4 * g4 + 0] = fmaf(xi, ww.x, acc[4 * g4 + 0]);
+                acc[4 * g4 + 1] = fmaf(xi, ww.y, acc[4 * g4 + 1]);
+                acc[4 * g4 + 2] = fmaf(xi, ww.z, acc[4 * g4 + 2]);
+                acc[4 * g4 + 3] = fmaf(xi, ww.w, acc[4 * g4 + 3]);
             }
         }
 #pragma unroll
-        for (int g = 0; g < HP; ++g) h[g] = tanhf(h[g]);
+        for (int g = 0; g < GC; ++g) sh[(g0 + g) * THREADS + tid] = tanh_act(acc[g]);
     }
-    for (int l = 1; l < wl.L; ++l) {
-        float h2[HP];
-        const float* bh = sw + wl.off_bh(l);
-#pragma unroll
-        for (int g = 0; g < HP; ++g) h2[g] = bh[g];
-        const float4* wh = reinterpret_cast<const float4*>(sw + wl.off_wh(l));
-#pragma unroll
-        for (int i = 0; i < HP; ++i) {
-            const float xi = h[i];
-#pragma unroll
-            for (int g4 = 0; g4 < HP / 4; ++g4) {
-                const float4 w = wh[i * (HP / 4) + g4];
-                h2[4 * g4 + 0] = fmaf(xi, w.x, h2[4 * g4 + 0]);
-                h2[4 * g4 + 1] = fmaf(xi, w.y, h2[4 * g4 + 1]);
-                h2[4 * g4 + 2] = fmaf(xi, w.z, h2[4 * g4 + 2]);
-                h2[4 * g4 + 3] = fmaf(xi, w.w, h2[4 * g4 + 3]);
-            }
-        }
-#pragma unroll
-        for (int g = 0; g < HP; ++g) h[g] = tanhf(h2[g]);
-    }
-    const float2* wlp = reinterpret_cast<const float2*>(sw + wl.off_wl());
-    const float* bl = sw + wl.off_bl();
-    float a0 = bl[0], a1 = bl[1];
-#pragma unroll
-    for (int i = 0; i < HP; ++i) {
-        const float2 w = wlp[i];
-        a0 = fmaf(h[i], w.x, a0);
-        a1 = fmaf(h[i], w.y, a1);
-    }
-    o0 = a0;
-    o1 = a1;
-}
-
-// Wide layers (HP = 128): activations staged in shared memory (column per thread), weights read
-// through L1 as warp-uniform loads.  Correct for any HP; used where registers would not hold h[].
-template <int IN, int HP, int THREADS>
-__device__ __forceinline__ void mlp_wide(const float (&in)[IN], const float* __restrict__ gw, const WeightLayout wl,
-                                         float* sh /* [2][HP][THREADS] */, float& o0, float& o1) {
-    const int tid = threadIdx.x;
+    // hidden layers: activations from shared memory, rolled loop over the input index.
+    // With more than one output chunk the layer writes to the second half of sh (ping-pong).
     float* cur = sh;
-    float* nxt = sh + HP * THREADS;
-    for (int g = 0; g < HP; ++g) {
-        float acc = __ldg(gw + wl.off_b0() + g);
-#pragma unroll
-        for (int i = 0; i < IN; ++i) acc = fmaf(in[i], __ldg(gw + wl.off_w0() + i * HP + g), acc);
-        cur[g * THREADS + tid] = tanhf(acc);
-    }
+    float* nxt = (HP > GC) ? sh + HP * THREADS : sh;
     for (int l = 1; l < wl.L; ++l) {
-        for (int g0 = 0; g0 < HP; g0 += 16) {
-            float acc[16];
+#pragma unroll 1
+        for (int g0 = 0; g0 < HP; g0 += GC) {
+            float acc[GC];
+            const float4* b4 = reinterpret_cast<const float4*>(w + wl.off_bh(l) + g0);
 #pragma unroll
-            for (int u = 0; u < 16; ++u) acc[u] = __ldg(gw + wl.off_bh(l) + g0 + u);
+            for (int g4 = 0; g4 < GC / 4; ++g4) {
+                const float4 bb = b4[g4];
+                acc[4 * g4 + 0] = bb.x; acc[4 * g4 + 1] = bb.y; acc[4 * g4 + 2] = bb.z; acc[4 * g4 + 3] = bb.w;
+            }
+#pragma unroll 2
             for (int i = 0; i < HP; ++i) {
                 const float xi = cur[i * THREADS + tid];
-                const float4* w = reinterpret_cast<const float4*>(gw + wl.off_wh(l) + i * HP + g0);
+                const float4* w4 = reinterpret_cast<const float4*>(w + wl.off_wh(l) + i * HP + g0);
 #pragma unroll
-                for (int u4 = 0; u4 < 4; ++u4) {
-                    const float4 ww = __ldg(w + u4);
-                    acc[4 * u4 + 0] = fmaf(xi, ww.x, acc[4 * u4 + 0]);
-                    acc[4 * u4 + 1] = fmaf(xi, ww.y, acc[4 * u4 + 1]);
-                    acc[4 * u4 + 2] = fmaf(xi, ww.z, acc[4 * u4 + 2]);
-                    acc[4 * u4 + 3] = fmaf(xi, ww.w, acc[4 * u4 + 3]);
+                for (int g4 = 0; g4 < GC / 4; ++g4) {
+                    const float4 ww = w4[g4];
+                    acc[4 * g4 + 0] = fmaf(xi, ww.x, acc[4 * g4 + 0]);
+                    acc[4 * g4 + 1] = fmaf(xi, ww.y, acc[4 * g4 + 1]);
+                    acc[4 * g4 + 2] = fmaf(xi, ww.z, acc[4 * g4 + 2]);
+                    acc[4 * g4 + 3] = fmaf(xi, ww.w, acc[4 * g4 + 3]);
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 16; ++u) nxt[(g0 + u) * THREADS + tid] = tanhf(acc[u]);
+            for (int g = 0; g < GC; ++g) nxt[(g0 + g) * THREADS + tid] = tanh_act(acc[g]);
         }
-        float* tmp = cur; cur = nxt; nxt = tmp;
+        if (HP > GC) { float* tmp = cur; cur = nxt; nxt = tmp; }
     }
-    float a0 = __ldg(gw + wl.off_bl()), a1 = __ldg(gw + wl.off_bl() + 1);
+    const float2* wlp = reinterpret_cast<const float2*>(w + wl.off_wl());
+    float a0 = w[wl.off_bl()], a1 = w[wl.off_bl() + 1];
+#pragma unroll 4
     for (int i = 0; i < HP; ++i) {
         const float xi = cur[i * THREADS + tid];
-        a0 = fmaf(xi, __ldg(gw + wl.off_wl() + 2 * i), a0);
-        a1 = fmaf(xi, __ldg(gw + wl.off_wl() + 2 * i + 1), a1);
+        const float2 ww = wlp[i];
+        a0 = fmaf(xi, ww.x, a0);
+        a1 = fmaf(xi, ww.y, a1);
     }
     o0 = a0;
     o1 = a1;
@@ -124,6 +119,8 @@ __global__ void __launch_bounds__(FINAL_THREADS) k_final(Params p) {
     WeightLayout wl;
     wl.in0 = F * K; wl.HP = HP; wl.L = p.L;
     constexpr bool WIDE = (HP > 64);
+    // smem: [weights (HP <= 64 only)] [activation staging: HP x THREADS (x2 when HP = 128)]
+    float* sh_act = smem + (WIDE ? 0 : wl.total());
     if (!WIDE) {
         const int nw4 = wl.total() / 4;
         const float4* gw = reinterpret_cast<const float4*>(p.weights);
@@ -134,6 +131,7 @@ __global__ void __launch_bounds__(FINAL_THREADS) k_final(Params p) {
     const int t = *p.t;
     const size_t M = p.M;
     const int n_tiles = (p.M + FINAL_THREADS - 1) / FINAL_THREADS;
+    double racc[4] = {0, 0, 0, 0};
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int a = tile * FINAL_THREADS + threadIdx.x;
         const bool valid = a < p.M;
@@ -166,13 +164,26 @@ __global__ void __launch_bounds__(FINAL_THREADS) k_final(Params p) {
                 float acc[F];
 #pragma unroll
                 for (int f = 0; f < F; ++f) acc[f] = 0.f;
-                for (int e = 0; e < d; ++e) {
-                    const int m = __ldg(&cols[e]);
-                    const float sc = __ldg(&sinv[m]);
-                    float v[F];
-                    load_row6(src, m, v);
+                for (int e = 0; e < d; e += HOP_UNROLL) {
+                    int m[HOP_UNROLL];
+                    float sc[HOP_UNROLL];
+                    float v[HOP_UNROLL][F];
 #pragma unroll
-                    for (int f = 0; f < F; ++f) acc[f] = fmaf(v[f], sc, acc[f]);
+                    for (int u = 0; u < HOP_UNROLL; ++u) m[u] = (e + u < d) ? __ldg(&cols[e + u]) : -1;
+#pragma unroll
+                    for (int u = 0; u < HOP_UNROLL; ++u) {
+                        if (m[u] >= 0) {
+                            sc[u] = __ldg(&sinv[m[u]]);
+                            load_row6(src, m[u], v[u]);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < HOP_UNROLL; ++u) {
+                        if (m[u] >= 0) {
+#pragma unroll
+                            for (int f = 0; f < F; ++f) acc[f] = fmaf(v[u][f], sc[u], acc[f]);
+                        }
+                    }
                 }
 #pragma unroll
                 for (int f = 0; f < F; ++f) in[(K - 1) * F + f] = acc[f];
@@ -180,16 +191,13 @@ __global__ void __launch_bounds__(FINAL_THREADS) k_final(Params p) {
             }
         }
         float o0, o1;
-        if (WIDE) {
-            mlp_wide<F * K, HP, FINAL_THREADS>(in, p.weights, wl, smem, o0, o1);
-        } else {
-            mlp_ffma<F * K, HP>(in, smem, wl, o0, o1);
-        }
+        mlp_ffma<F * K, HP, FINAL_THREADS>(in, WIDE ? p.weights : smem, wl, sh_act, o0, o1);
         if (valid) {
             reinterpret_cast<float2*>(p.action)[a] = make_float2(o0, o1);
-            if (CLOSED) integrate_and_bin(p, a, o0, o1);
+            if (CLOSED) integrate_and_bin(p, a, o0, o1, racc);
         }
     }
+    if (CLOSED) reward_block_flush<FINAL_THREADS>(p, racc);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -238,11 +246,7 @@ __global__ void __launch_bounds__(FINAL_THREADS) k_actor_dense(const float* __re
     }
     __syncthreads();
     float o0, o1;
-    if (WIDE) {
-        mlp_wide<F * K, HP, FINAL_THREADS>(in, weights, wl, sw, o0, o1);
-    } else {
-        mlp_ffma<F * K, HP>(in, sw, wl, o0, o1);
-    }
+    mlp_ffma<F * K, HP, FINAL_THREADS>(in, WIDE ? weights : sw, wl, sw + (WIDE ? 0 : wl.total()), o0, o1);
     if (valid) {
         out[((size_t)b * 2 + 0) * N2 + n] = o0;
         out[((size_t)b * 2 + 1) * N2 + n] = o1;

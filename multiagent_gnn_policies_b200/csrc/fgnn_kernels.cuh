@@ -15,6 +15,8 @@ constexpr int KMAX = 4;       // filter taps supported
 constexpr int LMAX = 4;       // hidden layers supported
 constexpr int FINAL_THREADS = 128;   // block size of the fused final kernel and the dense Actor kernel
 constexpr int DENSE_MT = 32;         // m-tile of the dense Actor kernel
+constexpr int RSLOTS = 64;          // reward accumulators per episode (spreads same-address atomics)
+constexpr int HOP_UNROLL = 4;        // edges gathered concurrently per thread in the hop loops
 
 // All device pointers one step needs.  Passed by value to every kernel.
 struct Params {
@@ -59,7 +61,9 @@ struct Params {
     float* action;            // [M][2]
     const float* weights;     // packed, see WeightLayout
 
-    double* racc;             // [B][4] sum vx, vy, vx^2, vy^2
+    double* racc;             // [RSLOTS][B][4] sum vx, vy, vx^2, vy^2 (slotted atomics, B > 1)
+    double* racc_part;        // [max grid][4] per-block partial sums (B == 1: no atomics, fixed order)
+    int* n_partials;          // number of valid rows in racc_part
     double* reward;           // [B]
     int* reward_pending;
     double* reward_log;       // [T][B] or null
@@ -129,19 +133,49 @@ __global__ void __launch_bounds__(256) k_bin(Params p) {
     atomicAdd(&p.cell_count[c], 1);
 }
 
-// reward_b = -(var(vx) + var(vy)) per episode from the accumulated sums; clears the sums
+// reward_b = -(var(vx) + var(vy)) per episode from the accumulated sums; clears the sums.
+// B == 1: per-block partials summed in a fixed order (bit-reproducible); B > 1: RSLOTS atomic slots per episode.
 static __device__ __forceinline__ void finalize_reward(const Params& p) {
     if (*p.reward_pending == 0) return;
     __syncthreads();
     const int li = p.reward_log ? *p.log_index : 0;
-    for (int b = threadIdx.x; b < p.B; b += blockDim.x) {
-        double n = (double)p.N;
-        double sx = p.racc[b * 4 + 0], sy = p.racc[b * 4 + 1], qx = p.racc[b * 4 + 2], qy = p.racc[b * 4 + 3];
-        double mx = sx / n, my = sy / n;
-        double r = -((qx / n - mx * mx) + (qy / n - my * my));
-        p.reward[b] = r;
-        if (p.reward_log) p.reward_log[(size_t)li * p.B + b] = r;
-        p.racc[b * 4 + 0] = 0.0; p.racc[b * 4 + 1] = 0.0; p.racc[b * 4 + 2] = 0.0; p.racc[b * 4 + 3] = 0.0;
+    const double n = (double)p.N;
+    if (p.B == 1) {
+        __shared__ double s_red[4][256];
+        const int np = *p.n_partials;
+        double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+        for (int i = threadIdx.x; i < np; i += blockDim.x) {
+            a0 += p.racc_part[i * 4 + 0]; a1 += p.racc_part[i * 4 + 1];
+            a2 += p.racc_part[i * 4 + 2]; a3 += p.racc_part[i * 4 + 3];
+        }
+        s_red[0][threadIdx.x] = a0; s_red[1][threadIdx.x] = a1; s_red[2][threadIdx.x] = a2; s_red[3][threadIdx.x] = a3;
+        __syncthreads();
+        for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+            if (threadIdx.x < o) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) s_red[k][threadIdx.x] += s_red[k][threadIdx.x + o];
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            const double mx = s_red[0][0] / n, my = s_red[1][0] / n;
+            const double r = -((s_red[2][0] / n - mx * mx) + (s_red[3][0] / n - my * my));
+            p.reward[0] = r;
+            if (p.reward_log) p.reward_log[(size_t)li] = r;
+        }
+    } else {
+        for (int b = threadIdx.x; b < p.B; b += blockDim.x) {
+            double q[4] = {0, 0, 0, 0};
+            for (int sidx = 0; sidx < RSLOTS; ++sidx) {
+                double* src = p.racc + ((size_t)sidx * p.B + b) * 4;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { q[k] += src[k]; src[k] = 0.0; }
+            }
+            const double mx = q[0] / n, my = q[1] / n;
+            const double r = -((q[2] / n - mx * mx) + (q[3] / n - my * my));
+            p.reward[b] = r;
+            if (p.reward_log) p.reward_log[(size_t)li * p.B + b] = r;
+        }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -150,7 +184,7 @@ static __device__ __forceinline__ void finalize_reward(const Params& p) {
     }
 }
 
-__global__ void k_finalize_reward(Params p) { finalize_reward(p); }
+__global__ void __launch_bounds__(256) k_finalize_reward(Params p) { finalize_reward(p); }
 
 // ------------------------------------------------------------------------------------------
 // K_B  scan: exclusive prefix sum of cell_count[0..C] -> cell_start[0..C] (single pass,
@@ -282,40 +316,71 @@ __global__ void __launch_bounds__(256) k_canon(Params p) {
 // ------------------------------------------------------------------------------------------
 // K_D  adjacency + degree + 6-d relative features (gym_flock compute_helpers), CSR emission.
 //      One thread per agent, in cell-sorted order; float64 arithmetic for the radius cut and the
-//      feature sums (bit-identical edge set to the float64 oracle).
+//      feature sums (bit-identical edge set to the float64 oracle).  Single pass over the 3x3 cell
+//      neighbourhood (the three cells of a grid row are one contiguous slot range): accepted
+//      neighbour ids are staged in shared memory, the warp then reserves one contiguous run of edge
+//      slots for its 32 rows and flushes the staged ids; rows longer than the stage re-scan.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_adjacency(Params p) {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
+constexpr int ADJ_THREADS = 128;
+
+__global__ void __launch_bounds__(ADJ_THREADS) k_adjacency(Params p, int stage_cap) {
+    extern __shared__ int s_stage[];                      // [stage_cap][ADJ_THREADS]
+    const int tid = threadIdx.x;
+    const int s = blockIdx.x * ADJ_THREADS + tid;
+    const int lane = tid & 31;
     // housekeeping for the next scan
-    for (int i = s; i < p.n_tiles; i += gridDim.x * blockDim.x) p.tile_status[i] = 0;
+    for (int i = s; i < p.n_tiles; i += gridDim.x * ADJ_THREADS) p.tile_status[i] = 0;
     if (s == 0) *p.tile_counter = 0;
 
     const int t = *p.t;
     const int g = slot_of(t, p.K);
     const bool valid = s < p.M;
-    int a = 0, ep = 0;
+    int a = 0;
     double4 me = make_double4(0, 0, 0, 0);
     int q0[9], q1[9];
     int count = 0;
+    double f0 = 0, f1 = 0, f2 = 0, f3 = 0, f4 = 0, f5 = 0;
     if (valid) {
         a = p.sorted_id[s];
         me = p.sorted_state[s];
-        ep = a / p.N;
+        const int ep = a / p.N;
         long long ix, iy;
         cell_coords(p, me.x, me.y, ix, iy);
+        const int cxw = wrap(ix, p.G);
 #pragma unroll
-        for (int j = 0; j < 9; ++j) {
-            int c = cell_index(p, ep, ix + (j % 3) - 1, iy + (j / 3) - 1);
-            q0[j] = __ldg(&p.cell_start[c]);
-            q1[j] = __ldg(&p.cell_start[c + 1]);
+        for (int r = 0; r < 3; ++r) {
+            const int rowbase = (ep * p.G + wrap(iy + r - 1, p.G)) * p.G;
+            if (cxw >= 1 && cxw <= p.G - 2) {            // the row's three cells are contiguous slots
+                q0[3 * r] = __ldg(&p.cell_start[rowbase + cxw - 1]);
+                q1[3 * r] = __ldg(&p.cell_start[rowbase + cxw + 2]);
+                q0[3 * r + 1] = q1[3 * r + 1] = q0[3 * r + 2] = q1[3 * r + 2] = 0;
+            } else {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const int cell = rowbase + wrap(ix + c - 1, p.G);
+                    q0[3 * r + c] = __ldg(&p.cell_start[cell]);
+                    q1[3 * r + c] = __ldg(&p.cell_start[cell + 1]);
+                }
+            }
         }
 #pragma unroll
         for (int j = 0; j < 9; ++j) {
             for (int q = q0[j]; q < q1[j]; ++q) {
-                const double2 o = *reinterpret_cast<const double2*>(&p.sorted_state[q]);
-                double r2 = r2_exact(me.x - o.x, me.y - o.y);
-                count += (q != s && r2 < p.R2) ? 1 : 0;
+                const double4 o = p.sorted_state[q];
+                const double dx = me.x - o.x, dy = me.y - o.y;
+                const double r2 = r2_exact(dx, dy);
+                if (q != s && r2 < p.R2) {
+                    const double inv = 1.0 / r2;
+                    const double inv2 = inv * inv;
+                    f0 += me.z - o.z;
+                    f1 += dx * inv2;
+                    f2 += dx * inv;
+                    f3 += me.w - o.w;
+                    f4 += dy * inv2;
+                    f5 += dy * inv;
+                    if (count < stage_cap) s_stage[count * ADJ_THREADS + tid] = __ldg(&p.sorted_id[q]);
+                    ++count;
+                }
             }
         }
     }
@@ -337,26 +402,19 @@ __global__ void __launch_bounds__(256) k_adjacency(Params p) {
         count = 0;
         row = 0;
     }
-    double f0 = 0, f1 = 0, f2 = 0, f3 = 0, f4 = 0, f5 = 0;
     int* cols = p.cols + (size_t)g * p.nnz_cap + row;
-    int w = 0;
-    if (count > 0) {
+    const int staged = count < stage_cap ? count : stage_cap;
+    for (int e = 0; e < staged; ++e) cols[e] = s_stage[e * ADJ_THREADS + tid];
+    if (count > stage_cap) {                              // long row: re-scan for the tail (same order)
+        int w = 0;
 #pragma unroll
         for (int j = 0; j < 9; ++j) {
             for (int q = q0[j]; q < q1[j]; ++q) {
-                const double4 o = p.sorted_state[q];
-                double dx = me.x - o.x, dy = me.y - o.y;
-                double r2 = r2_exact(dx, dy);
+                const double2 o = *reinterpret_cast<const double2*>(&p.sorted_state[q]);
+                const double r2 = r2_exact(me.x - o.x, me.y - o.y);
                 if (q != s && r2 < p.R2) {
-                    double inv = 1.0 / r2;
-                    double inv2 = inv * inv;
-                    f0 += me.z - o.z;
-                    f1 += dx * inv2;
-                    f2 += dx * inv;
-                    f3 += me.w - o.w;
-                    f4 += dy * inv2;
-                    f5 += dy * inv;
-                    cols[w++] = __ldg(&p.sorted_id[q]);
+                    if (w >= stage_cap) cols[w] = __ldg(&p.sorted_id[q]);
+                    ++w;
                 }
             }
         }
@@ -401,15 +459,29 @@ __global__ void __launch_bounds__(256) k_hop(Params p, int j) {
     for (int b = 0; b < NB; ++b)
 #pragma unroll
         for (int f = 0; f < F; ++f) acc[b][f] = 0.f;
-    for (int e = 0; e < d; ++e) {
-        const int m = __ldg(&cols[e]);
-        const float sc = __ldg(&sinv[m]);
+    // edges in chunks of HOP_UNROLL: all indices, then all row gathers in flight, then in-order accumulation
+    for (int e = 0; e < d; e += HOP_UNROLL) {
+        int m[HOP_UNROLL];
+        float sc[HOP_UNROLL];
+        float v[HOP_UNROLL][NB][F];
 #pragma unroll
-        for (int b = 0; b < NB; ++b) {
-            float v[F];
-            load_row6(src[b], m, v);
+        for (int u = 0; u < HOP_UNROLL; ++u) m[u] = (e + u < d) ? __ldg(&cols[e + u]) : -1;
 #pragma unroll
-            for (int f = 0; f < F; ++f) acc[b][f] = fmaf(v[f], sc, acc[b][f]);
+        for (int u = 0; u < HOP_UNROLL; ++u) {
+            if (m[u] >= 0) {
+                sc[u] = __ldg(&sinv[m[u]]);
+#pragma unroll
+                for (int b = 0; b < NB; ++b) load_row6(src[b], m[u], v[u][b]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < HOP_UNROLL; ++u) {
+            if (m[u] >= 0) {
+#pragma unroll
+                for (int b = 0; b < NB; ++b)
+#pragma unroll
+                    for (int f = 0; f < F; ++f) acc[b][f] = fmaf(v[u][b][f], sc[u], acc[b][f]);
+            }
         }
     }
 #pragma unroll
@@ -417,7 +489,7 @@ __global__ void __launch_bounds__(256) k_hop(Params p, int j) {
 }
 
 // double integrator exactly in numpy's evaluation order (no FMA contraction), then bin the new position
-__device__ __forceinline__ void integrate_and_bin(const Params& p, int a, float u0, float u1) {
+__device__ __forceinline__ void integrate_and_bin(const Params& p, int a, float u0, float u1, double (&racc)[4]) {
     double4 s = p.state[a];
     const double ax = __dmul_rn((double)u0, p.gain), ay = __dmul_rn((double)u1, p.gain);
     double nx = __dadd_rn(s.x, __dmul_rn(s.z, p.dt));
@@ -435,37 +507,68 @@ __device__ __forceinline__ void integrate_and_bin(const Params& p, int a, float 
     const int c = cell_index(p, ep, ix, iy);
     p.cell_of[a] = c;
     atomicAdd(&p.cell_count[c], 1);
-    // velocity-variance reward: per-episode sums (warp-reduced when the warp sits in one episode)
-    double v0 = nvx, v1 = nvy, v2 = nvx * nvx, v3 = nvy * nvy;
-    const unsigned mask = __activemask();
-    const int ep0 = __shfl_sync(mask, ep, __ffs(mask) - 1);
-    const bool uniform = __all_sync(mask, ep == ep0);
-    if (uniform && mask == 0xffffffffu) {
+    // velocity-variance reward sums
+    if (p.B == 1) {                 // thread-local; reduced per block by reward_block_flush()
+        racc[0] += nvx; racc[1] += nvy; racc[2] += nvx * nvx; racc[3] += nvy * nvy;
+    } else {                        // slotted atomics, warp-reduced when the warp sits in one episode
+        double v0 = nvx, v1 = nvy, v2 = nvx * nvx, v3 = nvy * nvy;
+        const unsigned mask = __activemask();
+        const int ep0 = __shfl_sync(mask, ep, __ffs(mask) - 1);
+        const bool uniform = __all_sync(mask, ep == ep0);
+        double* dst = p.racc + ((size_t)(blockIdx.x % RSLOTS) * p.B + ep) * 4;
+        if (uniform && mask == 0xffffffffu) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            v0 += __shfl_xor_sync(0xffffffffu, v0, o);
-            v1 += __shfl_xor_sync(0xffffffffu, v1, o);
-            v2 += __shfl_xor_sync(0xffffffffu, v2, o);
-            v3 += __shfl_xor_sync(0xffffffffu, v3, o);
+            for (int o = 16; o > 0; o >>= 1) {
+                v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+                v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+                v2 += __shfl_xor_sync(0xffffffffu, v2, o);
+                v3 += __shfl_xor_sync(0xffffffffu, v3, o);
+            }
+            if ((threadIdx.x & 31) == 0) {
+                atomicAdd(dst + 0, v0); atomicAdd(dst + 1, v1); atomicAdd(dst + 2, v2); atomicAdd(dst + 3, v3);
+            }
+        } else {
+            atomicAdd(dst + 0, v0); atomicAdd(dst + 1, v1); atomicAdd(dst + 2, v2); atomicAdd(dst + 3, v3);
         }
-        if ((threadIdx.x & 31) == 0) {
-            atomicAdd(&p.racc[ep * 4 + 0], v0); atomicAdd(&p.racc[ep * 4 + 1], v1);
-            atomicAdd(&p.racc[ep * 4 + 2], v2); atomicAdd(&p.racc[ep * 4 + 3], v3);
-        }
-    } else {
-        atomicAdd(&p.racc[ep * 4 + 0], v0); atomicAdd(&p.racc[ep * 4 + 1], v1);
-        atomicAdd(&p.racc[ep * 4 + 2], v2); atomicAdd(&p.racc[ep * 4 + 3], v3);
     }
     if (a == 0) *p.reward_pending = 1;
+}
+
+// B == 1: sum the block's thread-local reward sums in a fixed order and store them as this block's partial.
+// Must be called by every thread of the block (even ones that integrated nothing).
+template <int THREADS>
+__device__ __forceinline__ void reward_block_flush(const Params& p, const double (&racc)[4]) {
+    if (p.B != 1) return;
+    __shared__ double s_part[4][THREADS / 32];
+    double v[4] = {racc[0], racc[1], racc[2], racc[3]};
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s_part[k][threadIdx.x >> 5] = v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double t = 0;
+#pragma unroll
+        for (int w = 0; w < THREADS / 32; ++w) t += s_part[threadIdx.x][w];
+        p.racc_part[(size_t)blockIdx.x * 4 + threadIdx.x] = t;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *p.n_partials = gridDim.x;
 }
 
 #ifdef FGNN_MAIN_TU
 // first half of env.step(u) with an externally supplied action
 __global__ void __launch_bounds__(256) k_integrate(Params p, const float* __restrict__ u) {
     int a = blockIdx.x * blockDim.x + threadIdx.x;
-    if (a >= p.M) return;
-    const float2 uu = reinterpret_cast<const float2*>(u)[a];
-    integrate_and_bin(p, a, uu.x, uu.y);
+    double racc[4] = {0, 0, 0, 0};
+    if (a < p.M) {
+        const float2 uu = reinterpret_cast<const float2*>(u)[a];
+        integrate_and_bin(p, a, uu.x, uu.y, racc);
+    }
+    reward_block_flush<256>(p, racc);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -85,32 +85,34 @@ class SparseDelayState:
         self.hist_x = [x] + ([] if prev_state is None else prev_state.hist_x[:k - 1])
         self.hist_a = [network_csr_f32] + ([] if prev_state is None else prev_state.hist_a[:k - 1])
 
-    def aggregate(self):
-        """(K, N, F) array of z_k rows."""
+    def aggregate(self, dtype=np.float32):
+        """(K, N, F) array of z_k rows.  dtype=float64 evaluates the same fp32 inputs without rounding
+        (a conditioning yardstick for tests, not the reference arithmetic)."""
         n, f = self.hist_x[0].shape
-        z = np.zeros((self.k, n, f), dtype=np.float32)
+        z = np.zeros((self.k, n, f), dtype=dtype)
         z[0] = self.hist_x[0]
         for k in range(1, self.k):
             if k >= len(self.hist_x):
                 break
-            y = self.hist_x[k]
+            y = self.hist_x[k].astype(dtype)
             for a in self.hist_a[:k]:            # A_t first, then A_{t-1}, ...
-                y = (a.T @ y).astype(np.float32)  # (y A)[n] = sum_m A[m,n] y[m]
+                y = (a.T.astype(dtype) @ y).astype(dtype)  # (y A)[n] = sum_m A[m,n] y[m]
             z[k] = y
         return z
 
 
-def readout(layers, z_knf):
-    """Per-agent MLP on (K,N,F) aggregated features -> (N, n_a)  (actor.py:73-82)."""
+def readout(layers, z_knf, dtype=np.float32):
+    """Per-agent MLP on (K,N,F) aggregated features -> (N, n_a)  (actor.py:73-82).
+    dtype=float64: same weights/inputs evaluated without fp32 rounding (conditioning yardstick)."""
     K, N, F = z_knf.shape
     w0, b0 = layers[0]
-    x = np.einsum('gfk,knf->ng', w0, z_knf, dtype=np.float32) + b0
+    x = np.einsum('gfk,knf->ng', w0.astype(dtype), z_knf.astype(dtype), dtype=dtype) + b0.astype(dtype)
     n_layers = len(layers)
     if n_layers > 1:
-        x = np.tanh(x.astype(np.float32))
+        x = np.tanh(x.astype(dtype))
     for i in range(1, n_layers):
         w, b = layers[i]
-        x = x @ w[:, :, 0].T + b
+        x = x @ w[:, :, 0].T.astype(dtype) + b.astype(dtype)
         if i < n_layers - 1:
-            x = np.tanh(x.astype(np.float32))
-    return x.astype(np.float32)
+            x = np.tanh(x.astype(dtype))
+    return x.astype(dtype)

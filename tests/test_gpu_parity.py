@@ -20,11 +20,17 @@ def make_engine(g, **kw):
     return eng
 
 
+FFMA, TENSOR = 1, 2      # fgnn_config.readout_mode
+
+
 @pytest.mark.parametrize("name", golden_names())
 @pytest.mark.parametrize("mode", ["env_step", "teacher_forced"])
-def test_golden_trajectory(name, mode):
+@pytest.mark.parametrize("readout", [FFMA, TENSOR])
+def test_golden_trajectory(name, mode, readout):
     g = load_golden(name)
-    eng = make_engine(g)
+    if readout == TENSOR and g["hidden"] > 64:
+        pytest.skip("tensor-core readout covers hidden <= 64")
+    eng = make_engine(g, readout_mode=readout)
     eng.reset(g["x"][0])
     for t in range(g["steps"]):
         if t > 0:
@@ -79,12 +85,15 @@ def oracle_closed_loop(g, steps):
 
 
 @pytest.mark.parametrize("name", ["ckpt_n100_k3", "rand_n100_k4_h64_l2", "rand_n64_k3_h128_l4", "rand_n50_k2_h16_l3"])
-def test_closed_loop_step_and_graph_rollout(name):
+@pytest.mark.parametrize("readout", [FFMA, TENSOR])
+def test_closed_loop_step_and_graph_rollout(name, readout):
     g = load_golden(name)
+    if readout == TENSOR and g["hidden"] > 64:
+        pytest.skip("tensor-core readout covers hidden <= 64")
     T = 6
     acts_o, rew_o, x_o = oracle_closed_loop(g, T)
     # stepwise fused kernel
-    eng = make_engine(g)
+    eng = make_engine(g, readout_mode=readout)
     eng.reset(g["x"][0])
     acts, rews = [], []
     for t in range(T):
@@ -99,14 +108,14 @@ def test_closed_loop_step_and_graph_rollout(name):
     np.testing.assert_allclose(rews, rew_o, rtol=1e-5)
     x_step = eng.get_state()
     # CUDA-graph rollout must reproduce the stepwise path bit for bit
-    eng2 = make_engine(g)
+    eng2 = make_engine(g, readout_mode=readout)
     eng2.reset(g["x"][0])
     rew2 = eng2.rollout(T, want_reward=True)
     np.testing.assert_array_equal(eng2.get_state(), x_step)
     np.testing.assert_array_equal(eng2.get_action(), acts[-1])
     np.testing.assert_allclose(rew2[:, 0], rews, rtol=1e-12)
     # API-split path (policy + env_step) is the same arithmetic as the fused kernel
-    eng3 = make_engine(g)
+    eng3 = make_engine(g, readout_mode=readout)
     eng3.reset(g["x"][0])
     for t in range(T):
         a = eng3.policy().cpu().numpy()
@@ -197,9 +206,15 @@ def test_large_n_against_sparse_oracle(n, R, hidden):
         sstate = sparse.SparseDelayState(sv, a_net, prev_state=sstate, k=3)
         act_o = sparse.readout(layers, sstate.aggregate())
         act = eng.policy().cpu().numpy()
-        assert rel_inf(act, act_o) <= TOL_ACTION
         z = eng.get_aggregated()
         assert rel_inf(z, sstate.aggregate()) <= 1e-6
+        # Among 2e4+ agents some sit where fp32 rounding of |z| ~ 1e3 inputs is amplified by the trained
+        # weights (||W2|| ||W3|| ~ 40), so two correct fp32 evaluations differ by more than 1e-5 of ||a||.
+        # Yardstick: the same inputs evaluated in float64.  The CUDA path must be as close to it as the
+        # fp32 oracle (the reference arithmetic) is, or within the 1e-5 bar.
+        truth = sparse.readout(layers, sstate.aggregate(np.float64), np.float64)
+        assert rel_inf(act, truth) <= max(TOL_ACTION, 4.0 * rel_inf(act_o, truth))
+        assert rel_inf(act, act_o) <= max(TOL_ACTION, 8.0 * rel_inf(act_o, truth))
         # drive the env with the expert (DAGGER with beta = 1): keeps agents apart, so |features| stay
         # O(1e3) and the fp32 readout stays well conditioned (a random policy makes agents collide)
         u = sparse.controller_sparse(x, R).astype(np.float32)
