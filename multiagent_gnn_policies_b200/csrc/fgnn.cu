@@ -172,6 +172,7 @@ extern "C" int fgnn_create(const fgnn_config* cfg, fgnn_handle** out) {
     rc |= dalloc(h, &p.row_start, K * M);
     rc |= dalloc(h, &p.deg, K * M);
     rc |= dalloc(h, &p.cols, K * (size_t)p.nnz_cap, false);
+    rc |= dalloc(h, &p.ell, K * M * ELLW);
     rc |= dalloc(h, &p.nnz_cursor, K);
     rc |= dalloc(h, &p.overflow, 1);
     rc |= dalloc(h, &p.zbuf, K * M * ROW);
@@ -390,9 +391,10 @@ static int enqueue_hops(fgnn_handle* h, cudaStream_t st) {
     const int gb = blocks_for(p.M, 256);
     for (int j = 0; j + 2 < p.K; ++j) {     // hops 0 .. K-3 ; hop K-2 lives in the final kernel
         const int nb = p.K - 1 - j;
-        if (nb == 3) k_hop<3><<<gb, 256, 0, st>>>(p, j);
-        else if (nb == 2) k_hop<2><<<gb, 256, 0, st>>>(p, j);
-        else k_hop<1><<<gb, 256, 0, st>>>(p, j);
+        if (nb == 3) k_hop<3, true><<<gb, 256, 0, st>>>(p, j);              // K = 4, hop 0
+        else if (nb == 2 && j == 0) k_hop<2, true><<<gb, 256, 0, st>>>(p, j);   // K = 3, hop 0
+        else if (nb == 2) k_hop<2, false><<<gb, 256, 0, st>>>(p, j);           // K = 4, hop 1
+        else return fail("internal: unexpected hop shape");
         if (launch_check(h, j == 0 ? "hop0" : "hop1")) return 1;
     }
     return 0;

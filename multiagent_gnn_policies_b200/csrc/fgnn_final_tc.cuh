@@ -195,34 +195,12 @@ __global__ void __launch_bounds__(FINAL_THREADS) k_final_tc(Params p, const uint
                 const int g = slot_of(t - j, K);
                 const float* __restrict__ src = (j == 0) ? p.xhist + (size_t)slot_of(t - (K - 1), K) * M * ROW
                                                          : p.ybuf + ((size_t)((j - 1) & 1) * K + (K - 1)) * M * ROW;
-                const unsigned rs = p.row_start[(size_t)g * M + a];
-                const int d = p.deg[(size_t)g * M + a];
-                const int* __restrict__ cols = p.cols + (size_t)g * p.nnz_cap + rs;
-                const float* __restrict__ sinv = p.sinv + (size_t)g * M;
+                const float* const srcs[1] = {src};
+                float acc1[1][F];
+                gather_rows<1, (j > 0)>(p, g, a, srcs, acc1);
                 float acc[F];
 #pragma unroll
-                for (int f = 0; f < F; ++f) acc[f] = 0.f;
-                for (int e = 0; e < d; e += HOP_UNROLL) {
-                    int m[HOP_UNROLL];
-                    float sc[HOP_UNROLL];
-                    float v[HOP_UNROLL][F];
-#pragma unroll
-                    for (int u = 0; u < HOP_UNROLL; ++u) m[u] = (e + u < d) ? __ldg(&cols[e + u]) : -1;
-#pragma unroll
-                    for (int u = 0; u < HOP_UNROLL; ++u) {
-                        if (m[u] >= 0) {
-                            sc[u] = __ldg(&sinv[m[u]]);
-                            load_row6(src, m[u], v[u]);
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < HOP_UNROLL; ++u) {
-                        if (m[u] >= 0) {
-#pragma unroll
-                            for (int f = 0; f < F; ++f) acc[f] = fmaf(v[u][f], sc[u], acc[f]);
-                        }
-                    }
-                }
+                for (int f = 0; f < F; ++f) acc[f] = acc1[0][f];
 #pragma unroll
                 for (int f = 0; f < F; ++f) in[(K - 1) * F + f] = acc[f];
                 if (p.write_z_last) store_row6(p.zbuf + (size_t)(K - 1) * M * ROW, a, acc);

@@ -16,6 +16,7 @@ constexpr int LMAX = 4;       // hidden layers supported
 constexpr int FINAL_THREADS = 128;   // block size of the fused final kernel and the dense Actor kernel
 constexpr int DENSE_MT = 32;         // m-tile of the dense Actor kernel
 constexpr int RSLOTS = 64;          // reward accumulators per episode (spreads same-address atomics)
+constexpr int ELLW = 8;             // neighbours kept inline per agent: one dependent load less per gather
 constexpr int HOP_UNROLL = 4;        // edges gathered concurrently per thread in the hop loops
 
 // All device pointers one step needs.  Passed by value to every kernel.
@@ -53,6 +54,7 @@ struct Params {
     unsigned* row_start;      // [K][M]
     int* deg;                 // [K][M]
     int* cols;                // [K][nnz_cap]
+    int* ell;                 // [K][M][ELLW] first ELLW neighbours of every row, -1 padded (copy of the CSR head)
     unsigned* nnz_cursor;     // [K]
     int* overflow;            // sticky flag
 
@@ -314,17 +316,21 @@ __global__ void __launch_bounds__(256) k_canon(Params p) {
 }
 
 // ------------------------------------------------------------------------------------------
-// K_D  adjacency + degree + 6-d relative features (gym_flock compute_helpers), CSR emission.
+// K_D  adjacency + degree + 6-d relative features (gym_flock compute_helpers), CSR/ELL emission.
 //      One thread per agent, in cell-sorted order; float64 arithmetic for the radius cut and the
-//      feature sums (bit-identical edge set to the float64 oracle).  Single pass over the 3x3 cell
-//      neighbourhood (the three cells of a grid row are one contiguous slot range): accepted
-//      neighbour ids are staged in shared memory, the warp then reserves one contiguous run of edge
-//      slots for its 32 rows and flushes the staged ids; rows longer than the stage re-scan.
+//      feature sums (bit-identical edge set to the float64 oracle).
+//      Phase 1 (filter): scan the 3x3 cell neighbourhood (the three cells of a grid row are one
+//        contiguous slot range), stage the slots of accepted neighbours in shared memory.
+//      Phase 2 (compute): loop over the staged neighbours only -- the divide-heavy feature math is
+//        not executed under the divergent accept branch of the candidate loop.
+//      The warp reserves one contiguous run of CSR edge slots for its 32 rows; the first ELLW
+//      neighbour ids are also stored inline per agent (ELL head).  Rows longer than the stage
+//      re-scan their tail.
 // ------------------------------------------------------------------------------------------
 constexpr int ADJ_THREADS = 128;
 
 __global__ void __launch_bounds__(ADJ_THREADS) k_adjacency(Params p, int stage_cap) {
-    extern __shared__ int s_stage[];                      // [stage_cap][ADJ_THREADS]
+    extern __shared__ int s_stage[];                      // [stage_cap][ADJ_THREADS] slots of accepted neighbours
     const int tid = threadIdx.x;
     const int s = blockIdx.x * ADJ_THREADS + tid;
     const int lane = tid & 31;
@@ -339,7 +345,6 @@ __global__ void __launch_bounds__(ADJ_THREADS) k_adjacency(Params p, int stage_c
     double4 me = make_double4(0, 0, 0, 0);
     int q0[9], q1[9];
     int count = 0;
-    double f0 = 0, f1 = 0, f2 = 0, f3 = 0, f4 = 0, f5 = 0;
     if (valid) {
         a = p.sorted_id[s];
         me = p.sorted_state[s];
@@ -366,19 +371,10 @@ __global__ void __launch_bounds__(ADJ_THREADS) k_adjacency(Params p, int stage_c
 #pragma unroll
         for (int j = 0; j < 9; ++j) {
             for (int q = q0[j]; q < q1[j]; ++q) {
-                const double4 o = p.sorted_state[q];
-                const double dx = me.x - o.x, dy = me.y - o.y;
-                const double r2 = r2_exact(dx, dy);
+                const double2 o = *reinterpret_cast<const double2*>(&p.sorted_state[q]);
+                const double r2 = r2_exact(me.x - o.x, me.y - o.y);
                 if (q != s && r2 < p.R2) {
-                    const double inv = 1.0 / r2;
-                    const double inv2 = inv * inv;
-                    f0 += me.z - o.z;
-                    f1 += dx * inv2;
-                    f2 += dx * inv;
-                    f3 += me.w - o.w;
-                    f4 += dy * inv2;
-                    f5 += dy * inv;
-                    if (count < stage_cap) s_stage[count * ADJ_THREADS + tid] = __ldg(&p.sorted_id[q]);
+                    if (count < stage_cap) s_stage[count * ADJ_THREADS + tid] = q;
                     ++count;
                 }
             }
@@ -403,38 +399,153 @@ __global__ void __launch_bounds__(ADJ_THREADS) k_adjacency(Params p, int stage_c
         row = 0;
     }
     int* cols = p.cols + (size_t)g * p.nnz_cap + row;
+    int head[ELLW];
+#pragma unroll
+    for (int e = 0; e < ELLW; ++e) head[e] = -1;
+    double f0 = 0, f1 = 0, f2 = 0, f3 = 0, f4 = 0, f5 = 0;
     const int staged = count < stage_cap ? count : stage_cap;
-    for (int e = 0; e < staged; ++e) cols[e] = s_stage[e * ADJ_THREADS + tid];
+    for (int e = 0; e < staged; ++e) {
+        const int q = s_stage[e * ADJ_THREADS + tid];
+        const double4 o = p.sorted_state[q];
+        const int id = __ldg(&p.sorted_id[q]);
+        const double dx = me.x - o.x, dy = me.y - o.y;
+        const double r2 = r2_exact(dx, dy);
+        const double inv = 1.0 / r2;
+        const double inv2 = inv * inv;
+        f0 += me.z - o.z;
+        f1 += dx * inv2;
+        f2 += dx * inv;
+        f3 += me.w - o.w;
+        f4 += dy * inv2;
+        f5 += dy * inv;
+        cols[e] = id;
+#pragma unroll
+        for (int u = 0; u < ELLW; ++u)
+            if (u == e) head[u] = id;
+    }
     if (count > stage_cap) {                              // long row: re-scan for the tail (same order)
         int w = 0;
 #pragma unroll
         for (int j = 0; j < 9; ++j) {
             for (int q = q0[j]; q < q1[j]; ++q) {
-                const double2 o = *reinterpret_cast<const double2*>(&p.sorted_state[q]);
-                const double r2 = r2_exact(me.x - o.x, me.y - o.y);
+                const double4 o = p.sorted_state[q];
+                const double dx = me.x - o.x, dy = me.y - o.y;
+                const double r2 = r2_exact(dx, dy);
                 if (q != s && r2 < p.R2) {
-                    if (w >= stage_cap) cols[w] = __ldg(&p.sorted_id[q]);
+                    if (w >= stage_cap) {
+                        const double inv = 1.0 / r2;
+                        const double inv2 = inv * inv;
+                        f0 += me.z - o.z;
+                        f1 += dx * inv2;
+                        f2 += dx * inv;
+                        f3 += me.w - o.w;
+                        f4 += dy * inv2;
+                        f5 += dy * inv;
+                        cols[w] = __ldg(&p.sorted_id[q]);
+                    }
                     ++w;
                 }
             }
         }
     }
-    float* xr = p.xhist + ((size_t)g * p.M + a) * ROW;
+    const size_t ga = (size_t)g * p.M + a;
+    int4* ellp = reinterpret_cast<int4*>(p.ell + ga * ELLW);
+    ellp[0] = make_int4(head[0], head[1], head[2], head[3]);
+    ellp[1] = make_int4(head[4], head[5], head[6], head[7]);
+    float* xr = p.xhist + ga * ROW;
     reinterpret_cast<float4*>(xr)[0] = make_float4((float)f0, (float)f1, (float)f2, (float)f3);
     reinterpret_cast<float4*>(xr)[1] = make_float4((float)f4, (float)f5, 0.f, 0.f);
-    p.deg[(size_t)g * p.M + a] = count;
-    p.row_start[(size_t)g * p.M + a] = row;
-    p.sinv[(size_t)g * p.M + a] = p.mean_pooling ? (float)(1.0 / (double)(count > 0 ? count : 1)) : 1.0f;
+    p.deg[ga] = count;
+    p.row_start[ga] = row;
+    p.sinv[ga] = p.mean_pooling ? (float)(1.0 / (double)(count > 0 ? count : 1)) : 1.0f;
 }
 
 #endif  // FGNN_MAIN_TU
 
 // ------------------------------------------------------------------------------------------
+// Neighbour gather shared by the hop kernels and the fused final kernel:
+//   acc[b][:] = sum_{m in N_g(a)} src[b][m][:] * (PRESCALED ? 1 : sinv_g[m])      (in row order)
+// Row metadata (deg, row_start) and the first ELLW column indices come from per-agent arrays, so the
+// row gathers start after ONE dependent load; rows longer than ELLW continue from the CSR array.
+// ------------------------------------------------------------------------------------------
+template <int NB, bool PRESCALED>
+__device__ __forceinline__ void gather_rows(const Params& p, int g, int a, const float* const (&src)[NB],
+                                            float (&acc)[NB][F]) {
+    const size_t M = p.M;
+    const int d = __ldg(&p.deg[(size_t)g * M + a]);
+    const unsigned rs = __ldg(&p.row_start[(size_t)g * M + a]);
+    const int4* ellp = reinterpret_cast<const int4*>(p.ell + ((size_t)g * M + a) * ELLW);
+    const int4 c0 = __ldg(ellp), c1 = __ldg(ellp + 1);
+    const float* __restrict__ sinv = p.sinv + (size_t)g * M;
+    const int head[ELLW] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+#pragma unroll
+    for (int b = 0; b < NB; ++b)
+#pragma unroll
+        for (int f = 0; f < F; ++f) acc[b][f] = 0.f;
+#pragma unroll
+    for (int e0 = 0; e0 < ELLW; e0 += HOP_UNROLL) {
+        if (e0 < d) {
+            float sc[HOP_UNROLL];
+            float v[HOP_UNROLL][NB][F];
+#pragma unroll
+            for (int u = 0; u < HOP_UNROLL; ++u) {
+                const int m = head[e0 + u];
+                if (m >= 0) {
+                    sc[u] = PRESCALED ? 1.f : __ldg(&sinv[m]);
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) load_row6(src[b], m, v[u][b]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < HOP_UNROLL; ++u) {
+                if (head[e0 + u] >= 0) {
+#pragma unroll
+                    for (int b = 0; b < NB; ++b)
+#pragma unroll
+                        for (int f = 0; f < F; ++f)
+                            acc[b][f] = PRESCALED ? acc[b][f] + v[u][b][f] : fmaf(v[u][b][f], sc[u], acc[b][f]);
+                }
+            }
+        }
+    }
+    if (d > ELLW) {                                       // long rows: the tail lives in the CSR array
+        const int* __restrict__ cols = p.cols + (size_t)g * p.nnz_cap + rs;
+        for (int e = ELLW; e < d; e += HOP_UNROLL) {
+            int m[HOP_UNROLL];
+            float sc[HOP_UNROLL];
+            float v[HOP_UNROLL][NB][F];
+#pragma unroll
+            for (int u = 0; u < HOP_UNROLL; ++u) m[u] = (e + u < d) ? __ldg(&cols[e + u]) : -1;
+#pragma unroll
+            for (int u = 0; u < HOP_UNROLL; ++u) {
+                if (m[u] >= 0) {
+                    sc[u] = PRESCALED ? 1.f : __ldg(&sinv[m[u]]);
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) load_row6(src[b], m[u], v[u][b]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < HOP_UNROLL; ++u) {
+                if (m[u] >= 0) {
+#pragma unroll
+                    for (int b = 0; b < NB; ++b)
+#pragma unroll
+                        for (int f = 0; f < F; ++f)
+                            acc[b][f] = PRESCALED ? acc[b][f] + v[u][b][f] : fmaf(v[u][b][f], sc[u], acc[b][f]);
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // K_E  graph-shift hop j (not the last one): for taps k = j+1 .. K-1
 //      Y_k <- Y_k * A_{t-j}   i.e.  out_k[n] = sum_{m in N_{t-j}(n)} in_k[m] * sinv_{t-j}[m]
 //      in_k = x_{t-k} (j == 0) or the previous hop's intermediate; tap k = j+1 is finished (z_k).
+//      Intermediates are stored PRE-SCALED by the source scale of the next hop's graph,
+//      sinv_{t-j-1}[n], so the consumer gathers one 32-byte row per edge and nothing else.
 // ------------------------------------------------------------------------------------------
-template <int NB>
+template <int NB, bool FIRST>
 __global__ void __launch_bounds__(256) k_hop(Params p, int j) {
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= p.M) return;
@@ -446,46 +557,22 @@ __global__ void __launch_bounds__(256) k_hop(Params p, int j) {
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
         int k = j + 1 + b;
-        src[b] = (j == 0) ? p.xhist + (size_t)slot_of(t - k, p.K) * M * ROW
-                          : p.ybuf + ((size_t)((j - 1) & 1) * p.K + k) * M * ROW;
+        src[b] = FIRST ? p.xhist + (size_t)slot_of(t - k, p.K) * M * ROW
+                       : p.ybuf + ((size_t)((j - 1) & 1) * p.K + k) * M * ROW;
         dst[b] = (b == 0) ? p.zbuf + (size_t)k * M * ROW : p.ybuf + ((size_t)(j & 1) * p.K + k) * M * ROW;
     }
-    const unsigned rs = p.row_start[(size_t)g * M + a];
-    const int d = p.deg[(size_t)g * M + a];
-    const int* __restrict__ cols = p.cols + (size_t)g * p.nnz_cap + rs;
-    const float* __restrict__ sinv = p.sinv + (size_t)g * M;
     float acc[NB][F];
+    gather_rows<NB, !FIRST>(p, g, a, src, acc);
+    store_row6(dst[0], a, acc[0]);
+    if (NB > 1) {
+        const float sn = __ldg(&p.sinv[(size_t)slot_of(t - j - 1, p.K) * M + a]);
 #pragma unroll
-    for (int b = 0; b < NB; ++b)
+        for (int b = 1; b < NB; ++b) {
 #pragma unroll
-        for (int f = 0; f < F; ++f) acc[b][f] = 0.f;
-    // edges in chunks of HOP_UNROLL: all indices, then all row gathers in flight, then in-order accumulation
-    for (int e = 0; e < d; e += HOP_UNROLL) {
-        int m[HOP_UNROLL];
-        float sc[HOP_UNROLL];
-        float v[HOP_UNROLL][NB][F];
-#pragma unroll
-        for (int u = 0; u < HOP_UNROLL; ++u) m[u] = (e + u < d) ? __ldg(&cols[e + u]) : -1;
-#pragma unroll
-        for (int u = 0; u < HOP_UNROLL; ++u) {
-            if (m[u] >= 0) {
-                sc[u] = __ldg(&sinv[m[u]]);
-#pragma unroll
-                for (int b = 0; b < NB; ++b) load_row6(src[b], m[u], v[u][b]);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < HOP_UNROLL; ++u) {
-            if (m[u] >= 0) {
-#pragma unroll
-                for (int b = 0; b < NB; ++b)
-#pragma unroll
-                    for (int f = 0; f < F; ++f) acc[b][f] = fmaf(v[u][b][f], sc[u], acc[b][f]);
-            }
+            for (int f = 0; f < F; ++f) acc[b][f] *= sn;
+            store_row6(dst[b], a, acc[b]);
         }
     }
-#pragma unroll
-    for (int b = 0; b < NB; ++b) store_row6(dst[b], a, acc[b]);
 }
 
 // double integrator exactly in numpy's evaluation order (no FMA contraction), then bin the new position
