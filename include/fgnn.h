@@ -91,6 +91,12 @@ int fgnn_env_step(fgnn_handle* h, const float* u_bn2, double* reward_b, void* st
  * history the engine keeps: K-hop aggregation + readout.  action_bn2 (B*N,2) fp32 [h/d]. */
 int fgnn_policy(fgnn_handle* h, float* action_bn2, void* stream);
 
+/* env.env.controller(centralized) (learner/gnn_dagger.py:156, learner/gnn_baseline.py:16): expert
+ * potential-based action for the CURRENT state/graph, (B*N,2) fp32 [h/d] in action units (already
+ * clipped to +-max_accel and divided by the gain).  centralized != 0: velocity term over all agents
+ * of the episode, potential term inside its own cut-off (r^2 <= comm_radius). */
+int fgnn_controller(fgnn_handle* h, int32_t centralized, double max_accel, float* u_bn2, void* stream);
+
 /* One closed-loop rollout step (learner/gnn_dagger.py:196-201, test_model.py:38-45):
  * select_action -> env.step(action).  action_bn2 / reward_b may be NULL. */
 int fgnn_step(fgnn_handle* h, float* action_bn2, double* reward_b, void* stream);

@@ -692,6 +692,31 @@ extern "C" int fgnn_get_stats(fgnn_handle* h, fgnn_stats* out, void* stream) {
     return 0;
 }
 
+extern "C" int fgnn_controller(fgnn_handle* h, int32_t centralized, double max_accel, float* u, void* stream) {
+    if (!h || !u) return fail("fgnn_controller: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    Params& p = h->p;
+    CK(cudaSetDevice(h->cfg.device));
+    if (h->binned) return fail("fgnn_controller: state was integrated but the graph not rebuilt");
+    double* vsum = reinterpret_cast<double*>(h->d_staging);      // [B][2], staging is at least M*8 floats
+    if ((size_t)p.B * 2 * sizeof(double) > (size_t)p.M * 8 * sizeof(float)) return fail("fgnn_controller: staging too small");
+    if (centralized) {
+        CK(cudaMemsetAsync(vsum, 0, (size_t)p.B * 2 * sizeof(double), st));
+        k_vel_sum<<<blocks_for(p.M, 256), 256, 0, st>>>(p, vsum);
+        if (launch_check(h, "vel_sum")) return 1;
+    }
+    const double R = h->cfg.comm_radius;
+    const double cell = 1.0 / p.inv_cell;
+    // decentralised: neighbours are inside the 3x3 window; centralised: potential cut-off sqrt(R)
+    int window = 1;
+    if (centralized) window = (int)std::ceil(std::sqrt(R) / cell - 1e-12);
+    if (window < 1) window = 1;
+    k_controller<<<blocks_for(p.M, 128), 128, 0, st>>>(p, centralized ? 1 : 0, window, R, max_accel * p.gain, vsum,
+                                                        h->d_u_in);
+    if (launch_check(h, "controller")) return 1;
+    return copy_out(u, h->d_u_in, (size_t)p.M * 2 * sizeof(float), st);
+}
+
 extern "C" int fgnn_profile_step(fgnn_handle* h, int32_t max_kernels, float* ms_out, char* names_out, int32_t* n_out,
                                  void* stream) {
     if (!h || !ms_out || !n_out) return fail("fgnn_profile_step: null argument");

@@ -680,6 +680,73 @@ __global__ void k_export_dense(Params p, int g, float* __restrict__ out) {
     for (int e = 0; e < d; ++e) row[cols[e] % p.N] = sc;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Expert controller (gym_flock FlockingRelativeEnv.controller):
+//   u_i = -sum_j [ grad(dp_ij, r2_ij) * 1(r2_ij <= comm_radius) + dv_ij ] over j in the mask,
+//   grad(d, r2) = -2 d / r2^2 + 2 d / r2;  mask = radius neighbours (decentralised) or every other
+//   agent of the episode (centralised); clipped to +-max_accel*gain and divided by gain.
+// Runs on the cell structure of the CURRENT graph (sorted_state / cell_start), float64.
+// Centralised: the velocity term over all agents is N v_i - sum_j v_j (per-episode sums, k_vel_sum);
+// the potential term has a finite cut-off sqrt(comm_radius) and is found by a (2w+1)^2 cell search.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_vel_sum(Params p, double* __restrict__ vsum /* [B][2] */) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= p.M) return;
+    const double4 s = p.state[a];
+    const int ep = a / p.N;
+    atomicAdd(&vsum[ep * 2 + 0], s.z);
+    atomicAdd(&vsum[ep * 2 + 1], s.w);
+}
+
+__global__ void __launch_bounds__(128) k_controller(Params p, int centralized, int window, double grad_cut /* comm_radius */,
+                                                    double max_u, const double* __restrict__ vsum, float* __restrict__ out) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= p.M) return;
+    const int a = p.sorted_id[s];
+    const double4 me = p.sorted_state[s];
+    const int ep = a / p.N;
+    long long ix, iy;
+    cell_coords(p, me.x, me.y, ix, iy);
+    double gx = 0, gy = 0, dvx = 0, dvy = 0;
+    // distinct wrapped cells only: a window wider than the grid would visit cells twice
+    const int span = 2 * window + 1 <= p.G ? 2 * window + 1 : p.G;
+    const long long x0 = 2 * window + 1 <= p.G ? ix - window : 0;
+    const long long y0 = 2 * window + 1 <= p.G ? iy - window : 0;
+    for (int ry = 0; ry < span; ++ry) {
+        for (int rx = 0; rx < span; ++rx) {
+            const int c = cell_index(p, ep, x0 + rx, y0 + ry);
+            const int q0 = __ldg(&p.cell_start[c]), q1 = __ldg(&p.cell_start[c + 1]);
+            for (int q = q0; q < q1; ++q) {
+                if (q == s) continue;
+                const double4 o = p.sorted_state[q];
+                const double dx = me.x - o.x, dy = me.y - o.y;
+                const double r2 = r2_exact(dx, dy);
+                const bool nb = r2 < p.R2;
+                if (!centralized && !nb) continue;
+                if (!(r2 > grad_cut)) {
+                    const double inv = 1.0 / r2;
+                    const double gsc = -2.0 * inv * inv + 2.0 * inv;
+                    gx += dx * gsc;
+                    gy += dy * gsc;
+                }
+                if (!centralized) {
+                    dvx += me.z - o.z;
+                    dvy += me.w - o.w;
+                }
+            }
+        }
+    }
+    if (centralized) {
+        dvx = (double)p.N * me.z - vsum[ep * 2 + 0];
+        dvy = (double)p.N * me.w - vsum[ep * 2 + 1];
+    }
+    double ux = -gx - dvx, uy = -gy - dvy;
+    ux = fmin(fmax(ux, -max_u), max_u) / p.gain;
+    uy = fmin(fmax(uy, -max_u), max_u) / p.gain;
+    reinterpret_cast<float2*>(out)[a] = make_float2((float)ux, (float)uy);
+}
+
 #endif  // FGNN_MAIN_TU
 
 }  // namespace fgnn

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libfgnn.so")
 
 ABI_SYMBOLS = [
     "fgnn_last_error", "fgnn_version", "fgnn_create", "fgnn_destroy", "fgnn_set_weights", "fgnn_reset",
-    "fgnn_set_state", "fgnn_build_graph", "fgnn_integrate", "fgnn_env_step", "fgnn_policy", "fgnn_step",
+    "fgnn_set_state", "fgnn_build_graph", "fgnn_integrate", "fgnn_env_step", "fgnn_policy", "fgnn_controller", "fgnn_step",
     "fgnn_rollout", "fgnn_actor_forward_dense", "fgnn_get_state", "fgnn_get_features", "fgnn_get_degrees",
     "fgnn_get_aggregated", "fgnn_get_action", "fgnn_export_network_dense", "fgnn_get_csr", "fgnn_get_stats",
     "fgnn_profile_step", "fgnn_memcpy_sync", "fgnn_launch_count",
@@ -69,6 +69,7 @@ def load_library(path=None):
     lib.fgnn_integrate.argtypes = [vp, vp, vp, vp]
     lib.fgnn_env_step.argtypes = [vp, vp, vp, vp]
     lib.fgnn_policy.argtypes = [vp, vp, vp]
+    lib.fgnn_controller.argtypes = [vp, i32, ctypes.c_double, vp, vp]
     lib.fgnn_step.argtypes = [vp, vp, vp, vp]
     lib.fgnn_rollout.argtypes = [vp, i32, vp, vp]
     lib.fgnn_actor_forward_dense.argtypes = [vp, i32, i32, vp, vp, vp, vp]
@@ -136,6 +137,7 @@ class FlockEngine:
                          self.comm_radius, self.dt, self.action_scalar)
         self._h = ctypes.c_void_p()
         self._check(self.lib.fgnn_create(ctypes.byref(cfg), ctypes.byref(self._h)))
+        self.step_index = -1          # host mirror of the engine's step counter t (-1: never reset)
 
     # -- plumbing ---------------------------------------------------------------------------
     def _check(self, rc):
@@ -189,6 +191,7 @@ class FlockEngine:
     def reset(self, x):
         x = self._as_state(x)
         self._check(self.lib.fgnn_reset(self._h, _ptr(x), self.stream))
+        self.step_index = 0
         if isinstance(x, np.ndarray):
             self.sync()
 
@@ -200,6 +203,7 @@ class FlockEngine:
 
     def build_graph(self, advance=True):
         self._check(self.lib.fgnn_build_graph(self._h, int(bool(advance)), self.stream))
+        self.step_index += int(bool(advance))
 
     def _as_action(self, u):
         if hasattr(u, "data_ptr"):
@@ -222,6 +226,7 @@ class FlockEngine:
         u = self._as_action(u)
         r = np.empty(self.n_episodes, dtype=np.float64)
         self._check(self.lib.fgnn_env_step(self._h, _ptr(u), _ptr(r), self.stream))
+        self.step_index += 1
         self.sync()
         return r
 
@@ -236,15 +241,26 @@ class FlockEngine:
             self.sync()
         return out
 
+    def controller(self, centralized=True, max_accel=1.0, out=None):
+        """Expert controller action (B*N,2) fp32 for the current state (env.env.controller)."""
+        if out is None:
+            out = np.empty((self.M, 2), dtype=np.float32)
+        self._check(self.lib.fgnn_controller(self._h, int(bool(centralized)), float(max_accel), _ptr(out), self.stream))
+        if isinstance(out, np.ndarray):
+            self.sync()
+        return out
+
     def step(self, action_out=None, reward_out=None):
         """One closed-loop step (select_action -> env.step).  Outputs optional, see ``policy``."""
         self._check(self.lib.fgnn_step(self._h, _ptr(action_out), _ptr(reward_out), self.stream))
+        self.step_index += 1
         if isinstance(action_out, np.ndarray) or isinstance(reward_out, np.ndarray):
             self.sync()
 
     def rollout(self, steps, want_reward=False):
         r = np.empty((steps, self.n_episodes), dtype=np.float64) if want_reward else None
         self._check(self.lib.fgnn_rollout(self._h, int(steps), _ptr(r), self.stream))
+        self.step_index += int(steps)
         if want_reward:
             self.sync()
         return r
@@ -333,6 +349,7 @@ class FlockEngine:
         n = ctypes.c_int32(0)
         self._check(self.lib.fgnn_profile_step(self._h, 16, ctypes.addressof(ms), ctypes.addressof(names),
                                                ctypes.byref(n), self.stream))
+        self.step_index += 1
         return [(names.raw[16 * i:16 * i + 16].split(b"\0")[0].decode(), float(ms[i])) for i in range(n.value)]
 
     def launch_count(self):
