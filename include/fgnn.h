@@ -39,6 +39,10 @@ typedef struct fgnn_config {
     int32_t grid_dim;        /* cells per side of the wrapped cell grid, 0 = auto             */
     int32_t edge_capacity;   /* directed-edge capacity per agent (mean), 0 = auto (48)        */
     int32_t readout_mode;    /* 0 = auto, 1 = FFMA (CUDA cores), 2 = tensor cores (3xTF32)    */
+    int32_t grid_dim_y;      /* cells along y, 0 = same as grid_dim                           */
+    int32_t shard_lo;        /* multi-GPU: first agent this rank owns ...                     */
+    int32_t shard_count;     /* ... and how many (0 = all: single-GPU)                        */
+    int32_t ghost_capacity;  /* multi-GPU: max agents received from other ranks per step      */
     int32_t reserved0;
     double  comm_radius;     /* R                                (cfg key comm_radius)        */
     double  dt;              /*                                  (cfg key dt)                 */
@@ -121,6 +125,21 @@ int fgnn_export_network_dense(fgnn_handle* h, int32_t age, float* network_bnn, v
 int fgnn_get_csr(fgnn_handle* h, int32_t age, const uint32_t** row_start, const int32_t** deg,
                  const int32_t** cols, const float** src_scale);
 int fgnn_get_stats(fgnn_handle* h, fgnn_stats* out, void* stream);   /* synchronises the stream */
+
+/* ---- multi-GPU (agents sharded by index, n_episodes == 1; every rank holds full-size arrays) ----
+ * One closed-loop step on a rank =  fgnn_shard_local_step  (K-hop aggregation over the agents present on
+ * the rank, readout + integrator for the OWNED agents)  ->  fgnn_shard_pack (owned agents inside another
+ * rank's x-window -> send buffer)  ->  all-gather of the buffers by the host (NCCL)  ->
+ * fgnn_shard_unpack (install received states as ghosts)  ->  fgnn_build_graph(advance = 1).
+ * Buffers are DEVICE arrays of doubles: per rank (cap + 1) records of 5 doubles; record 0 is the header
+ * [count, x_lo, x_hi, 0, 0] (the rank's own x-interval), records 1..count are [agent id, px, py, vx, vy].
+ * `windows` is a device array holding every rank's [x_lo, x_hi] at windows[q * window_stride + {0, 1}]
+ * (so the headers of the previous step's gathered buffer can be passed directly). */
+int fgnn_shard_local_step(fgnn_handle* h, void* stream);
+int fgnn_shard_pack(fgnn_handle* h, const double* windows, int64_t window_stride, int32_t world, int32_t rank,
+                    double depth, double* send_buf, int32_t cap, void* stream);
+int fgnn_shard_unpack(fgnn_handle* h, const double* recv_buf, int32_t world, int32_t rank, int32_t cap,
+                      double depth, void* stream);
 
 /* One closed-loop step (same work as fgnn_step) with a CUDA event after every kernel: ms_out[i] is the
  * device time of kernel i, names_out (16 bytes each, may be NULL) its name.  For bench.py's roofline. */

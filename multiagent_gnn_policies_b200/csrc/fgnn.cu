@@ -57,6 +57,12 @@ struct fgnn_handle {
     size_t tc_smem = 0;
     int tc_grid_closed = 0, tc_grid_open = 0;
     std::vector<std::vector<float>> raw_w, raw_b;   // per layer, reference layout
+    // sharding
+    bool sharded = false;
+    int* d_pool = nullptr;
+    int* d_n_pool = nullptr;
+    int* d_pack_counter = nullptr;
+    int launch_pool = 0;             // grid sizing for kernels over the pool (pool capacity, or M)
     // per-kernel profiling of one step (fgnn_profile_step)
     bool profiling = false;
     cudaStream_t prof_stream = nullptr;
@@ -138,10 +144,23 @@ extern "C" int fgnn_create(const fgnn_config* cfg, fgnn_handle** out) {
     Params& p = h->p;
     memset(&p, 0, sizeof p);
     p.M = (int)M64; p.N = cfg->n_agents; p.B = cfg->n_episodes; p.K = cfg->k; p.L = cfg->n_layers;
-    int G = cfg->grid_dim > 0 ? cfg->grid_dim : (int)std::ceil(std::sqrt((double)cfg->n_agents));
+    h->sharded = cfg->shard_count > 0;
+    if (h->sharded) {
+        if (cfg->n_episodes != 1) return fail("fgnn_create: sharding needs n_episodes == 1");
+        if (cfg->shard_lo < 0 || (long long)cfg->shard_lo + cfg->shard_count > M64) return fail("fgnn_create: shard range outside the agents");
+        if (cfg->ghost_capacity < 0) return fail("fgnn_create: ghost_capacity < 0");
+    }
+    const long long n_local = h->sharded ? (long long)cfg->shard_count + cfg->ghost_capacity : (long long)cfg->n_agents;
+    int G = cfg->grid_dim > 0 ? cfg->grid_dim : (int)std::ceil(std::sqrt((double)n_local));
     if (G < 3) G = 3;
-    if ((long long)G * G * cfg->n_episodes > (1ll << 30)) return fail("fgnn_create: cell grid too large");
-    p.G = G; p.C = G * G * cfg->n_episodes;
+    int Gy = cfg->grid_dim_y > 0 ? cfg->grid_dim_y : G;
+    if (Gy < 3) Gy = 3;
+    if ((long long)G * Gy * cfg->n_episodes > (1ll << 30)) return fail("fgnn_create: cell grid too large");
+    p.G = G; p.Gy = Gy; p.C = G * Gy * cfg->n_episodes;
+    p.a_lo = h->sharded ? cfg->shard_lo : 0;
+    p.n_own = h->sharded ? cfg->shard_count : (int)M64;
+    p.pool_cap = h->sharded ? (int)n_local : (int)M64;
+    h->launch_pool = p.pool_cap;
     p.mean_pooling = cfg->mean_pooling; p.half_accel = cfg->half_accel_term;
     const long long cap_per = cfg->edge_capacity > 0 ? cfg->edge_capacity : 48;
     long long cap = cap_per * M64;
@@ -184,6 +203,13 @@ extern "C" int fgnn_create(const fgnn_config* cfg, fgnn_handle** out) {
     rc |= dalloc(h, &p.reward, (size_t)p.B);
     rc |= dalloc(h, &p.reward_pending, 1);
     rc |= dalloc(h, &p.log_index, 1);
+    if (h->sharded) {
+        rc |= dalloc(h, &h->d_pool, (size_t)p.pool_cap);
+        rc |= dalloc(h, &h->d_n_pool, 1);
+        rc |= dalloc(h, &h->d_pack_counter, 1);
+        p.pool = h->d_pool;
+        p.n_pool = h->d_n_pool;
+    }
     rc |= dalloc(h, &h->d_u_in, M * 2);
     rc |= dalloc(h, &h->d_staging, K * M * F > (size_t)M * 4 * 2 ? K * M * F : (size_t)M * 4 * 2);
     WeightLayout wl{F * p.K, h->HP, p.L};
@@ -203,7 +229,7 @@ extern "C" int fgnn_create(const fgnn_config* cfg, fgnn_handle** out) {
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)fk, FINAL_THREADS, h->final_smem));
         if (occ < 1) occ = 1;
         int grid = h->sm_count * occ;
-        int tiles = blocks_for(p.M, FINAL_THREADS);
+        int tiles = blocks_for(p.n_own, FINAL_THREADS);
         if (grid > tiles) grid = tiles;
         (closed ? h->final_grid_closed : h->final_grid_open) = grid;
     }
@@ -240,7 +266,7 @@ extern "C" int fgnn_create(const fgnn_config* cfg, fgnn_handle** out) {
             const int max_by_tmem = 512 / tc_tmem_cols(h->HP);
             if (occ > max_by_tmem) occ = max_by_tmem;
             int grid = h->sm_count * occ;
-            int tiles = blocks_for(p.M, FINAL_THREADS);
+            int tiles = blocks_for(p.n_own, FINAL_THREADS);
             if (grid > tiles) grid = tiles;
             (closed ? h->tc_grid_closed : h->tc_grid_open) = grid;
         }
@@ -368,9 +394,10 @@ static int launch_check(fgnn_handle* h, const char* name) {
 // bin (if needed) -> scan -> scatter -> canon -> adjacency
 static int enqueue_build(fgnn_handle* h, int advance, cudaStream_t st) {
     Params& p = h->p;
-    const int gb = blocks_for(p.M, 256);
+    const int gb = blocks_for(h->launch_pool, 256);
     if (!h->binned) {
-        k_bin<<<gb, 256, 0, st>>>(p);
+        if (h->sharded) return fail("sharded engine: the graph is built after fgnn_shard_unpack (state not binned)");
+        k_bin<<<gb, 256, 0, st>>>(p, 0);
         if (launch_check(h, "bin")) return 1;
     }
     k_scan<<<p.n_tiles, SCAN_THREADS, 0, st>>>(p, advance);
@@ -379,7 +406,7 @@ static int enqueue_build(fgnn_handle* h, int advance, cudaStream_t st) {
     if (launch_check(h, "scatter")) return 1;
     k_canon<<<gb, 256, 0, st>>>(p);
     if (launch_check(h, "canon")) return 1;
-    k_adjacency<<<blocks_for(p.M, ADJ_THREADS), ADJ_THREADS, (size_t)h->adj_stage * ADJ_THREADS * sizeof(int), st>>>(p, h->adj_stage);
+    k_adjacency<<<blocks_for(h->launch_pool, ADJ_THREADS), ADJ_THREADS, (size_t)h->adj_stage * ADJ_THREADS * sizeof(int), st>>>(p, h->adj_stage);
     if (launch_check(h, "adjacency")) return 1;
     h->binned = false;
     if (advance) h->t_host += 1;
@@ -388,7 +415,7 @@ static int enqueue_build(fgnn_handle* h, int advance, cudaStream_t st) {
 
 static int enqueue_hops(fgnn_handle* h, cudaStream_t st) {
     Params& p = h->p;
-    const int gb = blocks_for(p.M, 256);
+    const int gb = blocks_for(h->launch_pool, 256);
     for (int j = 0; j + 2 < p.K; ++j) {     // hops 0 .. K-3 ; hop K-2 lives in the final kernel
         const int nb = p.K - 1 - j;
         if (nb == 3) k_hop<3, true><<<gb, 256, 0, st>>>(p, j);              // K = 4, hop 0
@@ -462,6 +489,15 @@ extern "C" int fgnn_reset(fgnn_handle* h, const double* x, void* stream) {
     h->binned = false;
     h->t_host = 0;
     CK(cudaMemcpyAsync(p.state, x, M * sizeof(double4), cudaMemcpyDefault, st));
+    if (h->sharded) {
+        // owned agents are binned here; ghosts arrive through fgnn_shard_pack/unpack, then fgnn_build_graph(0)
+        k_pool_init<<<blocks_for(p.n_own, 256), 256, 0, st>>>(p, h->d_pool, h->d_n_pool, h->d_pack_counter);
+        if (launch_check(h, "pool_init")) return 1;
+        k_bin<<<blocks_for(p.n_own, 256), 256, 0, st>>>(p, 0);
+        if (launch_check(h, "bin")) return 1;
+        h->binned = true;
+        return 0;
+    }
     return enqueue_build(h, 0, st);
 }
 
@@ -481,7 +517,7 @@ extern "C" int fgnn_integrate(fgnn_handle* h, const float* u, double* reward_b, 
         CK(cudaMemsetAsync(p.racc, 0, (size_t)RSLOTS * p.B * 4 * sizeof(double), st));
     }
     CK(cudaMemcpyAsync(h->d_u_in, u, (size_t)p.M * 2 * sizeof(float), cudaMemcpyDefault, st));
-    k_integrate<<<blocks_for(p.M, 256), 256, 0, st>>>(p, h->d_u_in);
+    k_integrate<<<blocks_for(p.n_own, 256), 256, 0, st>>>(p, h->d_u_in);
     if (launch_check(h, "integrate")) return 1;
     h->binned = true;
     if (reward_b) {
@@ -711,10 +747,50 @@ extern "C" int fgnn_controller(fgnn_handle* h, int32_t centralized, double max_a
     int window = 1;
     if (centralized) window = (int)std::ceil(std::sqrt(R) / cell - 1e-12);
     if (window < 1) window = 1;
-    k_controller<<<blocks_for(p.M, 128), 128, 0, st>>>(p, centralized ? 1 : 0, window, R, max_accel * p.gain, vsum,
+    k_controller<<<blocks_for(h->launch_pool, 128), 128, 0, st>>>(p, centralized ? 1 : 0, window, R, max_accel * p.gain, vsum,
                                                         h->d_u_in);
     if (launch_check(h, "controller")) return 1;
     return copy_out(u, h->d_u_in, (size_t)p.M * 2 * sizeof(float), st);
+}
+
+extern "C" int fgnn_shard_local_step(fgnn_handle* h, void* stream) {
+    if (!h || !h->sharded) return fail("fgnn_shard_local_step: handle is not sharded");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(h->cfg.device));
+    if (h->binned) return fail("fgnn_shard_local_step: graph not rebuilt since the last step");
+    if (enqueue_hops(h, st)) return 1;
+    return enqueue_final(h, true, 0, st);
+}
+
+extern "C" int fgnn_shard_pack(fgnn_handle* h, const double* windows, int64_t window_stride, int32_t world, int32_t rank,
+                               double depth, double* send_buf, int32_t cap, void* stream) {
+    if (!h || !h->sharded || !windows || !send_buf) return fail("fgnn_shard_pack: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    Params& p = h->p;
+    CK(cudaSetDevice(h->cfg.device));
+    k_pool_init<<<blocks_for(p.n_own, 256), 256, 0, st>>>(p, h->d_pool, h->d_n_pool, h->d_pack_counter);
+    if (launch_check(h, "pool_init")) return 1;
+    // windows may live inside a gathered buffer: compact them first (world x 2 doubles)
+    double* win = reinterpret_cast<double*>(h->d_staging);
+    for (int q = 0; q < world; ++q)
+        CK(cudaMemcpyAsync(win + 2 * q, windows + (size_t)q * window_stride, 2 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    k_shard_pack<<<blocks_for(p.n_own, 256), 256, 0, st>>>(p, win, world, rank, depth, send_buf, cap, h->d_pack_counter);
+    if (launch_check(h, "shard_pack")) return 1;
+    k_shard_header<<<1, 1024, 0, st>>>(p, send_buf, h->d_pack_counter);
+    return launch_check(h, "shard_header");
+}
+
+extern "C" int fgnn_shard_unpack(fgnn_handle* h, const double* recv_buf, int32_t world, int32_t rank, int32_t cap,
+                                 double depth, void* stream) {
+    if (!h || !h->sharded || !recv_buf) return fail("fgnn_shard_unpack: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    Params& p = h->p;
+    CK(cudaSetDevice(h->cfg.device));
+    k_shard_unpack<<<blocks_for(world * cap, 256), 256, 0, st>>>(p, recv_buf, world, rank, cap, depth, h->d_pool,
+                                                                  h->d_n_pool, p.overflow);
+    if (launch_check(h, "shard_unpack")) return 1;
+    h->binned = true;
+    return 0;
 }
 
 extern "C" int fgnn_profile_step(fgnn_handle* h, int32_t max_kernels, float* ms_out, char* names_out, int32_t* n_out,

@@ -130,11 +130,11 @@ __global__ void __launch_bounds__(FINAL_THREADS) k_final(Params p) {
     }
     const int t = *p.t;
     const size_t M = p.M;
-    const int n_tiles = (p.M + FINAL_THREADS - 1) / FINAL_THREADS;
+    const int n_tiles = (p.n_own + FINAL_THREADS - 1) / FINAL_THREADS;
     double racc[4] = {0, 0, 0, 0};
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int a = tile * FINAL_THREADS + threadIdx.x;
-        const bool valid = a < p.M;
+        const int a = p.a_lo + tile * FINAL_THREADS + threadIdx.x;
+        const bool valid = a < p.a_lo + p.n_own;
         float in[F * K];
 #pragma unroll
         for (int i = 0; i < F * K; ++i) in[i] = 0.f;

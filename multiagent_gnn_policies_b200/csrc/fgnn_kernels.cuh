@@ -26,8 +26,15 @@ struct Params {
     int B;                    // episodes
     int K;                    // taps
     int L;                    // hidden layers
-    int G;                    // cells per side (wrapped grid)
-    int C;                    // total cells = B*G*G
+    int G;                    // cells along x of the wrapped cell grid
+    int Gy;                   // cells along y
+    int C;                    // total cells = B*G*Gy
+    // sharding (one rank of a multi-GPU flock; single-GPU: a_lo = 0, n_own = M, pool = null)
+    int a_lo;                 // first agent this rank owns (integrates)
+    int n_own;                // number of owned agents
+    int pool_cap;             // capacity of the pool list
+    const int* pool;          // [pool_cap] agents present on this rank: owned range, then ghosts; null = all M
+    const int* n_pool;        // device count of valid pool entries (null = M)
     int mean_pooling;
     int half_accel;
     int write_z_last;         // final kernel also stores z_{K-1} (debug / fgnn_get_aggregated)
@@ -100,8 +107,12 @@ __device__ __forceinline__ void cell_coords(const Params& p, double px, double p
 }
 
 __device__ __forceinline__ int cell_index(const Params& p, int ep, long long ix, long long iy) {
-    return (ep * p.G + wrap(iy, p.G)) * p.G + wrap(ix, p.G);
+    return (ep * p.Gy + wrap(iy, p.Gy)) * p.G + wrap(ix, p.G);
 }
+
+// number of agents present on this rank and the i-th of them
+__device__ __forceinline__ int pool_size(const Params& p) { return p.pool ? *p.n_pool : p.M; }
+__device__ __forceinline__ int pool_agent(const Params& p, int i) { return p.pool ? p.pool[i] : i; }
 
 // r2 exactly as numpy evaluates dx*dx + dy*dy (two roundings of the products, one of the sum; no FMA)
 __device__ __forceinline__ double r2_exact(double dx, double dy) {
@@ -124,9 +135,10 @@ __device__ __forceinline__ void store_row6(float* base, int idx, const float (&v
 // ------------------------------------------------------------------------------------------
 // K_A  bin: cell of every agent + per-cell population count
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_bin(Params p) {
-    int a = blockIdx.x * blockDim.x + threadIdx.x;
-    if (a >= p.M) return;
+__global__ void __launch_bounds__(256) k_bin(Params p, int first) {
+    const int i = first + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= pool_size(p)) return;
+    const int a = pool_agent(p, i);
     double4 s = p.state[a];
     long long ix, iy;
     cell_coords(p, s.x, s.y, ix, iy);
@@ -292,8 +304,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(Params p, int advance) {
 // K_C  scatter agent ids into their cell's slot range (atomic order, canonicalised by K_C2)
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_scatter(Params p) {
-    int a = blockIdx.x * blockDim.x + threadIdx.x;
-    if (a >= p.M) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= pool_size(p)) return;
+    const int a = pool_agent(p, i);
     int c = p.cell_of[a];
     int slot = p.cell_start[c] + atomicAdd(&p.cell_count[c], 1);
     p.tmp_id[slot] = a;
@@ -304,7 +317,7 @@ __global__ void __launch_bounds__(256) k_scatter(Params p) {
 __global__ void __launch_bounds__(256) k_canon(Params p) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     for (int i = s; i <= p.C; i += gridDim.x * blockDim.x) p.cell_count[i] = 0;   // fill counters -> 0 for the next bin
-    if (s >= p.M) return;
+    if (s >= pool_size(p)) return;
     int a = p.tmp_id[s];
     int c = p.cell_of[a];
     int q0 = p.cell_start[c], q1 = p.cell_start[c + 1];
@@ -340,7 +353,7 @@ __global__ void __launch_bounds__(ADJ_THREADS) k_adjacency(Params p, int stage_c
 
     const int t = *p.t;
     const int g = slot_of(t, p.K);
-    const bool valid = s < p.M;
+    const bool valid = s < pool_size(p);
     int a = 0;
     double4 me = make_double4(0, 0, 0, 0);
     int q0[9], q1[9];
@@ -354,7 +367,7 @@ __global__ void __launch_bounds__(ADJ_THREADS) k_adjacency(Params p, int stage_c
         const int cxw = wrap(ix, p.G);
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
-            const int rowbase = (ep * p.G + wrap(iy + r - 1, p.G)) * p.G;
+            const int rowbase = (ep * p.Gy + wrap(iy + r - 1, p.Gy)) * p.G;
             if (cxw >= 1 && cxw <= p.G - 2) {            // the row's three cells are contiguous slots
                 q0[3 * r] = __ldg(&p.cell_start[rowbase + cxw - 1]);
                 q1[3 * r] = __ldg(&p.cell_start[rowbase + cxw + 2]);
@@ -547,8 +560,9 @@ __device__ __forceinline__ void gather_rows(const Params& p, int g, int a, const
 // ------------------------------------------------------------------------------------------
 template <int NB, bool FIRST>
 __global__ void __launch_bounds__(256) k_hop(Params p, int j) {
-    const int a = blockIdx.x * blockDim.x + threadIdx.x;
-    if (a >= p.M) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= pool_size(p)) return;
+    const int a = pool_agent(p, i);
     const int t = *p.t;
     const int g = slot_of(t - j, p.K);
     const size_t M = p.M;
@@ -618,7 +632,7 @@ __device__ __forceinline__ void integrate_and_bin(const Params& p, int a, float 
             atomicAdd(dst + 0, v0); atomicAdd(dst + 1, v1); atomicAdd(dst + 2, v2); atomicAdd(dst + 3, v3);
         }
     }
-    if (a == 0) *p.reward_pending = 1;
+    if (a == p.a_lo) *p.reward_pending = 1;
 }
 
 // B == 1: sum the block's thread-local reward sums in a fixed order and store them as this block's partial.
@@ -649,9 +663,10 @@ __device__ __forceinline__ void reward_block_flush(const Params& p, const double
 #ifdef FGNN_MAIN_TU
 // first half of env.step(u) with an externally supplied action
 __global__ void __launch_bounds__(256) k_integrate(Params p, const float* __restrict__ u) {
-    int a = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int a = p.a_lo + i;
     double racc[4] = {0, 0, 0, 0};
-    if (a < p.M) {
+    if (i < p.n_own) {
         const float2 uu = reinterpret_cast<const float2*>(u)[a];
         integrate_and_bin(p, a, uu.x, uu.y, racc);
     }
@@ -702,7 +717,7 @@ __global__ void __launch_bounds__(256) k_vel_sum(Params p, double* __restrict__ 
 __global__ void __launch_bounds__(128) k_controller(Params p, int centralized, int window, double grad_cut /* comm_radius */,
                                                     double max_u, const double* __restrict__ vsum, float* __restrict__ out) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= p.M) return;
+    if (s >= pool_size(p)) return;
     const int a = p.sorted_id[s];
     const double4 me = p.sorted_state[s];
     const int ep = a / p.N;
@@ -711,9 +726,10 @@ __global__ void __launch_bounds__(128) k_controller(Params p, int centralized, i
     double gx = 0, gy = 0, dvx = 0, dvy = 0;
     // distinct wrapped cells only: a window wider than the grid would visit cells twice
     const int span = 2 * window + 1 <= p.G ? 2 * window + 1 : p.G;
+    const int spany = 2 * window + 1 <= p.Gy ? 2 * window + 1 : p.Gy;
     const long long x0 = 2 * window + 1 <= p.G ? ix - window : 0;
-    const long long y0 = 2 * window + 1 <= p.G ? iy - window : 0;
-    for (int ry = 0; ry < span; ++ry) {
+    const long long y0 = 2 * window + 1 <= p.Gy ? iy - window : 0;
+    for (int ry = 0; ry < spany; ++ry) {
         for (int rx = 0; rx < span; ++rx) {
             const int c = cell_index(p, ep, x0 + rx, y0 + ry);
             const int q0 = __ldg(&p.cell_start[c]), q1 = __ldg(&p.cell_start[c + 1]);
@@ -745,6 +761,92 @@ __global__ void __launch_bounds__(128) k_controller(Params p, int centralized, i
     ux = fmin(fmax(ux, -max_u), max_u) / p.gain;
     uy = fmin(fmax(uy, -max_u), max_u) / p.gain;
     reinterpret_cast<float2*>(out)[a] = make_float2((float)ux, (float)uy);
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Multi-GPU halo exchange (agents sharded by index; every rank keeps full-size arrays).
+// Record = 5 doubles: [agent id, px, py, vx, vy]; row 0 of a rank's buffer is the header
+// [count, own x-interval lo, hi, 0, 0].
+//   k_shard_pack  : owned agents whose x lies inside any other rank's window [lo_q - D, hi_q + D]
+//   k_shard_unpack: install the received states, append the agents to the pool list and bin them
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_shard_pack(Params p, const double* __restrict__ windows /* [world][2] */, int world,
+                                                    int rank, double depth, double* __restrict__ buf, int cap,
+                                                    int* __restrict__ counter) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n_own) return;
+    const int a = p.a_lo + i;
+    const double4 s = p.state[a];
+    bool wanted = false;
+    for (int q = 0; q < world; ++q) {
+        if (q == rank) continue;
+        wanted = wanted || (s.x >= windows[2 * q] - depth && s.x <= windows[2 * q + 1] + depth);
+    }
+    if (!wanted) return;
+    const int slot = atomicAdd(counter, 1);
+    if (slot >= cap) return;                       // overflow is reported through the header count
+    double* rec = buf + (size_t)(slot + 1) * 5;
+    rec[0] = (double)a; rec[1] = s.x; rec[2] = s.y; rec[3] = s.z; rec[4] = s.w;
+}
+
+// own x-interval (min / max px over owned agents) -> header; one block
+__global__ void __launch_bounds__(1024) k_shard_header(Params p, double* __restrict__ buf, const int* __restrict__ counter) {
+    __shared__ double s_lo[32], s_hi[32];
+    double lo = 1e300, hi = -1e300;
+    for (int i = threadIdx.x; i < p.n_own; i += blockDim.x) {
+        const double x = p.state[p.a_lo + i].x;
+        lo = fmin(lo, x);
+        hi = fmax(hi, x);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0) { s_lo[threadIdx.x >> 5] = lo; s_hi[threadIdx.x >> 5] = hi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { lo = fmin(lo, s_lo[w]); hi = fmax(hi, s_hi[w]); }
+        buf[0] = (double)*counter; buf[1] = lo; buf[2] = hi; buf[3] = 0.0; buf[4] = 0.0;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_shard_unpack(Params p, const double* __restrict__ recv /* [world][cap+1][5] */,
+                                                      int world, int rank, int cap, double depth,
+                                                      int* __restrict__ pool, int* __restrict__ n_pool,
+                                                      int* __restrict__ overflow) {
+    // this rank's window: its own x-interval (header of its own buffer) +- depth; depth < 0 accepts everything
+    const double* own = recv + (size_t)rank * (cap + 1) * 5;
+    const double win_lo = depth < 0 ? -1e300 : own[1] - depth;
+    const double win_hi = depth < 0 ? 1e300 : own[2] + depth;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int q = idx / cap, r = idx % cap;
+    if (q >= world || q == rank) return;
+    const double* base = recv + (size_t)q * (cap + 1) * 5;
+    const int count = (int)base[0];
+    if (r == 0 && count > cap) *overflow = 1;
+    if (r >= count || r >= cap) return;
+    const double* rec = base + (size_t)(r + 1) * 5;
+    if (rec[1] < win_lo || rec[1] > win_hi) return;          // not near this rank
+    const int a = (int)rec[0];
+    p.state[a] = make_double4(rec[1], rec[2], rec[3], rec[4]);
+    const int slot = atomicAdd(n_pool, 1);
+    if (slot >= p.pool_cap) { *overflow = 1; return; }
+    pool[slot] = a;
+    long long ix, iy;
+    cell_coords(p, rec[1], rec[2], ix, iy);
+    const int c = cell_index(p, a / p.N, ix, iy);
+    p.cell_of[a] = c;
+    atomicAdd(&p.cell_count[c], 1);
+}
+
+// pool[0..n_own) = owned range, n_pool = n_own  (start of every exchange)
+__global__ void __launch_bounds__(256) k_pool_init(Params p, int* __restrict__ pool, int* __restrict__ n_pool,
+                                                   int* __restrict__ counter) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < p.n_own) pool[i] = p.a_lo + i;
+    if (i == 0) { *n_pool = p.n_own; *counter = 0; }
 }
 
 #endif  // FGNN_MAIN_TU

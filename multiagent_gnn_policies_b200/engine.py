@@ -17,7 +17,7 @@ ABI_SYMBOLS = [
     "fgnn_set_state", "fgnn_build_graph", "fgnn_integrate", "fgnn_env_step", "fgnn_policy", "fgnn_controller", "fgnn_step",
     "fgnn_rollout", "fgnn_actor_forward_dense", "fgnn_get_state", "fgnn_get_features", "fgnn_get_degrees",
     "fgnn_get_aggregated", "fgnn_get_action", "fgnn_export_network_dense", "fgnn_get_csr", "fgnn_get_stats",
-    "fgnn_profile_step", "fgnn_memcpy_sync", "fgnn_launch_count",
+    "fgnn_shard_local_step", "fgnn_shard_pack", "fgnn_shard_unpack", "fgnn_profile_step", "fgnn_memcpy_sync", "fgnn_launch_count",
 ]
 
 
@@ -27,7 +27,8 @@ class FgnnConfig(ctypes.Structure):
         ("n_states", ctypes.c_int32), ("n_actions", ctypes.c_int32), ("hidden", ctypes.c_int32),
         ("n_layers", ctypes.c_int32), ("mean_pooling", ctypes.c_int32), ("half_accel_term", ctypes.c_int32),
         ("device", ctypes.c_int32), ("grid_dim", ctypes.c_int32), ("edge_capacity", ctypes.c_int32),
-        ("readout_mode", ctypes.c_int32), ("reserved0", ctypes.c_int32),
+        ("readout_mode", ctypes.c_int32), ("grid_dim_y", ctypes.c_int32), ("shard_lo", ctypes.c_int32),
+        ("shard_count", ctypes.c_int32), ("ghost_capacity", ctypes.c_int32), ("reserved0", ctypes.c_int32),
         ("comm_radius", ctypes.c_double), ("dt", ctypes.c_double), ("action_scalar", ctypes.c_double),
     ]
 
@@ -81,6 +82,9 @@ def load_library(path=None):
     lib.fgnn_export_network_dense.argtypes = [vp, i32, vp, vp]
     lib.fgnn_get_csr.argtypes = [vp, i32, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp)]
     lib.fgnn_get_stats.argtypes = [vp, ctypes.POINTER(FgnnStats), vp]
+    lib.fgnn_shard_local_step.argtypes = [vp, vp]
+    lib.fgnn_shard_pack.argtypes = [vp, vp, i64, i32, i32, ctypes.c_double, vp, i32, vp]
+    lib.fgnn_shard_unpack.argtypes = [vp, vp, i32, i32, i32, ctypes.c_double, vp]
     lib.fgnn_profile_step.argtypes = [vp, i32, vp, vp, ctypes.POINTER(i32), vp]
     lib.fgnn_memcpy_sync.argtypes = [vp, vp, ctypes.c_uint64, vp]
     lib.fgnn_launch_count.argtypes = [vp]
@@ -117,7 +121,8 @@ class FlockEngine:
 
     def __init__(self, n_agents, k=3, hidden=32, n_layers=2, comm_radius=1.0, dt=0.01, n_episodes=1,
                  device=0, action_scalar=10.0, mean_pooling=True, half_accel_term=True, grid_dim=0,
-                 edge_capacity=0, readout_mode=0, n_states=6, n_actions=2, stream=None):
+                 edge_capacity=0, readout_mode=0, n_states=6, n_actions=2, stream=None, grid_dim_y=0,
+                 shard_lo=0, shard_count=0, ghost_capacity=0):
         import torch  # device memory + streams only
         if not torch.cuda.is_available():
             raise FgnnError("no CUDA device: the rollout engine has no CPU fallback")
@@ -133,8 +138,10 @@ class FlockEngine:
         self._stream = stream
         cfg = FgnnConfig(self.n_agents, self.n_episodes, self.k, self.n_states, self.n_actions, self.hidden,
                          self.n_layers, int(bool(mean_pooling)), int(bool(half_accel_term)), self.device_index,
-                         int(grid_dim), int(edge_capacity), int(readout_mode), 0,
+                         int(grid_dim), int(edge_capacity), int(readout_mode), int(grid_dim_y), int(shard_lo),
+                         int(shard_count), int(ghost_capacity), 0,
                          self.comm_radius, self.dt, self.action_scalar)
+        self.shard_lo, self.shard_count, self.ghost_capacity = int(shard_lo), int(shard_count), int(ghost_capacity)
         self._h = ctypes.c_void_p()
         self._check(self.lib.fgnn_create(ctypes.byref(cfg), ctypes.byref(self._h)))
         self.step_index = -1          # host mirror of the engine's step counter t (-1: never reset)
@@ -341,6 +348,17 @@ class FlockEngine:
         self._check(self.lib.fgnn_get_stats(self._h, ctypes.byref(s), self.stream))
         return {"step": s.step, "n_edges": s.n_edges, "overflow": bool(s.overflow), "grid_dim": s.grid_dim,
                 "n_cells": s.n_cells, "edge_capacity": s.edge_capacity}
+
+    # -- multi-GPU pieces (orchestrated by parallel.ShardedFlock) ---------------------------
+    def shard_local_step(self):
+        self._check(self.lib.fgnn_shard_local_step(self._h, self.stream))
+
+    def shard_pack(self, windows, window_stride, world, rank, depth, send_buf, cap):
+        self._check(self.lib.fgnn_shard_pack(self._h, _ptr(windows), int(window_stride), world, rank, float(depth),
+                                             _ptr(send_buf), cap, self.stream))
+
+    def shard_unpack(self, recv_buf, world, rank, cap, depth):
+        self._check(self.lib.fgnn_shard_unpack(self._h, _ptr(recv_buf), world, rank, cap, float(depth), self.stream))
 
     def profile_step(self):
         """One closed-loop step with per-kernel CUDA-event timing: [(kernel name, ms), ...]."""

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_config_struct_layout_matches_header():
     import ctypes
-    assert ctypes.sizeof(engine.FgnnConfig) == 14 * 4 + 3 * 8
+    assert ctypes.sizeof(engine.FgnnConfig) == 18 * 4 + 3 * 8
     assert ctypes.sizeof(engine.FgnnStats) == 8 + 8 + 4 + 4 + 8 + 8
 
 
