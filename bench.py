@@ -221,9 +221,27 @@ def main():
 
     N = args.n_agents
     side = np.sqrt(N / DENSITY)
-    x0 = make_workload(N, seed=11 + rank, x_offset=rank * side)
     sd, weights_note = make_weights(args.hidden, args.k, args.n_layers)
     cap = int(max(24, 3.2 * np.pi * args.radius ** 2 * DENSITY + 16))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            tms = torch.tensor([ms], device="cuda")
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            return float(tms.item())
+        return ms
+
+    if world > 1:
+        run_sharded(args, rank, world, local_rank, N, side, sd, weights_note, cap, config, barrier, max_over_ranks)
+        dist.destroy_process_group()
+        return
+
+    x0 = make_workload(N, seed=11)
     eng = FlockEngine(n_agents=N, k=args.k, hidden=args.hidden, n_layers=args.n_layers, comm_radius=args.radius,
                       dt=0.01, device=local_rank, edge_capacity=cap)
     eng.load_state_dict(sd)
@@ -231,17 +249,11 @@ def main():
     st0 = eng.stats()
     deg_start = st0["n_edges"] / N
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     # ---- device-resident throughput: CUDA-graph rollout ------------------------------------
     eng.rollout(args.warmup)
     barrier()
     sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    sampler.start()
     l0 = eng.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -251,11 +263,7 @@ def main():
     barrier()
     ms = e0.elapsed_time(e1)
     launches = eng.launch_count() - l0
-    clocks = sampler.stop() if rank == 0 else None
-    if world > 1:
-        tms = torch.tensor([ms], device="cuda")
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        ms = float(tms.item())
+    clocks = sampler.stop()
     st1 = eng.stats()
     deg_end = st1["n_edges"] / N
     if st1["overflow"]:
@@ -291,16 +299,7 @@ def main():
     t1.record()
     barrier()
     e2e_ms = t0.elapsed_time(t1)
-    if world > 1:
-        tms = torch.tensor([e2e_ms], device="cuda")
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        e2e_ms = float(tms.item())
     e2e_value = world * N * e2e_steps / (e2e_ms * 1e-3)
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
 
     # ---- roofline of the dominant kernel ---------------------------------------------------
     peak, peak_src = measured_peaks()
@@ -334,8 +333,90 @@ def main():
                     "h2d_bytes_per_step": int(N * 2 * 4), "d2h_bytes_per_step": int(N * 2 * 4 + 8)},
             "roofline": roof, "cpu_baseline": cb}
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+
+
+def run_sharded(args, rank, world, local_rank, N, side, sd, weights_note, edge_cap, config, barrier, max_over_ranks):
+    """N > 1: ONE flock of world*N agents, sharded by index (rank r owns the r-th strip of N agents), one
+    NCCL halo all-gather per step (multiagent_gnn_policies_b200.parallel).  Weak scaling: N agents per GPU."""
+    import torch
+    from multiagent_gnn_policies_b200 import parallel
+    n_total = world * N
+    ranges = parallel.shard_ranges(n_total, world)
+    lo, cnt = ranges[rank]
+    # every rank generates its own strip and the two neighbouring strips (all it needs at reset)
+    x_global = np.zeros((n_total, 4))
+    x_global[:, 0] = parallel.FAR
+    for q in (rank - 1, rank, rank + 1):
+        if 0 <= q < world:
+            x_global[ranges[q][0]:ranges[q][0] + ranges[q][1]] = make_workload(N, seed=11 + q, x_offset=q * side)
+    depth = parallel.halo_depth(args.k, args.radius)
+    halo_cap = int(1.6 * (depth + args.radius) * side * DENSITY * 2) + 1024        # both boundaries, with slack
+    cell = args.radius
+    gx = int(np.ceil((side + 2 * depth + 4) / cell)) + 2
+    gy = int(np.ceil(side / cell)) + 4
+    be = parallel.CudaShardBackend(n_total, lo, cnt, ghost_capacity=2 * halo_cap, device=local_rank, k=args.k,
+                                   hidden=args.hidden, n_layers=args.n_layers, comm_radius=args.radius, dt=0.01,
+                                   edge_capacity=edge_cap, grid_dim=gx, grid_dim_y=gy)
+    be.engine.load_state_dict(sd)
+    flock = parallel.ShardedFlock(be, rank, world, args.k, args.radius, halo_cap,
+                                  parallel.nccl_all_gather(world, halo_cap, be.device))
+    flock.reset(x_global, ranges)
+    for _ in range(args.warmup):
+        flock.step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = be.engine.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        flock.step()
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = be.engine.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    st = be.engine.stats()
+    if st["overflow"]:
+        raise RuntimeError("capacity overflow (edges / halo) during the timed region: results void")
+    value = n_total * args.steps / (ms * 1e-3)
+    ghosts = int(flock.recv[:, 0, 0].sum().item())
+
+    # e2e: the same step through host buffers (select_action -> pinned host -> env.step)
+    e2e_steps = args.e2e_steps or min(args.steps, 50)
+    act_host = torch.empty((cnt, 2), dtype=torch.float32, pin_memory=True).numpy()
+    for _ in range(3):
+        flock.step_host(act_host)
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(e2e_steps):
+        flock.step_host(act_host)
+    t1.record()
+    barrier()
+    e2e_ms = max_over_ranks(t0.elapsed_time(t1))
+    if rank != 0:
+        return
+    peak, peak_src = measured_peaks()
+    d = st["n_edges"] / max(1, (cnt + ghosts / world))
+    step_bytes = 268 + 12 * d
+    config = dict(config, parallelism=f"index-sharded x{world}, halo all-gather (NCCL) of {flock.cap}-record buffers, "
+                                      f"halo depth {depth:.2f}", n_agents_total=n_total)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 learner / f64 env", "data": f"synthetic ({weights_note})", "config": config,
+            "halo_records_per_step": ghosts, "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": n_total * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "steps": e2e_steps,
+                    "ms_per_step": e2e_ms / e2e_steps, "h2d_bytes_per_step": int(cnt * 2 * 4) * world,
+                    "d2h_bytes_per_step": int(cnt * 2 * 4) * world},
+            "roofline": {"bound": "hbm", "kernel": None, "unit": "GB/s", "peak": peak, "peak_source": peak_src,
+                         "achieved": step_bytes * value / world / 1e9, "frac": step_bytes * value / world / 1e9 / peak,
+                         "traffic": None, "note": "whole step per GPU (268 + 12 d) B per agent-step; per-kernel breakdown "
+                                                  "is reported by the 1-GPU run"},
+            "cpu_baseline": None}
+    print(json.dumps(line))
 
 
 if __name__ == "__main__":

@@ -134,7 +134,9 @@ int fgnn_get_stats(fgnn_handle* h, fgnn_stats* out, void* stream);   /* synchron
  * Buffers are DEVICE arrays of doubles: per rank (cap + 1) records of 5 doubles; record 0 is the header
  * [count, x_lo, x_hi, 0, 0] (the rank's own x-interval), records 1..count are [agent id, px, py, vx, vy].
  * `windows` is a device array holding every rank's [x_lo, x_hi] at windows[q * window_stride + {0, 1}]
- * (so the headers of the previous step's gathered buffer can be passed directly). */
+ * (so the headers of the previous step's gathered buffer can be passed directly).
+ * On a sharded handle fgnn_policy / fgnn_integrate read and write the OWNED slice only (count x 2 floats);
+ * fgnn_step / fgnn_rollout / fgnn_env_step are refused (the host drives the exchange between the halves). */
 int fgnn_shard_local_step(fgnn_handle* h, void* stream);
 int fgnn_shard_pack(fgnn_handle* h, const double* windows, int64_t window_stride, int32_t world, int32_t rank,
                     double depth, double* send_buf, int32_t cap, void* stream);

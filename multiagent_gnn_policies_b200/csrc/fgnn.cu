@@ -516,7 +516,8 @@ extern "C" int fgnn_integrate(fgnn_handle* h, const float* u, double* reward_b, 
         CK(cudaMemsetAsync(p.cell_count, 0, ((size_t)p.C + 1) * sizeof(int), st));
         CK(cudaMemsetAsync(p.racc, 0, (size_t)RSLOTS * p.B * 4 * sizeof(double), st));
     }
-    CK(cudaMemcpyAsync(h->d_u_in, u, (size_t)p.M * 2 * sizeof(float), cudaMemcpyDefault, st));
+    // sharded handle: u covers the owned range only
+    CK(cudaMemcpyAsync(h->d_u_in + (size_t)p.a_lo * 2, u, (size_t)p.n_own * 2 * sizeof(float), cudaMemcpyDefault, st));
     k_integrate<<<blocks_for(p.n_own, 256), 256, 0, st>>>(p, h->d_u_in);
     if (launch_check(h, "integrate")) return 1;
     h->binned = true;
@@ -529,6 +530,7 @@ extern "C" int fgnn_integrate(fgnn_handle* h, const float* u, double* reward_b, 
 }
 
 extern "C" int fgnn_env_step(fgnn_handle* h, const float* u, double* reward_b, void* stream) {
+    if (h && h->sharded) return fail("fgnn_env_step: sharded handle -- integrate, exchange the halo, then build the graph");
     if (fgnn_integrate(h, u, nullptr, stream)) return 1;
     if (enqueue_build(h, 1, (cudaStream_t)stream)) return 1;
     return copy_out(reward_b, h->p.reward, (size_t)h->p.B * sizeof(double), (cudaStream_t)stream);
@@ -540,7 +542,7 @@ extern "C" int fgnn_policy(fgnn_handle* h, float* action, void* stream) {
     CK(cudaSetDevice(h->cfg.device));
     if (enqueue_hops(h, st)) return 1;
     if (enqueue_final(h, false, 1, st)) return 1;
-    return copy_out(action, h->p.action, (size_t)h->p.M * 2 * sizeof(float), st);
+    return copy_out(action, h->p.action + (size_t)h->p.a_lo * 2, (size_t)h->p.n_own * 2 * sizeof(float), st);
 }
 
 static int enqueue_closed_step(fgnn_handle* h, cudaStream_t st) {
@@ -553,6 +555,7 @@ extern "C" int fgnn_step(fgnn_handle* h, float* action, double* reward_b, void* 
     if (!h) return fail("fgnn_step: null handle");
     cudaStream_t st = (cudaStream_t)stream;
     CK(cudaSetDevice(h->cfg.device));
+    if (h->sharded) return fail("fgnn_step: sharded handle -- use fgnn_shard_local_step / pack / unpack / build_graph");
     if (h->binned) return fail("fgnn_step: state was integrated but the graph not rebuilt (call fgnn_build_graph)");
     if (enqueue_closed_step(h, st)) return 1;
     if (copy_out(action, h->p.action, (size_t)h->p.M * 2 * sizeof(float), st)) return 1;
@@ -564,6 +567,7 @@ extern "C" int fgnn_rollout(fgnn_handle* h, int32_t T, double* reward_bt, void* 
     cudaStream_t st = (cudaStream_t)stream;
     Params& p = h->p;
     CK(cudaSetDevice(h->cfg.device));
+    if (h->sharded) return fail("fgnn_rollout: sharded handle -- the host drives the per-step halo exchange");
     if (h->binned) return fail("fgnn_rollout: state was integrated but the graph not rebuilt");
     if (T == 0) return 0;
     const bool want_log = reward_bt != nullptr;

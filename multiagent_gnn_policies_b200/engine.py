@@ -214,10 +214,10 @@ class FlockEngine:
 
     def _as_action(self, u):
         if hasattr(u, "data_ptr"):
-            assert u.dtype == self._torch.float32 and u.numel() == self.M * 2
+            assert u.dtype == self._torch.float32 and u.numel() == (self.shard_count or self.M) * 2
             return u.contiguous()
         u = np.ascontiguousarray(u, dtype=np.float32)
-        assert u.size == self.M * 2
+        assert u.size == (self.shard_count or self.M) * 2
         return u
 
     def integrate(self, u, want_reward=False):
@@ -242,7 +242,7 @@ class FlockEngine:
         """select_action: (B*N, 2) fp32.  ``out`` may be a torch CUDA tensor or a (pinned) numpy array;
         default is a fresh CUDA tensor."""
         if out is None:
-            out = self._torch.empty((self.M, 2), dtype=self._torch.float32, device=self.device)
+            out = self._torch.empty((self.shard_count or self.M, 2), dtype=self._torch.float32, device=self.device)
         self._check(self.lib.fgnn_policy(self._h, _ptr(out), self.stream))
         if isinstance(out, np.ndarray):
             self.sync()

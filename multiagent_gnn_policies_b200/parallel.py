@@ -59,6 +59,14 @@ class CudaShardBackend:
     def local_step(self):
         self.engine.shard_local_step()
 
+    def policy(self, out):
+        """select_action for the owned agents into ``out`` (owned slice; host or device)."""
+        return self.engine.policy(out=out)
+
+    def integrate(self, u):
+        """first half of env.step for the owned agents from ``u`` (owned slice; host or device)."""
+        self.engine.integrate(u)
+
     def pack(self, windows, window_stride, world, rank, depth, send, cap):
         self.engine.shard_pack(windows, window_stride, world, rank, depth, send, cap)
 
@@ -124,6 +132,14 @@ class ShardedFlock:
     def step(self):
         """One closed-loop step: local policy + integrator for owned agents, halo exchange, rebuild."""
         self.backend.local_step()
+        self._exchange(self.recv, (self.cap + 1) * RECORD)
+        self.backend.build(True)
+
+    def step_host(self, action_host):
+        """The same step through host buffers, as the reference loop does it (learner/gnn_dagger.py:196-201):
+        select_action -> host array -> env.step(host array).  ``action_host``: (count, 2) fp32, pinned."""
+        self.backend.policy(action_host)          # D2H (synchronises)
+        self.backend.integrate(action_host)       # H2D
         self._exchange(self.recv, (self.cap + 1) * RECORD)
         self.backend.build(True)
 
