@@ -143,6 +143,13 @@ int fgnn_shard_pack(fgnn_handle* h, const double* windows, int64_t window_stride
 int fgnn_shard_unpack(fgnn_handle* h, const double* recv_buf, int32_t world, int32_t rank, int32_t cap,
                       double depth, void* stream);
 
+/* CUDA-graph replayed halves of a sharded step: begin = fgnn_shard_local_step + fgnn_shard_pack,
+ * end = fgnn_shard_unpack + fgnn_build_graph(advance = 1); the host's all-gather goes in between. */
+int fgnn_shard_step_begin(fgnn_handle* h, const double* windows, int64_t window_stride, int32_t world, int32_t rank,
+                          double depth, double* send_buf, int32_t cap, void* stream);
+int fgnn_shard_step_end(fgnn_handle* h, const double* recv_buf, int32_t world, int32_t rank, int32_t cap,
+                        double depth, void* stream);
+
 /* One closed-loop step (same work as fgnn_step) with a CUDA event after every kernel: ms_out[i] is the
  * device time of kernel i, names_out (16 bytes each, may be NULL) its name.  For bench.py's roofline. */
 int fgnn_profile_step(fgnn_handle* h, int32_t max_kernels, float* ms_out, char* names_out, int32_t* n_out,

@@ -63,6 +63,7 @@ struct fgnn_handle {
     int* d_n_pool = nullptr;
     int* d_pack_counter = nullptr;
     int launch_pool = 0;             // grid sizing for kernels over the pool (pool capacity, or M)
+    void* shard_graph_store = nullptr;
     // per-kernel profiling of one step (fgnn_profile_step)
     bool profiling = false;
     cudaStream_t prof_stream = nullptr;
@@ -757,6 +758,29 @@ extern "C" int fgnn_controller(fgnn_handle* h, int32_t centralized, double max_a
     return copy_out(u, h->d_u_in, (size_t)p.M * 2 * sizeof(float), st);
 }
 
+struct ShardGraph;
+static int enqueue_shard_pack(fgnn_handle* h, const double* windows, int64_t window_stride, int world, int rank,
+                              double depth, double* send_buf, int cap, cudaStream_t st) {
+    Params& p = h->p;
+    k_pool_init<<<blocks_for(p.n_own, 256), 256, 0, st>>>(p, h->d_pool, h->d_n_pool, h->d_pack_counter);
+    if (launch_check(h, "pool_init")) return 1;
+    k_shard_pack<<<blocks_for(p.n_own, 256), 256, 0, st>>>(p, windows, (long long)window_stride, world, rank, depth, send_buf,
+                                                            cap, h->d_pack_counter);
+    if (launch_check(h, "shard_pack")) return 1;
+    k_shard_header<<<1, 1024, 0, st>>>(p, send_buf, h->d_pack_counter);
+    return launch_check(h, "shard_header");
+}
+
+static int enqueue_shard_unpack(fgnn_handle* h, const double* recv_buf, int world, int rank, int cap, double depth,
+                                cudaStream_t st) {
+    Params& p = h->p;
+    k_shard_unpack<<<blocks_for(world * cap, 256), 256, 0, st>>>(p, recv_buf, world, rank, cap, depth, h->d_pool,
+                                                                  h->d_n_pool, p.overflow);
+    if (launch_check(h, "shard_unpack")) return 1;
+    h->binned = true;
+    return 0;
+}
+
 extern "C" int fgnn_shard_local_step(fgnn_handle* h, void* stream) {
     if (!h || !h->sharded) return fail("fgnn_shard_local_step: handle is not sharded");
     cudaStream_t st = (cudaStream_t)stream;
@@ -769,31 +793,93 @@ extern "C" int fgnn_shard_local_step(fgnn_handle* h, void* stream) {
 extern "C" int fgnn_shard_pack(fgnn_handle* h, const double* windows, int64_t window_stride, int32_t world, int32_t rank,
                                double depth, double* send_buf, int32_t cap, void* stream) {
     if (!h || !h->sharded || !windows || !send_buf) return fail("fgnn_shard_pack: bad argument");
-    cudaStream_t st = (cudaStream_t)stream;
-    Params& p = h->p;
     CK(cudaSetDevice(h->cfg.device));
-    k_pool_init<<<blocks_for(p.n_own, 256), 256, 0, st>>>(p, h->d_pool, h->d_n_pool, h->d_pack_counter);
-    if (launch_check(h, "pool_init")) return 1;
-    // windows may live inside a gathered buffer: compact them first (world x 2 doubles)
-    double* win = reinterpret_cast<double*>(h->d_staging);
-    for (int q = 0; q < world; ++q)
-        CK(cudaMemcpyAsync(win + 2 * q, windows + (size_t)q * window_stride, 2 * sizeof(double), cudaMemcpyDeviceToDevice, st));
-    k_shard_pack<<<blocks_for(p.n_own, 256), 256, 0, st>>>(p, win, world, rank, depth, send_buf, cap, h->d_pack_counter);
-    if (launch_check(h, "shard_pack")) return 1;
-    k_shard_header<<<1, 1024, 0, st>>>(p, send_buf, h->d_pack_counter);
-    return launch_check(h, "shard_header");
+    return enqueue_shard_pack(h, windows, window_stride, world, rank, depth, send_buf, cap, (cudaStream_t)stream);
 }
 
 extern "C" int fgnn_shard_unpack(fgnn_handle* h, const double* recv_buf, int32_t world, int32_t rank, int32_t cap,
                                  double depth, void* stream) {
     if (!h || !h->sharded || !recv_buf) return fail("fgnn_shard_unpack: bad argument");
-    cudaStream_t st = (cudaStream_t)stream;
-    Params& p = h->p;
     CK(cudaSetDevice(h->cfg.device));
-    k_shard_unpack<<<blocks_for(world * cap, 256), 256, 0, st>>>(p, recv_buf, world, rank, cap, depth, h->d_pool,
-                                                                  h->d_n_pool, p.overflow);
-    if (launch_check(h, "shard_unpack")) return 1;
+    return enqueue_shard_unpack(h, recv_buf, world, rank, cap, depth, (cudaStream_t)stream);
+}
+
+// CUDA-graph replay of the two halves of a sharded step around the host's all-gather:
+//   begin = hops + final(closed) + pack          end = unpack + scan/scatter/canon/adjacency (advance)
+// Graphs are captured on first use and re-captured when an argument (pointer, size, depth) changes.
+struct ShardGraph {
+    cudaGraphExec_t exec = nullptr;
+    int kernels = 0;
+    const void* a = nullptr; const void* b = nullptr;
+    long long i0 = 0, i1 = 0, i2 = 0, i3 = 0;
+    double d = 0;
+};
+static ShardGraph* shard_graphs(fgnn_handle* h) {     // two entries, lazily allocated (begin, end)
+    if (!h->shard_graph_store) h->shard_graph_store = new ShardGraph[2];
+    return reinterpret_cast<ShardGraph*>(h->shard_graph_store);
+}
+
+template <typename F>
+static int run_cached_graph(fgnn_handle* h, ShardGraph& g, const void* a, const void* b, long long i0, long long i1,
+                            long long i2, long long i3, double d, cudaStream_t st, F enqueue) {
+    const bool hit = g.exec && g.a == a && g.b == b && g.i0 == i0 && g.i1 == i1 && g.i2 == i2 && g.i3 == i3 && g.d == d;
+    if (!hit) {
+        if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+        cudaStream_t cs;
+        CK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+        const int64_t l0 = h->launches, t0 = h->t_host;
+        const bool binned0 = h->binned;
+        cudaGraph_t graph = nullptr;
+        CK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+        int rc = enqueue(cs);
+        cudaError_t e = cudaStreamEndCapture(cs, &graph);
+        cudaStreamDestroy(cs);
+        g.kernels = (int)(h->launches - l0);
+        h->launches = l0;
+        h->t_host = t0;
+        h->binned = binned0;
+        if (rc) return 1;
+        if (e != cudaSuccess) return fail(std::string("shard graph capture failed: ") + cudaGetErrorString(e));
+        CK(cudaGraphInstantiate(&g.exec, graph, 0));
+        cudaGraphDestroy(graph);
+        g.a = a; g.b = b; g.i0 = i0; g.i1 = i1; g.i2 = i2; g.i3 = i3; g.d = d;
+    }
+    CK(cudaGraphLaunch(g.exec, st));
+    h->launches += g.kernels;
+    return 0;
+}
+
+extern "C" int fgnn_shard_step_begin(fgnn_handle* h, const double* windows, int64_t window_stride, int32_t world,
+                                     int32_t rank, double depth, double* send_buf, int32_t cap, void* stream) {
+    if (!h || !h->sharded || !windows || !send_buf) return fail("fgnn_shard_step_begin: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(h->cfg.device));
+    if (h->binned) return fail("fgnn_shard_step_begin: graph not rebuilt since the last step");
+    ShardGraph& g = shard_graphs(h)[0];
+    int rc = run_cached_graph(h, g, windows, send_buf, window_stride, world, rank, cap, depth, st, [&](cudaStream_t cs) {
+        if (enqueue_hops(h, cs)) return 1;
+        if (enqueue_final(h, true, 0, cs)) return 1;
+        return enqueue_shard_pack(h, windows, window_stride, world, rank, depth, send_buf, cap, cs);
+    });
+    if (rc) return 1;
     h->binned = true;
+    return 0;
+}
+
+extern "C" int fgnn_shard_step_end(fgnn_handle* h, const double* recv_buf, int32_t world, int32_t rank, int32_t cap,
+                                   double depth, void* stream) {
+    if (!h || !h->sharded || !recv_buf) return fail("fgnn_shard_step_end: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(h->cfg.device));
+    if (!h->binned) return fail("fgnn_shard_step_end: call fgnn_shard_step_begin first");
+    ShardGraph& g = shard_graphs(h)[1];
+    int rc = run_cached_graph(h, g, recv_buf, nullptr, world, rank, cap, 0, depth, st, [&](cudaStream_t cs) {
+        if (enqueue_shard_unpack(h, recv_buf, world, rank, cap, depth, cs)) return 1;
+        return enqueue_build(h, 1, cs);
+    });
+    if (rc) return 1;
+    h->binned = false;
+    h->t_host += 1;
     return 0;
 }
 

@@ -771,8 +771,8 @@ __global__ void __launch_bounds__(128) k_controller(Params p, int centralized, i
 //   k_shard_pack  : owned agents whose x lies inside any other rank's window [lo_q - D, hi_q + D]
 //   k_shard_unpack: install the received states, append the agents to the pool list and bin them
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_shard_pack(Params p, const double* __restrict__ windows /* [world][2] */, int world,
-                                                    int rank, double depth, double* __restrict__ buf, int cap,
+__global__ void __launch_bounds__(256) k_shard_pack(Params p, const double* __restrict__ windows, long long wstride,
+                                                    int world, int rank, double depth, double* __restrict__ buf, int cap,
                                                     int* __restrict__ counter) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.n_own) return;
@@ -781,7 +781,7 @@ __global__ void __launch_bounds__(256) k_shard_pack(Params p, const double* __re
     bool wanted = false;
     for (int q = 0; q < world; ++q) {
         if (q == rank) continue;
-        wanted = wanted || (s.x >= windows[2 * q] - depth && s.x <= windows[2 * q + 1] + depth);
+        wanted = wanted || (s.x >= windows[q * wstride] - depth && s.x <= windows[q * wstride + 1] + depth);
     }
     if (!wanted) return;
     const int slot = atomicAdd(counter, 1);

@@ -17,7 +17,7 @@ ABI_SYMBOLS = [
     "fgnn_set_state", "fgnn_build_graph", "fgnn_integrate", "fgnn_env_step", "fgnn_policy", "fgnn_controller", "fgnn_step",
     "fgnn_rollout", "fgnn_actor_forward_dense", "fgnn_get_state", "fgnn_get_features", "fgnn_get_degrees",
     "fgnn_get_aggregated", "fgnn_get_action", "fgnn_export_network_dense", "fgnn_get_csr", "fgnn_get_stats",
-    "fgnn_shard_local_step", "fgnn_shard_pack", "fgnn_shard_unpack", "fgnn_profile_step", "fgnn_memcpy_sync", "fgnn_launch_count",
+    "fgnn_shard_local_step", "fgnn_shard_pack", "fgnn_shard_unpack", "fgnn_shard_step_begin", "fgnn_shard_step_end", "fgnn_profile_step", "fgnn_memcpy_sync", "fgnn_launch_count",
 ]
 
 
@@ -85,6 +85,8 @@ def load_library(path=None):
     lib.fgnn_shard_local_step.argtypes = [vp, vp]
     lib.fgnn_shard_pack.argtypes = [vp, vp, i64, i32, i32, ctypes.c_double, vp, i32, vp]
     lib.fgnn_shard_unpack.argtypes = [vp, vp, i32, i32, i32, ctypes.c_double, vp]
+    lib.fgnn_shard_step_begin.argtypes = [vp, vp, i64, i32, i32, ctypes.c_double, vp, i32, vp]
+    lib.fgnn_shard_step_end.argtypes = [vp, vp, i32, i32, i32, ctypes.c_double, vp]
     lib.fgnn_profile_step.argtypes = [vp, i32, vp, vp, ctypes.POINTER(i32), vp]
     lib.fgnn_memcpy_sync.argtypes = [vp, vp, ctypes.c_uint64, vp]
     lib.fgnn_launch_count.argtypes = [vp]
@@ -359,6 +361,14 @@ class FlockEngine:
 
     def shard_unpack(self, recv_buf, world, rank, cap, depth):
         self._check(self.lib.fgnn_shard_unpack(self._h, _ptr(recv_buf), world, rank, cap, float(depth), self.stream))
+
+    def shard_step_begin(self, windows, window_stride, world, rank, depth, send_buf, cap):
+        self._check(self.lib.fgnn_shard_step_begin(self._h, _ptr(windows), int(window_stride), world, rank, float(depth),
+                                                   _ptr(send_buf), cap, self.stream))
+
+    def shard_step_end(self, recv_buf, world, rank, cap, depth):
+        self._check(self.lib.fgnn_shard_step_end(self._h, _ptr(recv_buf), world, rank, cap, float(depth), self.stream))
+        self.step_index += 1
 
     def profile_step(self):
         """One closed-loop step with per-kernel CUDA-event timing: [(kernel name, ms), ...]."""

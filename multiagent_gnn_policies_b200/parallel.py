@@ -76,6 +76,13 @@ class CudaShardBackend:
     def build(self, advance):
         self.engine.build_graph(advance=advance)
 
+    # CUDA-graph replayed halves of a step (same kernels as local_step+pack / unpack+build)
+    def step_begin(self, windows, window_stride, world, rank, depth, send, cap):
+        self.engine.shard_step_begin(windows, window_stride, world, rank, depth, send, cap)
+
+    def step_end(self, recv, world, rank, cap, depth):
+        self.engine.shard_step_end(recv, world, rank, cap, depth)
+
     def owned_state(self):
         return self.engine.get_state()[self.lo:self.lo + self.count]
 
@@ -131,6 +138,13 @@ class ShardedFlock:
 
     def step(self):
         """One closed-loop step: local policy + integrator for owned agents, halo exchange, rebuild."""
+        if hasattr(self.backend, "step_begin"):          # CUDA backend: two graph launches around the all-gather
+            win_view = self.recv.reshape(-1)[1:]
+            self.backend.step_begin(win_view, (self.cap + 1) * RECORD, self.world, self.rank, self.send_depth,
+                                    self.send, self.cap)
+            self.recv = self.all_gather(self.send)
+            self.backend.step_end(self.recv, self.world, self.rank, self.cap, self.depth)
+            return
         self.backend.local_step()
         self._exchange(self.recv, (self.cap + 1) * RECORD)
         self.backend.build(True)

@@ -39,7 +39,7 @@ def make_world(n_total, world, x0, sd, k=3, hidden=32, comm_radius=1.0, cap=None
     return flocks, ranges
 
 
-def drive(flocks, ranges, x0, steps, know_all=True):
+def drive(flocks, ranges, x0, steps, know_all=True, graphs=False):
     from multiagent_gnn_policies_b200 import parallel
     import torch
     world = len(flocks)
@@ -70,19 +70,35 @@ def drive(flocks, ranges, x0, steps, know_all=True):
     for f in flocks:
         f.backend.build(False)
     out = []
+    stride = (flocks[0].cap + 1) * parallel.RECORD
+    shared = flocks[0].recv.clone()              # persistent gathered buffer: stable pointers for the graph cache
+    for f in flocks:
+        f.recv = shared
     for _ in range(steps):
-        for f in flocks:
-            f.backend.local_step()
-        exchange(lambda f: f.recv, (flocks[0].cap + 1) * parallel.RECORD)
-        for f in flocks:
-            f.backend.build(True)
+        if graphs:                               # CUDA-graph replayed halves
+            for f in flocks:
+                f.backend.step_begin(shared.reshape(-1)[1:], stride, world, f.rank, f.send_depth, f.send, f.cap)
+            gathered = torch.stack([f.send for f in flocks])
+            shared.copy_(gathered)
+            for f in flocks:
+                f.backend.step_end(shared, world, f.rank, f.cap, f.depth)
+        else:
+            for f in flocks:
+                f.backend.local_step()
+            exchange(lambda f: f.recv, stride)
+            for f in flocks:
+                f.backend.build(True)
+            shared.copy_(flocks[0].recv)
+            for f in flocks:
+                f.recv = shared
         out.append((np.concatenate([f.backend.owned_state() for f in flocks]),
                     np.concatenate([f.backend.owned_action() for f in flocks])))
     return out
 
 
-@pytest.mark.parametrize("world,n_total,order", [(2, 3000, "sorted"), (4, 5000, "sorted"), (3, 1500, "random")])
-def test_sharded_equals_single_engine(world, n_total, order):
+@pytest.mark.parametrize("world,n_total,order,graphs", [(2, 3000, "sorted", False), (4, 5000, "sorted", True),
+                                                        (3, 1500, "random", False), (2, 2000, "random", True)])
+def test_sharded_equals_single_engine(world, n_total, order, graphs):
     from multiagent_gnn_policies_b200.engine import FlockEngine
     g = load_golden("ckpt_n100_k3")
     x0 = flock_env.synthetic_state(n_total, seed=31, density=1.6)
@@ -95,7 +111,7 @@ def test_sharded_equals_single_engine(world, n_total, order):
     single.load_state_dict(g["state_dict"])
     single.reset(x0)
     flocks, ranges = make_world(n_total, world, x0, g["state_dict"])
-    got = drive(flocks, ranges, x0, steps, know_all=(order != "sorted"))
+    got = drive(flocks, ranges, x0, steps, know_all=(order != "sorted"), graphs=graphs)
     for t in range(steps):
         a = np.empty((n_total, 2), np.float32)
         single.step(a, None)
