@@ -62,6 +62,7 @@ struct fgnn_handle {
     int* d_pool = nullptr;
     int* d_n_pool = nullptr;
     int* d_pack_counter = nullptr;
+    long long* d_xminmax = nullptr;
     int launch_pool = 0;             // grid sizing for kernels over the pool (pool capacity, or M)
     void* shard_graph_store = nullptr;
     // per-kernel profiling of one step (fgnn_profile_step)
@@ -208,6 +209,11 @@ extern "C" int fgnn_create(const fgnn_config* cfg, fgnn_handle** out) {
         rc |= dalloc(h, &h->d_pool, (size_t)p.pool_cap);
         rc |= dalloc(h, &h->d_n_pool, 1);
         rc |= dalloc(h, &h->d_pack_counter, 1);
+        rc |= dalloc(h, &h->d_xminmax, 2);
+        if (!rc) {
+            const long long init[2] = {0x7fffffffffffffffll, -0x7fffffffffffffffll - 1};
+            CK(cudaMemcpy(h->d_xminmax, init, sizeof init, cudaMemcpyHostToDevice));
+        }
         p.pool = h->d_pool;
         p.n_pool = h->d_n_pool;
     }
@@ -765,9 +771,9 @@ static int enqueue_shard_pack(fgnn_handle* h, const double* windows, int64_t win
     k_pool_init<<<blocks_for(p.n_own, 256), 256, 0, st>>>(p, h->d_pool, h->d_n_pool, h->d_pack_counter);
     if (launch_check(h, "pool_init")) return 1;
     k_shard_pack<<<blocks_for(p.n_own, 256), 256, 0, st>>>(p, windows, (long long)window_stride, world, rank, depth, send_buf,
-                                                            cap, h->d_pack_counter);
+                                                            cap, h->d_pack_counter, h->d_xminmax);
     if (launch_check(h, "shard_pack")) return 1;
-    k_shard_header<<<1, 1024, 0, st>>>(p, send_buf, h->d_pack_counter);
+    k_shard_header<<<1, 32, 0, st>>>(send_buf, h->d_pack_counter, h->d_xminmax);
     return launch_check(h, "shard_header");
 }
 

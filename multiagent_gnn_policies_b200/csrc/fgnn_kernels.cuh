@@ -771,44 +771,59 @@ __global__ void __launch_bounds__(128) k_controller(Params p, int centralized, i
 //   k_shard_pack  : owned agents whose x lies inside any other rank's window [lo_q - D, hi_q + D]
 //   k_shard_unpack: install the received states, append the agents to the pool list and bin them
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_shard_pack(Params p, const double* __restrict__ windows, long long wstride,
-                                                    int world, int rank, double depth, double* __restrict__ buf, int cap,
-                                                    int* __restrict__ counter) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= p.n_own) return;
-    const int a = p.a_lo + i;
-    const double4 s = p.state[a];
-    bool wanted = false;
-    for (int q = 0; q < world; ++q) {
-        if (q == rank) continue;
-        wanted = wanted || (s.x >= windows[q * wstride] - depth && s.x <= windows[q * wstride + 1] + depth);
-    }
-    if (!wanted) return;
-    const int slot = atomicAdd(counter, 1);
-    if (slot >= cap) return;                       // overflow is reported through the header count
-    double* rec = buf + (size_t)(slot + 1) * 5;
-    rec[0] = (double)a; rec[1] = s.x; rec[2] = s.y; rec[3] = s.z; rec[4] = s.w;
+// order-preserving map double <-> signed 64-bit integer (for atomicMin / atomicMax on coordinates)
+__device__ __forceinline__ long long dkey(double x) {
+    long long b = __double_as_longlong(x);
+    return b >= 0 ? b : b ^ 0x7fffffffffffffffll;
+}
+__device__ __forceinline__ double dunkey(long long k) {
+    return __longlong_as_double(k >= 0 ? k : k ^ 0x7fffffffffffffffll);
 }
 
-// own x-interval (min / max px over owned agents) -> header; one block
-__global__ void __launch_bounds__(1024) k_shard_header(Params p, double* __restrict__ buf, const int* __restrict__ counter) {
-    __shared__ double s_lo[32], s_hi[32];
-    double lo = 1e300, hi = -1e300;
-    for (int i = threadIdx.x; i < p.n_own; i += blockDim.x) {
-        const double x = p.state[p.a_lo + i].x;
-        lo = fmin(lo, x);
-        hi = fmax(hi, x);
+__global__ void __launch_bounds__(256) k_shard_pack(Params p, const double* __restrict__ windows, long long wstride,
+                                                    int world, int rank, double depth, double* __restrict__ buf, int cap,
+                                                    int* __restrict__ counter, long long* __restrict__ xminmax) {
+    __shared__ long long s_lo[8], s_hi[8];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    long long klo = 0x7fffffffffffffffll, khi = -0x7fffffffffffffffll - 1;
+    if (i < p.n_own) {
+        const int a = p.a_lo + i;
+        const double4 s = p.state[a];
+        klo = khi = dkey(s.x);
+        bool wanted = false;
+        for (int q = 0; q < world; ++q) {
+            if (q == rank) continue;
+            wanted = wanted || (s.x >= windows[q * wstride] - depth && s.x <= windows[q * wstride + 1] + depth);
+        }
+        if (wanted) {
+            const int slot = atomicAdd(counter, 1);
+            if (slot < cap) {                      // overflow is reported through the header count
+                double* rec = buf + (size_t)(slot + 1) * 5;
+                rec[0] = (double)a; rec[1] = s.x; rec[2] = s.y; rec[3] = s.z; rec[4] = s.w;
+            }
+        }
     }
+    // own x-interval: block reduce, one atomic pair per block
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-        hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        klo = min(klo, __shfl_xor_sync(0xffffffffu, klo, o));
+        khi = max(khi, __shfl_xor_sync(0xffffffffu, khi, o));
     }
-    if ((threadIdx.x & 31) == 0) { s_lo[threadIdx.x >> 5] = lo; s_hi[threadIdx.x >> 5] = hi; }
+    if ((threadIdx.x & 31) == 0) { s_lo[threadIdx.x >> 5] = klo; s_hi[threadIdx.x >> 5] = khi; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { lo = fmin(lo, s_lo[w]); hi = fmax(hi, s_hi[w]); }
-        buf[0] = (double)*counter; buf[1] = lo; buf[2] = hi; buf[3] = 0.0; buf[4] = 0.0;
+        for (int w = 1; w < 8; ++w) { klo = min(klo, s_lo[w]); khi = max(khi, s_hi[w]); }
+        atomicMin(&xminmax[0], klo);
+        atomicMax(&xminmax[1], khi);
+    }
+}
+
+// header record [count, x_lo, x_hi, 0, 0]; re-arms the interval accumulators
+__global__ void k_shard_header(double* __restrict__ buf, const int* __restrict__ counter, long long* __restrict__ xminmax) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        buf[0] = (double)*counter; buf[1] = dunkey(xminmax[0]); buf[2] = dunkey(xminmax[1]); buf[3] = 0.0; buf[4] = 0.0;
+        xminmax[0] = 0x7fffffffffffffffll;
+        xminmax[1] = -0x7fffffffffffffffll - 1;
     }
 }
 
