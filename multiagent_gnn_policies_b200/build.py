@@ -21,7 +21,7 @@ KS = (1, 2, 3, 4)
 HPS = (16, 32, 64, 128)
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-COMMON = ARCH + ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "--fmad=true"]
+COMMON = ARCH + ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "--fmad=true"] + os.environ.get("FGNN_NVCC_FLAGS", "").split()
 
 
 def nvcc_path():

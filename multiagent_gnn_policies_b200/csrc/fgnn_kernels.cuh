@@ -17,7 +17,11 @@ constexpr int FINAL_THREADS = 128;   // block size of the fused final kernel and
 constexpr int DENSE_MT = 32;         // m-tile of the dense Actor kernel
 constexpr int RSLOTS = 64;          // reward accumulators per episode (spreads same-address atomics)
 constexpr int ELLW = 8;             // neighbours kept inline per agent: one dependent load less per gather
-constexpr int HOP_UNROLL = 4;        // edges gathered concurrently per thread in the hop loops
+#ifndef FGNN_HOP_UNROLL
+#define FGNN_HOP_UNROLL 2
+#endif
+constexpr int HOP_UNROLL = FGNN_HOP_UNROLL;        // edges gathered concurrently per thread in the hop loops (measured: 2 beats 1 and 4 -- the gathers
+                                                   // are latency-bound and more registers cost more in occupancy than the extra loads in flight gain)
 
 // All device pointers one step needs.  Passed by value to every kernel.
 struct Params {
@@ -332,10 +336,9 @@ __global__ void __launch_bounds__(256) k_canon(Params p) {
 // K_D  adjacency + degree + 6-d relative features (gym_flock compute_helpers), CSR/ELL emission.
 //      One thread per agent, in cell-sorted order; float64 arithmetic for the radius cut and the
 //      feature sums (bit-identical edge set to the float64 oracle).
-//      Phase 1 (filter): scan the 3x3 cell neighbourhood (the three cells of a grid row are one
-//        contiguous slot range), stage the slots of accepted neighbours in shared memory.
-//      Phase 2 (compute): loop over the staged neighbours only -- the divide-heavy feature math is
-//        not executed under the divergent accept branch of the candidate loop.
+//      Single pass over the 3x3 cell neighbourhood (the three cells of a grid row are one contiguous
+//      slot range): features accumulate in the accept branch, accepted neighbour ids are staged in
+//      shared memory.  (A filter-then-compute split was measured slower: more registers, lower occupancy.)
 //      The warp reserves one contiguous run of CSR edge slots for its 32 rows; the first ELLW
 //      neighbour ids are also stored inline per agent (ELL head).  Rows longer than the stage
 //      re-scan their tail.
@@ -358,6 +361,7 @@ __global__ void __launch_bounds__(ADJ_THREADS) k_adjacency(Params p, int stage_c
     double4 me = make_double4(0, 0, 0, 0);
     int q0[9], q1[9];
     int count = 0;
+    double f0 = 0, f1 = 0, f2 = 0, f3 = 0, f4 = 0, f5 = 0;
     if (valid) {
         a = p.sorted_id[s];
         me = p.sorted_state[s];
@@ -384,10 +388,19 @@ __global__ void __launch_bounds__(ADJ_THREADS) k_adjacency(Params p, int stage_c
 #pragma unroll
         for (int j = 0; j < 9; ++j) {
             for (int q = q0[j]; q < q1[j]; ++q) {
-                const double2 o = *reinterpret_cast<const double2*>(&p.sorted_state[q]);
-                const double r2 = r2_exact(me.x - o.x, me.y - o.y);
+                const double4 o = p.sorted_state[q];
+                const double dx = me.x - o.x, dy = me.y - o.y;
+                const double r2 = r2_exact(dx, dy);
                 if (q != s && r2 < p.R2) {
-                    if (count < stage_cap) s_stage[count * ADJ_THREADS + tid] = q;
+                    const double inv = 1.0 / r2;
+                    const double inv2 = inv * inv;
+                    f0 += me.z - o.z;
+                    f1 += dx * inv2;
+                    f2 += dx * inv;
+                    f3 += me.w - o.w;
+                    f4 += dy * inv2;
+                    f5 += dy * inv;
+                    if (count < stage_cap) s_stage[count * ADJ_THREADS + tid] = __ldg(&p.sorted_id[q]);
                     ++count;
                 }
             }
@@ -415,47 +428,23 @@ __global__ void __launch_bounds__(ADJ_THREADS) k_adjacency(Params p, int stage_c
     int head[ELLW];
 #pragma unroll
     for (int e = 0; e < ELLW; ++e) head[e] = -1;
-    double f0 = 0, f1 = 0, f2 = 0, f3 = 0, f4 = 0, f5 = 0;
     const int staged = count < stage_cap ? count : stage_cap;
     for (int e = 0; e < staged; ++e) {
-        const int q = s_stage[e * ADJ_THREADS + tid];
-        const double4 o = p.sorted_state[q];
-        const int id = __ldg(&p.sorted_id[q]);
-        const double dx = me.x - o.x, dy = me.y - o.y;
-        const double r2 = r2_exact(dx, dy);
-        const double inv = 1.0 / r2;
-        const double inv2 = inv * inv;
-        f0 += me.z - o.z;
-        f1 += dx * inv2;
-        f2 += dx * inv;
-        f3 += me.w - o.w;
-        f4 += dy * inv2;
-        f5 += dy * inv;
+        const int id = s_stage[e * ADJ_THREADS + tid];
         cols[e] = id;
 #pragma unroll
         for (int u = 0; u < ELLW; ++u)
             if (u == e) head[u] = id;
     }
-    if (count > stage_cap) {                              // long row: re-scan for the tail (same order)
+    if (count > stage_cap) {                              // long row: re-scan for the ids beyond the stage (same order)
         int w = 0;
 #pragma unroll
         for (int j = 0; j < 9; ++j) {
             for (int q = q0[j]; q < q1[j]; ++q) {
-                const double4 o = p.sorted_state[q];
-                const double dx = me.x - o.x, dy = me.y - o.y;
-                const double r2 = r2_exact(dx, dy);
+                const double2 o = *reinterpret_cast<const double2*>(&p.sorted_state[q]);
+                const double r2 = r2_exact(me.x - o.x, me.y - o.y);
                 if (q != s && r2 < p.R2) {
-                    if (w >= stage_cap) {
-                        const double inv = 1.0 / r2;
-                        const double inv2 = inv * inv;
-                        f0 += me.z - o.z;
-                        f1 += dx * inv2;
-                        f2 += dx * inv;
-                        f3 += me.w - o.w;
-                        f4 += dy * inv2;
-                        f5 += dy * inv;
-                        cols[w] = __ldg(&p.sorted_id[q]);
-                    }
+                    if (w >= stage_cap) cols[w] = __ldg(&p.sorted_id[q]);
                     ++w;
                 }
             }
