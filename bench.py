@@ -89,7 +89,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                          "-lms", "20", "-i", str(self.index)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -125,6 +125,16 @@ class ClockSampler:
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full`
+    capture of this workload (profiles/r1_traffic.json), or None."""
+    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    try:
+        return json.load(open(path)).get(kernel)
+    except Exception:
+        return None
 
 
 def measured_peaks():
@@ -175,8 +185,8 @@ def run_cpu_reference(n_sample, steps, warmup, hidden, k, n_layers, seed=11):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n-agents", type=int, default=1_000_000, help="agents per GPU")
     ap.add_argument("--hidden", type=int, default=32)
@@ -308,7 +318,8 @@ def main():
     alg_bytes = {"adjacency": 44 + 4 * d, "hop0": 104 + 4 * d, "final": 120 + 4 * d}
     dom = max(prof, key=prof.get)
     step_ms_prof = sum(prof.values())
-    roof = {"bound": "hbm", "kernel": dom, "unit": "GB/s", "peak": peak, "peak_source": peak_src, "traffic": None,
+    roof = {"bound": "hbm", "kernel": dom, "unit": "GB/s", "peak": peak, "peak_source": peak_src,
+            "traffic": ncu_traffic(dom) if (N == 1_000_000 and args.k == 3 and args.hidden == 32) else None,
             "kernel_ms": prof[dom], "kernel_share_of_step": prof[dom] / step_ms_prof,
             "per_kernel_ms": {k_: round(v, 5) for k_, v in prof.items()}}
     if dom in alg_bytes and args.k == 3:

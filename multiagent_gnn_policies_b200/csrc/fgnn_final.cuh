@@ -138,6 +138,8 @@ __global__ void __launch_bounds__(FINAL_THREADS) k_final(Params p) {
         float in[F * K];
 #pragma unroll
         for (int i = 0; i < F * K; ++i) in[i] = 0.f;
+        double4 st_own = make_double4(0, 0, 0, 0);         // integrator input, fetched early: its latency hides behind the gather
+        if (CLOSED && valid) st_own = p.state[a];
         if (valid) {
             {   // z_0 = x_t
                 float v[F];
@@ -172,7 +174,7 @@ __global__ void __launch_bounds__(FINAL_THREADS) k_final(Params p) {
         mlp_ffma<F * K, HP, FINAL_THREADS>(in, WIDE ? p.weights : smem, wl, sh_act, o0, o1);
         if (valid) {
             reinterpret_cast<float2*>(p.action)[a] = make_float2(o0, o1);
-            if (CLOSED) integrate_and_bin(p, a, o0, o1, racc);
+            if (CLOSED) integrate_and_bin(p, a, st_own, o0, o1, racc);
         }
     }
     if (CLOSED) reward_block_flush<FINAL_THREADS>(p, racc);

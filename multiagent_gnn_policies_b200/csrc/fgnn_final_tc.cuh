@@ -176,6 +176,8 @@ __global__ void __launch_bounds__(FINAL_THREADS) k_final_tc(Params p, const uint
         float in[K0];
 #pragma unroll
         for (int i = 0; i < K0; ++i) in[i] = 0.f;
+        double4 st_own = make_double4(0, 0, 0, 0);         // integrator input, fetched early: its latency hides behind the gather
+        if (CLOSED && valid) st_own = p.state[a];
         if (valid) {
             {   // z_0 = x_t
                 float v[F];
@@ -297,7 +299,7 @@ __global__ void __launch_bounds__(FINAL_THREADS) k_final_tc(Params p, const uint
         }
         if (valid) {
             reinterpret_cast<float2*>(p.action)[a] = make_float2(o0, o1);
-            if (CLOSED) integrate_and_bin(p, a, o0, o1, racc);
+            if (CLOSED) integrate_and_bin(p, a, st_own, o0, o1, racc);
         }
     }
     if (CLOSED) reward_block_flush<FINAL_THREADS>(p, racc);

@@ -579,8 +579,8 @@ __global__ void __launch_bounds__(256) k_hop(Params p, int j) {
 }
 
 // double integrator exactly in numpy's evaluation order (no FMA contraction), then bin the new position
-__device__ __forceinline__ void integrate_and_bin(const Params& p, int a, float u0, float u1, double (&racc)[4]) {
-    double4 s = p.state[a];
+__device__ __forceinline__ void integrate_and_bin(const Params& p, int a, const double4 s, float u0, float u1,
+                                                  double (&racc)[4]) {
     const double ax = __dmul_rn((double)u0, p.gain), ay = __dmul_rn((double)u1, p.gain);
     double nx = __dadd_rn(s.x, __dmul_rn(s.z, p.dt));
     double ny = __dadd_rn(s.y, __dmul_rn(s.w, p.dt));
@@ -657,7 +657,7 @@ __global__ void __launch_bounds__(256) k_integrate(Params p, const float* __rest
     double racc[4] = {0, 0, 0, 0};
     if (i < p.n_own) {
         const float2 uu = reinterpret_cast<const float2*>(u)[a];
-        integrate_and_bin(p, a, uu.x, uu.y, racc);
+        integrate_and_bin(p, a, p.state[a], uu.x, uu.y, racc);
     }
     reward_block_flush<256>(p, racc);
 }
