@@ -34,7 +34,7 @@ DENSITY = 1.6
 FALLBACK_HBM_GBS = 6650.0      # /opt/skills/guides/B200_PROFILING.md fallback
 
 
-def make_workload(n_agents, seed=11, density=DENSITY, v_max=3.0, min_dist=0.1, x_offset=0.0):
+def make_workload(n_agents, seed=11, density=DENSITY, v_max=3.0, min_dist=0.1, x_offset=0.0, bias_seed=None):
     """SURVEY.md 8(d) synthetic state: uniform square of side sqrt(N/density), cell-major order,
     no pair closer than min_dist (gym_flock's reset threshold)."""
     from scipy.spatial import cKDTree
@@ -48,7 +48,8 @@ def make_workload(n_agents, seed=11, density=DENSITY, v_max=3.0, min_dist=0.1, x
             break
         bad = np.unique(pairs[:, 1])
         x[bad, 0:2] = rng.uniform(0.0, side, size=(bad.size, 2))
-    bias = rng.uniform(-v_max, v_max, size=(2,))
+    # one flock = one common velocity bias: strips of a sharded flock pass the same bias_seed
+    bias = (rng if bias_seed is None else np.random.default_rng(bias_seed)).uniform(-v_max, v_max, size=(2,))
     x[:, 2:4] = rng.uniform(-v_max, v_max, size=(n_agents, 2)) + bias
     order = np.lexsort((np.floor(x[:, 0]).astype(np.int64), np.floor(x[:, 1]).astype(np.int64)))
     x = x[order]
@@ -359,9 +360,14 @@ def run_sharded(args, rank, world, local_rank, N, side, sd, weights_note, edge_c
     x_global[:, 0] = parallel.FAR
     for q in (rank - 1, rank, rank + 1):
         if 0 <= q < world:
-            x_global[ranges[q][0]:ranges[q][0] + ranges[q][1]] = make_workload(N, seed=11 + q, x_offset=q * side)
+            x_global[ranges[q][0]:ranges[q][0] + ranges[q][1]] = make_workload(N, seed=11 + q, x_offset=q * side,
+                                                                               bias_seed=11)
     depth = parallel.halo_depth(args.k, args.radius)
-    halo_cap = int(1.6 * (depth + args.radius) * side * DENSITY * 2) + 1024        # both boundaries, with slack
+    # both boundaries; agents of neighbouring strips interpenetrate as the rollout goes on (no re-partitioning
+    # yet), which widens the x-windows: size the buffers for the whole run (warm-up + timed + e2e steps)
+    total_steps = args.warmup + args.steps + (args.e2e_steps or min(args.steps, 50)) + 8
+    mix = 0.06 * total_steps                                                       # measured max penetration per step
+    halo_cap = int(1.3 * (depth + args.radius + 2 * mix) * side * DENSITY * 2) + 1024
     cell = args.radius
     gx = int(np.ceil((side + 2 * depth + 4) / cell)) + 2
     gy = int(np.ceil(side / cell)) + 4
