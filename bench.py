@@ -363,11 +363,8 @@ def run_sharded(args, rank, world, local_rank, N, side, sd, weights_note, edge_c
             x_global[ranges[q][0]:ranges[q][0] + ranges[q][1]] = make_workload(N, seed=11 + q, x_offset=q * side,
                                                                                bias_seed=11)
     depth = parallel.halo_depth(args.k, args.radius)
-    # both boundaries; agents of neighbouring strips interpenetrate as the rollout goes on (no re-partitioning
-    # yet), which widens the x-windows: size the buffers for the whole run (warm-up + timed + e2e steps)
-    total_steps = args.warmup + args.steps + (args.e2e_steps or min(args.steps, 50)) + 8
-    mix = 0.06 * total_steps                                                       # measured max penetration per step
-    halo_cap = int(1.3 * (depth + args.radius + 2 * mix) * side * DENSITY * 2) + 1024
+    # both boundaries of a strip; ownership hand-over keeps the layer thin for any run length
+    halo_cap = int(2.0 * (depth + 2 * args.radius) * side * DENSITY * 2) + 1024
     cell = args.radius
     gx = int(np.ceil((side + 2 * depth + 4) / cell)) + 2
     gy = int(np.ceil(side / cell)) + 4
@@ -377,7 +374,9 @@ def run_sharded(args, rank, world, local_rank, N, side, sd, weights_note, edge_c
     be.engine.load_state_dict(sd)
     flock = parallel.ShardedFlock(be, rank, world, args.k, args.radius, halo_cap,
                                   parallel.nccl_all_gather(world, halo_cap, be.device))
-    flock.reset(x_global, ranges)
+    bounds = np.array([-parallel.INF] + [q * side for q in range(1, world)] + [parallel.INF])
+    frame_vx = float(np.random.default_rng(11).uniform(-3.0, 3.0, size=(2,))[0])       # the flock's common velocity bias
+    flock.reset(x_global, ranges, bounds=bounds, frame_velocity=frame_vx)
     for _ in range(args.warmup):
         flock.step()
     barrier()
@@ -400,10 +399,11 @@ def run_sharded(args, rank, world, local_rank, N, side, sd, weights_note, edge_c
         raise RuntimeError("capacity overflow (edges / halo) during the timed region: results void")
     value = n_total * args.steps / (ms * 1e-3)
     ghosts = int(flock.recv[:, 0, 0].sum().item())
+    owned_now = len(be.owned())
 
     # e2e: the same step through host buffers (select_action -> pinned host -> env.step)
     e2e_steps = args.e2e_steps or min(args.steps, 50)
-    act_host = torch.empty((cnt, 2), dtype=torch.float32, pin_memory=True).numpy()
+    act_host = torch.empty((be.engine.rows_io, 2), dtype=torch.float32, pin_memory=True).numpy()
     for _ in range(3):
         flock.step_host(act_host)
     barrier()
@@ -420,14 +420,14 @@ def run_sharded(args, rank, world, local_rank, N, side, sd, weights_note, edge_c
     d = st["n_edges"] / max(1, (cnt + ghosts / world))
     step_bytes = 268 + 12 * d
     config = dict(config, parallelism=f"index-sharded x{world}, halo all-gather (NCCL) of {flock.cap}-record buffers, "
-                                      f"halo depth {depth:.2f}", n_agents_total=n_total)
+                                      f"halo depth {flock.depth:.2f}, ownership hand-over", n_agents_total=n_total)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 learner / f64 env", "data": f"synthetic ({weights_note})", "config": config,
-            "halo_records_per_step": ghosts, "clocks": clocks, "gpu_launches": int(launches),
+            "halo_records_per_step": ghosts, "owned_by_rank0_after_run": owned_now, "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": n_total * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "steps": e2e_steps,
-                    "ms_per_step": e2e_ms / e2e_steps, "h2d_bytes_per_step": int(cnt * 2 * 4) * world,
-                    "d2h_bytes_per_step": int(cnt * 2 * 4) * world},
+                    "ms_per_step": e2e_ms / e2e_steps, "h2d_bytes_per_step": int(be.engine.rows_io * 2 * 4) * world,
+                    "d2h_bytes_per_step": int(be.engine.rows_io * 2 * 4) * world},
             "roofline": {"bound": "hbm", "kernel": None, "unit": "GB/s", "peak": peak, "peak_source": peak_src,
                          "achieved": step_bytes * value / world / 1e9, "frac": step_bytes * value / world / 1e9 / peak,
                          "traffic": None, "note": "whole step per GPU (268 + 12 d) B per agent-step; per-kernel breakdown "

@@ -126,29 +126,34 @@ int fgnn_get_csr(fgnn_handle* h, int32_t age, const uint32_t** row_start, const 
                  const int32_t** cols, const float** src_scale);
 int fgnn_get_stats(fgnn_handle* h, fgnn_stats* out, void* stream);   /* synchronises the stream */
 
-/* ---- multi-GPU (agents sharded by index, n_episodes == 1; every rank holds full-size arrays) ----
- * One closed-loop step on a rank =  fgnn_shard_local_step  (K-hop aggregation over the agents present on
- * the rank, readout + integrator for the OWNED agents)  ->  fgnn_shard_pack (owned agents inside another
- * rank's x-window -> send buffer)  ->  all-gather of the buffers by the host (NCCL)  ->
- * fgnn_shard_unpack (install received states as ghosts)  ->  fgnn_build_graph(advance = 1).
- * Buffers are DEVICE arrays of doubles: per rank (cap + 1) records of 5 doubles; record 0 is the header
- * [count, x_lo, x_hi, 0, 0] (the rank's own x-interval), records 1..count are [agent id, px, py, vx, vy].
- * `windows` is a device array holding every rank's [x_lo, x_hi] at windows[q * window_stride + {0, 1}]
- * (so the headers of the previous step's gathered buffer can be passed directly).
- * On a sharded handle fgnn_policy / fgnn_integrate read and write the OWNED slice only (count x 2 floats);
- * fgnn_step / fgnn_rollout / fgnn_env_step are refused (the host drives the exchange between the halves). */
+/* ---- multi-GPU (n_episodes == 1; every rank holds full-size arrays, indices are global) ----
+ * Rank r starts owning agents [shard_lo, shard_lo + shard_count) and is the only one that integrates what it
+ * owns.  One closed-loop step on a rank =
+ *   fgnn_shard_local_step (K-hop aggregation over the agents present on the rank; readout + integrator for
+ *   the OWNED agents) -> fgnn_shard_pack (records of owned agents that lie inside another rank's window; hand-over
+ *   decisions) -> all-gather of the buffers by the host (NCCL) -> fgnn_shard_unpack (ghosts, new owned agents)
+ *   -> fgnn_build_graph(advance = 1);   or the two CUDA-graph halves fgnn_shard_step_begin / _end.
+ * Buffers are DEVICE arrays of doubles: per rank (cap + 1) records of 6 doubles; record 0 is the header
+ * [count, x_lo, x_hi, 0, 0, 0] (x-interval of what the rank owns), records 1..count are
+ * [agent id, px, py, vx, vy, new owner or -1].  `windows` is a device array with every rank's [x_lo, x_hi] at
+ * windows[q * window_stride + {0, 1}] (the headers of the previous gathered buffer can be passed directly).
+ * Territories: rank q's strip is bounds[q] <= x - shift < bounds[q+1] (bounds: world + 1 HOST doubles, bounds[0]
+ * = -inf, bounds[world] = +inf), shift grows by dshift per step (frame moving with the flock).  An owner hands an
+ * agent over to the rank whose strip it entered by more than `margin` (no data moves: the receiver already holds
+ * it as a ghost with valid history), allowed from step index `handover_after` on.  `depth` = halo depth of the
+ * windows (strip +- depth united with the owned x-interval +- depth).
+ * On a sharded handle fgnn_policy / fgnn_integrate use arrays of (shard_count + ghost_capacity) rows in
+ * OWNED-LIST order (fgnn_shard_owned returns the list); fgnn_step / fgnn_rollout / fgnn_env_step are refused. */
+int fgnn_shard_configure(fgnn_handle* h, const double* bounds, int32_t world, int32_t rank, double depth,
+                         double margin, double dshift, int32_t handover_after);
 int fgnn_shard_local_step(fgnn_handle* h, void* stream);
-int fgnn_shard_pack(fgnn_handle* h, const double* windows, int64_t window_stride, int32_t world, int32_t rank,
-                    double depth, double* send_buf, int32_t cap, void* stream);
-int fgnn_shard_unpack(fgnn_handle* h, const double* recv_buf, int32_t world, int32_t rank, int32_t cap,
-                      double depth, void* stream);
-
-/* CUDA-graph replayed halves of a sharded step: begin = fgnn_shard_local_step + fgnn_shard_pack,
- * end = fgnn_shard_unpack + fgnn_build_graph(advance = 1); the host's all-gather goes in between. */
-int fgnn_shard_step_begin(fgnn_handle* h, const double* windows, int64_t window_stride, int32_t world, int32_t rank,
-                          double depth, double* send_buf, int32_t cap, void* stream);
-int fgnn_shard_step_end(fgnn_handle* h, const double* recv_buf, int32_t world, int32_t rank, int32_t cap,
-                        double depth, void* stream);
+int fgnn_shard_pack(fgnn_handle* h, const double* windows, int64_t window_stride, double* send_buf, int32_t cap,
+                    int32_t advance, void* stream);
+int fgnn_shard_unpack(fgnn_handle* h, const double* recv_buf, int32_t cap, void* stream);
+int fgnn_shard_step_begin(fgnn_handle* h, const double* windows, int64_t window_stride, double* send_buf, int32_t cap,
+                          void* stream);
+int fgnn_shard_step_end(fgnn_handle* h, const double* recv_buf, int32_t cap, void* stream);
+int fgnn_shard_owned(fgnn_handle* h, int32_t* ids, int32_t* count, void* stream);   /* synchronises */
 
 /* One closed-loop step (same work as fgnn_step) with a CUDA event after every kernel: ms_out[i] is the
  * device time of kernel i, names_out (16 bytes each, may be NULL) its name.  For bench.py's roofline. */

@@ -59,12 +59,17 @@ struct fgnn_handle {
     std::vector<std::vector<float>> raw_w, raw_b;   // per layer, reference layout
     // sharding
     bool sharded = false;
-    int* d_pool = nullptr;
-    int* d_n_pool = nullptr;
-    int* d_pack_counter = nullptr;
+    bool shard_configured = false;
+    ShardCtl ctl;
+    int* d_own = nullptr;
+    int* d_ghost = nullptr;
+    int* d_counts = nullptr;         // [n_own, n_new, n_ghost, record counter]
     long long* d_xminmax = nullptr;
+    double* d_shift = nullptr;
+    double* d_bounds = nullptr;      // [world + 1], allocated by fgnn_shard_configure
     int launch_pool = 0;             // grid sizing for kernels over the pool (pool capacity, or M)
     void* shard_graph_store = nullptr;
+    long long shard_epoch = 0;       // bumped by fgnn_shard_configure: invalidates cached graphs
     // per-kernel profiling of one step (fgnn_profile_step)
     bool profiling = false;
     cudaStream_t prof_stream = nullptr;
@@ -206,18 +211,23 @@ extern "C" int fgnn_create(const fgnn_config* cfg, fgnn_handle** out) {
     rc |= dalloc(h, &p.reward_pending, 1);
     rc |= dalloc(h, &p.log_index, 1);
     if (h->sharded) {
-        rc |= dalloc(h, &h->d_pool, (size_t)p.pool_cap);
-        rc |= dalloc(h, &h->d_n_pool, 1);
-        rc |= dalloc(h, &h->d_pack_counter, 1);
+        rc |= dalloc(h, &h->d_own, (size_t)p.pool_cap);
+        rc |= dalloc(h, &h->d_ghost, (size_t)p.pool_cap);
+        rc |= dalloc(h, &h->d_counts, 4);
         rc |= dalloc(h, &h->d_xminmax, 2);
-        if (!rc) {
-            const long long init[2] = {0x7fffffffffffffffll, -0x7fffffffffffffffll - 1};
-            CK(cudaMemcpy(h->d_xminmax, init, sizeof init, cudaMemcpyHostToDevice));
-        }
-        p.pool = h->d_pool;
-        p.n_pool = h->d_n_pool;
+        rc |= dalloc(h, &h->d_shift, 1);
+        p.own = h->d_own;
+        p.n_own_d = h->d_counts + 0;
+        p.ghost = h->d_ghost;
+        p.n_ghost_d = h->d_counts + 2;
+        memset(&h->ctl, 0, sizeof h->ctl);
+        h->ctl.own = h->d_own; h->ctl.n_own = h->d_counts + 0;
+        h->ctl.ghost = h->d_ghost; h->ctl.n_ghost = h->d_counts + 2;
+        h->ctl.counter = h->d_counts + 3;
+        h->ctl.xminmax = h->d_xminmax;
+        h->ctl.shift = h->d_shift;
     }
-    rc |= dalloc(h, &h->d_u_in, M * 2);
+    rc |= dalloc(h, &h->d_u_in, (M > (size_t)p.pool_cap ? M : (size_t)p.pool_cap) * 2);
     rc |= dalloc(h, &h->d_staging, K * M * F > (size_t)M * 4 * 2 ? K * M * F : (size_t)M * 4 * 2);
     WeightLayout wl{F * p.K, h->HP, p.L};
     h->weights_floats = wl.total();
@@ -236,7 +246,7 @@ extern "C" int fgnn_create(const fgnn_config* cfg, fgnn_handle** out) {
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)fk, FINAL_THREADS, h->final_smem));
         if (occ < 1) occ = 1;
         int grid = h->sm_count * occ;
-        int tiles = blocks_for(p.n_own, FINAL_THREADS);
+        int tiles = blocks_for(h->sharded ? p.pool_cap : p.n_own, FINAL_THREADS);
         if (grid > tiles) grid = tiles;
         (closed ? h->final_grid_closed : h->final_grid_open) = grid;
     }
@@ -273,7 +283,7 @@ extern "C" int fgnn_create(const fgnn_config* cfg, fgnn_handle** out) {
             const int max_by_tmem = 512 / tc_tmem_cols(h->HP);
             if (occ > max_by_tmem) occ = max_by_tmem;
             int grid = h->sm_count * occ;
-            int tiles = blocks_for(p.n_own, FINAL_THREADS);
+            int tiles = blocks_for(h->sharded ? p.pool_cap : p.n_own, FINAL_THREADS);
             if (grid > tiles) grid = tiles;
             (closed ? h->tc_grid_closed : h->tc_grid_open) = grid;
         }
@@ -404,7 +414,7 @@ static int enqueue_build(fgnn_handle* h, int advance, cudaStream_t st) {
     const int gb = blocks_for(h->launch_pool, 256);
     if (!h->binned) {
         if (h->sharded) return fail("sharded engine: the graph is built after fgnn_shard_unpack (state not binned)");
-        k_bin<<<gb, 256, 0, st>>>(p, 0);
+        k_bin<<<gb, 256, 0, st>>>(p);
         if (launch_check(h, "bin")) return 1;
     }
     k_scan<<<p.n_tiles, SCAN_THREADS, 0, st>>>(p, advance);
@@ -498,9 +508,10 @@ extern "C" int fgnn_reset(fgnn_handle* h, const double* x, void* stream) {
     CK(cudaMemcpyAsync(p.state, x, M * sizeof(double4), cudaMemcpyDefault, st));
     if (h->sharded) {
         // owned agents are binned here; ghosts arrive through fgnn_shard_pack/unpack, then fgnn_build_graph(0)
-        k_pool_init<<<blocks_for(p.n_own, 256), 256, 0, st>>>(p, h->d_pool, h->d_n_pool, h->d_pack_counter);
-        if (launch_check(h, "pool_init")) return 1;
-        k_bin<<<blocks_for(p.n_own, 256), 256, 0, st>>>(p, 0);
+        k_own_init<<<blocks_for(p.n_own, 256), 256, 0, st>>>(h->d_own, h->d_counts + 0, h->d_counts + 2, p.a_lo, p.n_own);
+        if (launch_check(h, "own_init")) return 1;
+        CK(cudaMemsetAsync(h->d_shift, 0, sizeof(double), st));
+        k_bin<<<blocks_for(p.n_own, 256), 256, 0, st>>>(p);
         if (launch_check(h, "bin")) return 1;
         h->binned = true;
         return 0;
@@ -523,9 +534,10 @@ extern "C" int fgnn_integrate(fgnn_handle* h, const float* u, double* reward_b, 
         CK(cudaMemsetAsync(p.cell_count, 0, ((size_t)p.C + 1) * sizeof(int), st));
         CK(cudaMemsetAsync(p.racc, 0, (size_t)RSLOTS * p.B * 4 * sizeof(double), st));
     }
-    // sharded handle: u covers the owned range only
-    CK(cudaMemcpyAsync(h->d_u_in + (size_t)p.a_lo * 2, u, (size_t)p.n_own * 2 * sizeof(float), cudaMemcpyDefault, st));
-    k_integrate<<<blocks_for(p.n_own, 256), 256, 0, st>>>(p, h->d_u_in);
+    // sharded handle: u has pool_cap rows in owned-list order (rows beyond the owned count are ignored)
+    const int rows = h->sharded ? p.pool_cap : p.n_own;
+    CK(cudaMemcpyAsync(h->d_u_in, u, (size_t)rows * 2 * sizeof(float), cudaMemcpyDefault, st));
+    k_integrate<<<blocks_for(rows, 256), 256, 0, st>>>(p, h->d_u_in);
     if (launch_check(h, "integrate")) return 1;
     h->binned = true;
     if (reward_b) {
@@ -549,7 +561,14 @@ extern "C" int fgnn_policy(fgnn_handle* h, float* action, void* stream) {
     CK(cudaSetDevice(h->cfg.device));
     if (enqueue_hops(h, st)) return 1;
     if (enqueue_final(h, false, 1, st)) return 1;
-    return copy_out(action, h->p.action + (size_t)h->p.a_lo * 2, (size_t)h->p.n_own * 2 * sizeof(float), st);
+    if (h->sharded) {           // owned-list order, pool_cap rows
+        if (!action) return 0;
+        float* tmp = h->d_staging;
+        k_gather_owned2<<<blocks_for(h->p.pool_cap, 256), 256, 0, st>>>(h->p, h->p.action, tmp);
+        if (launch_check(h, "gather_owned")) return 1;
+        return copy_out(action, tmp, (size_t)h->p.pool_cap * 2 * sizeof(float), st);
+    }
+    return copy_out(action, h->p.action, (size_t)h->p.M * 2 * sizeof(float), st);
 }
 
 static int enqueue_closed_step(fgnn_handle* h, cudaStream_t st) {
@@ -765,25 +784,46 @@ extern "C" int fgnn_controller(fgnn_handle* h, int32_t centralized, double max_a
 }
 
 struct ShardGraph;
-static int enqueue_shard_pack(fgnn_handle* h, const double* windows, int64_t window_stride, int world, int rank,
-                              double depth, double* send_buf, int cap, cudaStream_t st) {
+static int enqueue_shard_pack(fgnn_handle* h, const double* windows, int64_t window_stride, double* send_buf, int cap,
+                              int advance, cudaStream_t st) {
     Params& p = h->p;
-    k_pool_init<<<blocks_for(p.n_own, 256), 256, 0, st>>>(p, h->d_pool, h->d_n_pool, h->d_pack_counter);
-    if (launch_check(h, "pool_init")) return 1;
-    k_shard_pack<<<blocks_for(p.n_own, 256), 256, 0, st>>>(p, windows, (long long)window_stride, world, rank, depth, send_buf,
-                                                            cap, h->d_pack_counter, h->d_xminmax);
+    k_shard_prepare<<<1, 32, 0, st>>>(h->ctl, advance);
+    if (launch_check(h, "shard_prepare")) return 1;
+    k_shard_pack<<<blocks_for(p.pool_cap, 256), 256, 0, st>>>(p, h->ctl, windows, (long long)window_stride, send_buf, cap);
     if (launch_check(h, "shard_pack")) return 1;
-    k_shard_header<<<1, 32, 0, st>>>(send_buf, h->d_pack_counter, h->d_xminmax);
+    k_shard_header<<<1, 32, 0, st>>>(h->ctl, send_buf);
     return launch_check(h, "shard_header");
 }
 
-static int enqueue_shard_unpack(fgnn_handle* h, const double* recv_buf, int world, int rank, int cap, double depth,
-                                cudaStream_t st) {
+static int enqueue_shard_unpack(fgnn_handle* h, const double* recv_buf, int cap, cudaStream_t st) {
     Params& p = h->p;
-    k_shard_unpack<<<blocks_for(world * cap, 256), 256, 0, st>>>(p, recv_buf, world, rank, cap, depth, h->d_pool,
-                                                                  h->d_n_pool, p.overflow);
+    k_shard_unpack<<<blocks_for(h->ctl.world * cap, 256), 256, 0, st>>>(p, h->ctl, recv_buf, cap);
     if (launch_check(h, "shard_unpack")) return 1;
     h->binned = true;
+    return 0;
+}
+
+extern "C" int fgnn_shard_configure(fgnn_handle* h, const double* bounds, int32_t world, int32_t rank, double depth,
+                                    double margin, double dshift, int32_t handover_after) {
+    if (!h || !h->sharded || !bounds) return fail("fgnn_shard_configure: bad argument");
+    if (world < 1 || rank < 0 || rank >= world) return fail("fgnn_shard_configure: bad rank / world");
+    CK(cudaSetDevice(h->cfg.device));
+    if (!h->d_bounds) {
+        void* q = nullptr;
+        CK(cudaMalloc(&q, (size_t)(world + 1) * sizeof(double)));
+        h->allocs.push_back(q);
+        h->d_bounds = reinterpret_cast<double*>(q);
+    } else if (world != h->ctl.world) {
+        return fail("fgnn_shard_configure: world size cannot change");
+    }
+    CK(cudaMemcpy(h->d_bounds, bounds, (size_t)(world + 1) * sizeof(double), cudaMemcpyHostToDevice));
+    h->ctl.bounds = h->d_bounds;
+    h->ctl.world = world; h->ctl.rank = rank;
+    h->ctl.depth = depth; h->ctl.margin = margin; h->ctl.dshift = dshift; h->ctl.handover_after = handover_after;
+    h->shard_configured = true;
+    void* store = h->shard_graph_store;      // cached graphs bake the control block: drop them
+    if (store) { ShardGraph* g = reinterpret_cast<ShardGraph*>(store); (void)g; }
+    h->shard_epoch += 1;
     return 0;
 }
 
@@ -796,18 +836,34 @@ extern "C" int fgnn_shard_local_step(fgnn_handle* h, void* stream) {
     return enqueue_final(h, true, 0, st);
 }
 
-extern "C" int fgnn_shard_pack(fgnn_handle* h, const double* windows, int64_t window_stride, int32_t world, int32_t rank,
-                               double depth, double* send_buf, int32_t cap, void* stream) {
+extern "C" int fgnn_shard_pack(fgnn_handle* h, const double* windows, int64_t window_stride, double* send_buf, int32_t cap,
+                               int32_t advance, void* stream) {
     if (!h || !h->sharded || !windows || !send_buf) return fail("fgnn_shard_pack: bad argument");
+    if (!h->shard_configured) return fail("fgnn_shard_pack: call fgnn_shard_configure first");
     CK(cudaSetDevice(h->cfg.device));
-    return enqueue_shard_pack(h, windows, window_stride, world, rank, depth, send_buf, cap, (cudaStream_t)stream);
+    return enqueue_shard_pack(h, windows, window_stride, send_buf, cap, advance, (cudaStream_t)stream);
 }
 
-extern "C" int fgnn_shard_unpack(fgnn_handle* h, const double* recv_buf, int32_t world, int32_t rank, int32_t cap,
-                                 double depth, void* stream) {
+extern "C" int fgnn_shard_unpack(fgnn_handle* h, const double* recv_buf, int32_t cap, void* stream) {
     if (!h || !h->sharded || !recv_buf) return fail("fgnn_shard_unpack: bad argument");
+    if (!h->shard_configured) return fail("fgnn_shard_unpack: call fgnn_shard_configure first");
     CK(cudaSetDevice(h->cfg.device));
-    return enqueue_shard_unpack(h, recv_buf, world, rank, cap, depth, (cudaStream_t)stream);
+    return enqueue_shard_unpack(h, recv_buf, cap, (cudaStream_t)stream);
+}
+
+extern "C" int fgnn_shard_owned(fgnn_handle* h, int32_t* ids, int32_t* count, void* stream) {
+    if (!h || !h->sharded || !count) return fail("fgnn_shard_owned: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(h->cfg.device));
+    int n = 0;
+    CK(cudaMemcpyAsync(&n, h->d_counts + 0, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    *count = n;
+    if (ids && n > 0) {          // the list may contain -1 entries (handed-over slots): the caller filters them
+        CK(cudaMemcpyAsync(ids, h->d_own, (size_t)n * sizeof(int), cudaMemcpyDefault, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    return 0;
 }
 
 // CUDA-graph replay of the two halves of a sharded step around the host's all-gather:
@@ -855,32 +911,32 @@ static int run_cached_graph(fgnn_handle* h, ShardGraph& g, const void* a, const 
     return 0;
 }
 
-extern "C" int fgnn_shard_step_begin(fgnn_handle* h, const double* windows, int64_t window_stride, int32_t world,
-                                     int32_t rank, double depth, double* send_buf, int32_t cap, void* stream) {
+extern "C" int fgnn_shard_step_begin(fgnn_handle* h, const double* windows, int64_t window_stride, double* send_buf,
+                                     int32_t cap, void* stream) {
     if (!h || !h->sharded || !windows || !send_buf) return fail("fgnn_shard_step_begin: bad argument");
+    if (!h->shard_configured) return fail("fgnn_shard_step_begin: call fgnn_shard_configure first");
     cudaStream_t st = (cudaStream_t)stream;
     CK(cudaSetDevice(h->cfg.device));
     if (h->binned) return fail("fgnn_shard_step_begin: graph not rebuilt since the last step");
     ShardGraph& g = shard_graphs(h)[0];
-    int rc = run_cached_graph(h, g, windows, send_buf, window_stride, world, rank, cap, depth, st, [&](cudaStream_t cs) {
+    int rc = run_cached_graph(h, g, windows, send_buf, window_stride, cap, h->shard_epoch, 0, 0.0, st, [&](cudaStream_t cs) {
         if (enqueue_hops(h, cs)) return 1;
         if (enqueue_final(h, true, 0, cs)) return 1;
-        return enqueue_shard_pack(h, windows, window_stride, world, rank, depth, send_buf, cap, cs);
+        return enqueue_shard_pack(h, windows, window_stride, send_buf, cap, 1, cs);
     });
     if (rc) return 1;
     h->binned = true;
     return 0;
 }
 
-extern "C" int fgnn_shard_step_end(fgnn_handle* h, const double* recv_buf, int32_t world, int32_t rank, int32_t cap,
-                                   double depth, void* stream) {
+extern "C" int fgnn_shard_step_end(fgnn_handle* h, const double* recv_buf, int32_t cap, void* stream) {
     if (!h || !h->sharded || !recv_buf) return fail("fgnn_shard_step_end: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
     CK(cudaSetDevice(h->cfg.device));
     if (!h->binned) return fail("fgnn_shard_step_end: call fgnn_shard_step_begin first");
     ShardGraph& g = shard_graphs(h)[1];
-    int rc = run_cached_graph(h, g, recv_buf, nullptr, world, rank, cap, 0, depth, st, [&](cudaStream_t cs) {
-        if (enqueue_shard_unpack(h, recv_buf, world, rank, cap, depth, cs)) return 1;
+    int rc = run_cached_graph(h, g, recv_buf, nullptr, cap, h->shard_epoch, 0, 0, 0.0, st, [&](cudaStream_t cs) {
+        if (enqueue_shard_unpack(h, recv_buf, cap, cs)) return 1;
         return enqueue_build(h, 1, cs);
     });
     if (rc) return 1;

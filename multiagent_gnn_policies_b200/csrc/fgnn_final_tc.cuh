@@ -168,11 +168,13 @@ __global__ void __launch_bounds__(FINAL_THREADS) k_final_tc(Params p, const uint
 
     const int t = *p.t;
     const size_t M = p.M;
-    const int n_tiles = (p.n_own + FINAL_THREADS - 1) / FINAL_THREADS;
+    const int n_owned = owned_count(p);
+    const int n_tiles = (n_owned + FINAL_THREADS - 1) / FINAL_THREADS;
     double racc[4] = {0, 0, 0, 0};
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int a = p.a_lo + tile * FINAL_THREADS + tid;
-        const bool valid = a < p.a_lo + p.n_own;
+        const int oi = tile * FINAL_THREADS + tid;
+        const int a = oi < n_owned ? owned_agent(p, oi) : -1;     // -1: beyond the list or a handed-over slot
+        const bool valid = a >= 0;
         float in[K0];
 #pragma unroll
         for (int i = 0; i < K0; ++i) in[i] = 0.f;

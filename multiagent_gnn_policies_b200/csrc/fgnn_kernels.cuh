@@ -33,12 +33,16 @@ struct Params {
     int G;                    // cells along x of the wrapped cell grid
     int Gy;                   // cells along y
     int C;                    // total cells = B*G*Gy
-    // sharding (one rank of a multi-GPU flock; single-GPU: a_lo = 0, n_own = M, pool = null)
-    int a_lo;                 // first agent this rank owns (integrates)
-    int n_own;                // number of owned agents
-    int pool_cap;             // capacity of the pool list
-    const int* pool;          // [pool_cap] agents present on this rank: owned range, then ghosts; null = all M
-    const int* n_pool;        // device count of valid pool entries (null = M)
+    // sharding (one rank of a multi-GPU flock).  Single GPU: own == null, the rank owns agents [a_lo, a_lo + n_own) = all.
+    // Sharded: the OWNED set is a device list (it changes when agents are handed over between ranks), the
+    // agents present on the rank (pool) = owned list followed by the ghost list.
+    int a_lo;                 // single GPU: first owned agent (0)
+    int n_own;                // single GPU: number of owned agents (M)
+    int pool_cap;             // capacity of the owned / ghost lists
+    const int* own;           // [pool_cap] owned agents (null = contiguous range)
+    const int* n_own_d;       // device count of owned agents
+    const int* ghost;         // [pool_cap] agents received from other ranks this step
+    const int* n_ghost_d;     // device count of ghosts
     int mean_pooling;
     int half_accel;
     int write_z_last;         // final kernel also stores z_{K-1} (debug / fgnn_get_aggregated)
@@ -115,8 +119,19 @@ __device__ __forceinline__ int cell_index(const Params& p, int ep, long long ix,
 }
 
 // number of agents present on this rank and the i-th of them
-__device__ __forceinline__ int pool_size(const Params& p) { return p.pool ? *p.n_pool : p.M; }
-__device__ __forceinline__ int pool_agent(const Params& p, int i) { return p.pool ? p.pool[i] : i; }
+// Sharded: the owned list keeps its order; an agent that is handed over leaves a tombstone (-1) and new agents
+// are appended, so the kernels keep walking spatially coherent runs.  owned_count = high-water mark,
+// owned_agent / pool_agent may return -1 (skip).
+__device__ __forceinline__ int owned_count(const Params& p) { return p.own ? *p.n_own_d : p.n_own; }
+__device__ __forceinline__ int owned_agent(const Params& p, int i) { return p.own ? p.own[i] : p.a_lo + i; }
+// number of agents in the cell-sorted arrays (valid after k_scan): the last scan entry
+__device__ __forceinline__ int sorted_count(const Params& p) { return p.own ? p.cell_start[p.C] : p.M; }
+__device__ __forceinline__ int pool_size(const Params& p) { return p.own ? *p.n_own_d + *p.n_ghost_d : p.M; }
+__device__ __forceinline__ int pool_agent(const Params& p, int i) {
+    if (!p.own) return i;
+    const int no = *p.n_own_d;
+    return i < no ? p.own[i] : p.ghost[i - no];
+}
 
 // r2 exactly as numpy evaluates dx*dx + dy*dy (two roundings of the products, one of the sum; no FMA)
 __device__ __forceinline__ double r2_exact(double dx, double dy) {
@@ -139,10 +154,11 @@ __device__ __forceinline__ void store_row6(float* base, int idx, const float (&v
 // ------------------------------------------------------------------------------------------
 // K_A  bin: cell of every agent + per-cell population count
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_bin(Params p, int first) {
-    const int i = first + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= pool_size(p)) return;
-    const int a = pool_agent(p, i);
+__global__ void __launch_bounds__(256) k_bin(Params p) {      // owned agents (ghosts are binned by k_shard_unpack)
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= owned_count(p)) return;
+    const int a = owned_agent(p, i);
+    if (a < 0) return;
     double4 s = p.state[a];
     long long ix, iy;
     cell_coords(p, s.x, s.y, ix, iy);
@@ -311,6 +327,7 @@ __global__ void __launch_bounds__(256) k_scatter(Params p) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= pool_size(p)) return;
     const int a = pool_agent(p, i);
+    if (a < 0) return;
     int c = p.cell_of[a];
     int slot = p.cell_start[c] + atomicAdd(&p.cell_count[c], 1);
     p.tmp_id[slot] = a;
@@ -321,7 +338,7 @@ __global__ void __launch_bounds__(256) k_scatter(Params p) {
 __global__ void __launch_bounds__(256) k_canon(Params p) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     for (int i = s; i <= p.C; i += gridDim.x * blockDim.x) p.cell_count[i] = 0;   // fill counters -> 0 for the next bin
-    if (s >= pool_size(p)) return;
+    if (s >= sorted_count(p)) return;
     int a = p.tmp_id[s];
     int c = p.cell_of[a];
     int q0 = p.cell_start[c], q1 = p.cell_start[c + 1];
@@ -356,7 +373,7 @@ __global__ void __launch_bounds__(ADJ_THREADS) k_adjacency(Params p, int stage_c
 
     const int t = *p.t;
     const int g = slot_of(t, p.K);
-    const bool valid = s < pool_size(p);
+    const bool valid = s < sorted_count(p);
     int a = 0;
     double4 me = make_double4(0, 0, 0, 0);
     int q0[9], q1[9];
@@ -552,6 +569,7 @@ __global__ void __launch_bounds__(256) k_hop(Params p, int j) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= pool_size(p)) return;
     const int a = pool_agent(p, i);
+    if (a < 0) return;
     const int t = *p.t;
     const int g = slot_of(t - j, p.K);
     const size_t M = p.M;
@@ -621,7 +639,7 @@ __device__ __forceinline__ void integrate_and_bin(const Params& p, int a, const 
             atomicAdd(dst + 0, v0); atomicAdd(dst + 1, v1); atomicAdd(dst + 2, v2); atomicAdd(dst + 3, v3);
         }
     }
-    if (a == p.a_lo) *p.reward_pending = 1;
+    if (threadIdx.x == 0 && blockIdx.x == 0) *p.reward_pending = 1;
 }
 
 // B == 1: sum the block's thread-local reward sums in a fixed order and store them as this block's partial.
@@ -646,18 +664,20 @@ __device__ __forceinline__ void reward_block_flush(const Params& p, const double
         for (int w = 0; w < THREADS / 32; ++w) t += s_part[threadIdx.x][w];
         p.racc_part[(size_t)blockIdx.x * 4 + threadIdx.x] = t;
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) *p.n_partials = gridDim.x;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { *p.n_partials = gridDim.x; *p.reward_pending = 1; }
 }
 
 #ifdef FGNN_MAIN_TU
 // first half of env.step(u) with an externally supplied action
 __global__ void __launch_bounds__(256) k_integrate(Params p, const float* __restrict__ u) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int a = p.a_lo + i;
     double racc[4] = {0, 0, 0, 0};
-    if (i < p.n_own) {
-        const float2 uu = reinterpret_cast<const float2*>(u)[a];
-        integrate_and_bin(p, a, p.state[a], uu.x, uu.y, racc);
+    if (i < owned_count(p)) {
+        const int a = owned_agent(p, i);
+        if (a >= 0) {
+            const float2 uu = reinterpret_cast<const float2*>(u)[i];      // u is in owned-list order
+            integrate_and_bin(p, a, p.state[a], uu.x, uu.y, racc);
+        }
     }
     reward_block_flush<256>(p, racc);
 }
@@ -706,7 +726,7 @@ __global__ void __launch_bounds__(256) k_vel_sum(Params p, double* __restrict__ 
 __global__ void __launch_bounds__(128) k_controller(Params p, int centralized, int window, double grad_cut /* comm_radius */,
                                                     double max_u, const double* __restrict__ vsum, float* __restrict__ out) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= pool_size(p)) return;
+    if (s >= sorted_count(p)) return;
     const int a = p.sorted_id[s];
     const double4 me = p.sorted_state[s];
     const int ep = a / p.N;
@@ -754,12 +774,40 @@ __global__ void __launch_bounds__(128) k_controller(Params p, int centralized, i
 
 
 // ------------------------------------------------------------------------------------------
-// Multi-GPU halo exchange (agents sharded by index; every rank keeps full-size arrays).
-// Record = 5 doubles: [agent id, px, py, vx, vy]; row 0 of a rank's buffer is the header
-// [count, own x-interval lo, hi, 0, 0].
-//   k_shard_pack  : owned agents whose x lies inside any other rank's window [lo_q - D, hi_q + D]
-//   k_shard_unpack: install the received states, append the agents to the pool list and bin them
+// Multi-GPU halo exchange with ownership hand-over (every rank keeps full-size arrays, indices are global).
+// Record = SREC doubles: [agent id, px, py, vx, vy, new owner or -1]; record 0 of a rank's buffer is the
+// header [count, own x_lo, own x_hi, 0, 0, 0].
+//
+// Territories are x-strips in a frame moving with the flock (bounds[q] <= x - shift < bounds[q+1] is rank q's
+// strip; shift advances by dshift per step).  An owner hands an agent over to the rank whose strip it has
+// entered by more than `margin`: the receiver already holds the agent as a ghost with a valid K-deep
+// history (it recomputes graph / features / hops for everything inside its window), so the hand-over moves
+// NO data -- the record just names the new owner.  Owned sets therefore stay spatially compact and the
+// halo stays a thin layer however long the rollout runs; an arbitrary initial index order re-partitions
+// itself after `handover_after` steps.
+//   k_shard_prepare : zero the per-step counters, advance the frame shift
+//   k_shard_pack    : hand-over decisions (tombstone in the owned list), records for the other ranks' windows
+//   k_shard_unpack  : install received states; new owner -> appended to the owned list, otherwise ghost list; bin
+// A rank's window = its strip +- depth, united with the x-interval of what it still owns +- depth.
 // ------------------------------------------------------------------------------------------
+constexpr int SREC = 6;
+
+struct ShardCtl {
+    const double* bounds;     // [world + 1] strip boundaries at shift = 0 (bounds[0] = -inf, bounds[world] = +inf)
+    double* shift;            // device scalar: frame displacement so far
+    double dshift;            // per step
+    double depth;             // halo depth for the windows
+    double margin;            // hand-over hysteresis
+    int world, rank;
+    int handover_after;       // first step index at which hand-overs are allowed (histories must be valid)
+    int* own;                 // [pool_cap] owned list: order kept, -1 = handed over, appended at n_own
+    int* n_own;               // high-water mark
+    int* ghost;               // [pool_cap]
+    int* n_ghost;
+    int* counter;             // records written
+    long long* xminmax;       // order-preserving keys of min / max px over the agents kept
+};
+
 // order-preserving map double <-> signed 64-bit integer (for atomicMin / atomicMax on coordinates)
 __device__ __forceinline__ long long dkey(double x) {
     long long b = __double_as_longlong(x);
@@ -769,30 +817,62 @@ __device__ __forceinline__ double dunkey(long long k) {
     return __longlong_as_double(k >= 0 ? k : k ^ 0x7fffffffffffffffll);
 }
 
-__global__ void __launch_bounds__(256) k_shard_pack(Params p, const double* __restrict__ windows, long long wstride,
-                                                    int world, int rank, double depth, double* __restrict__ buf, int cap,
-                                                    int* __restrict__ counter, long long* __restrict__ xminmax) {
+__global__ void k_shard_prepare(ShardCtl c, int advance) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        *c.n_ghost = 0; *c.counter = 0;
+        c.xminmax[0] = 0x7fffffffffffffffll;
+        c.xminmax[1] = -0x7fffffffffffffffll - 1;
+        if (advance) *c.shift += c.dshift;
+    }
+}
+
+__device__ __forceinline__ int strip_of(const ShardCtl& c, double xs) {
+    int s = 0;
+    for (int q = 1; q < c.world; ++q) s += (xs >= c.bounds[q]) ? 1 : 0;
+    return s;
+}
+
+__global__ void __launch_bounds__(256) k_shard_pack(Params p, ShardCtl c, const double* __restrict__ windows, long long wstride,
+                                                    double* __restrict__ buf, int cap) {
     __shared__ long long s_lo[8], s_hi[8];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     long long klo = 0x7fffffffffffffffll, khi = -0x7fffffffffffffffll - 1;
-    if (i < p.n_own) {
-        const int a = p.a_lo + i;
+    const int a = i < owned_count(p) ? owned_agent(p, i) : -1;
+    if (a >= 0) {
         const double4 s = p.state[a];
-        klo = khi = dkey(s.x);
-        bool wanted = false;
-        for (int q = 0; q < world; ++q) {
-            if (q == rank) continue;
-            wanted = wanted || (s.x >= windows[q * wstride] - depth && s.x <= windows[q * wstride + 1] + depth);
+        const double shift = *c.shift;
+        const double xs = s.x - shift;
+        // hand-over decision
+        int new_owner = -1;
+        if (*p.t >= c.handover_after) {
+            const int st = strip_of(c, xs);
+            if (st > c.rank && xs - c.bounds[c.rank + 1] > c.margin) new_owner = st;
+            if (st < c.rank && c.bounds[c.rank] - xs > c.margin) new_owner = st;
+        }
+        if (new_owner < 0) {
+            klo = khi = dkey(s.x);
+        } else {                                              // tombstone; stays here as a ghost for this step (already binned)
+            c.own[i] = -1;
+            const int slot = atomicAdd(c.n_ghost, 1);
+            if (slot < p.pool_cap) c.ghost[slot] = a; else *p.overflow = 1;
+        }
+        // who needs this agent's state?
+        bool wanted = new_owner >= 0;
+        for (int q = 0; q < c.world && !wanted; ++q) {
+            if (q == c.rank) continue;
+            const bool in_strip = xs >= c.bounds[q] - c.depth && xs <= c.bounds[q + 1] + c.depth;
+            const bool in_ival = s.x >= windows[q * wstride] - c.depth && s.x <= windows[q * wstride + 1] + c.depth;
+            wanted = in_strip || in_ival;
         }
         if (wanted) {
-            const int slot = atomicAdd(counter, 1);
-            if (slot < cap) {                      // overflow is reported through the header count
-                double* rec = buf + (size_t)(slot + 1) * 5;
-                rec[0] = (double)a; rec[1] = s.x; rec[2] = s.y; rec[3] = s.z; rec[4] = s.w;
+            const int slot = atomicAdd(c.counter, 1);
+            if (slot < cap) {                                  // overflow is reported through the header count
+                double* rec = buf + (size_t)(slot + 1) * SREC;
+                rec[0] = (double)a; rec[1] = s.x; rec[2] = s.y; rec[3] = s.z; rec[4] = s.w; rec[5] = (double)new_owner;
             }
         }
     }
-    // own x-interval: block reduce, one atomic pair per block
+    // x-interval of what this rank keeps: block reduce, one atomic pair per block
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         klo = min(klo, __shfl_xor_sync(0xffffffffu, klo, o));
@@ -802,55 +882,67 @@ __global__ void __launch_bounds__(256) k_shard_pack(Params p, const double* __re
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int w = 1; w < 8; ++w) { klo = min(klo, s_lo[w]); khi = max(khi, s_hi[w]); }
-        atomicMin(&xminmax[0], klo);
-        atomicMax(&xminmax[1], khi);
+        atomicMin(&c.xminmax[0], klo);
+        atomicMax(&c.xminmax[1], khi);
     }
 }
 
-// header record [count, x_lo, x_hi, 0, 0]; re-arms the interval accumulators
-__global__ void k_shard_header(double* __restrict__ buf, const int* __restrict__ counter, long long* __restrict__ xminmax) {
+// header record [count, x_lo, x_hi, 0, 0, 0]
+__global__ void k_shard_header(ShardCtl c, double* __restrict__ buf) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
-        buf[0] = (double)*counter; buf[1] = dunkey(xminmax[0]); buf[2] = dunkey(xminmax[1]); buf[3] = 0.0; buf[4] = 0.0;
-        xminmax[0] = 0x7fffffffffffffffll;
-        xminmax[1] = -0x7fffffffffffffffll - 1;
+        buf[0] = (double)*c.counter; buf[1] = dunkey(c.xminmax[0]); buf[2] = dunkey(c.xminmax[1]);
+        buf[3] = 0.0; buf[4] = 0.0; buf[5] = 0.0;
     }
 }
 
-__global__ void __launch_bounds__(256) k_shard_unpack(Params p, const double* __restrict__ recv /* [world][cap+1][5] */,
-                                                      int world, int rank, int cap, double depth,
-                                                      int* __restrict__ pool, int* __restrict__ n_pool,
-                                                      int* __restrict__ overflow) {
-    // this rank's window: its own x-interval (header of its own buffer) +- depth; depth < 0 accepts everything
-    const double* own = recv + (size_t)rank * (cap + 1) * 5;
-    const double win_lo = depth < 0 ? -1e300 : own[1] - depth;
-    const double win_hi = depth < 0 ? 1e300 : own[2] + depth;
+__global__ void __launch_bounds__(256) k_shard_unpack(Params p, ShardCtl c, const double* __restrict__ recv /* [world][cap+1][SREC] */,
+                                                      int cap) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int q = idx / cap, r = idx % cap;
-    if (q >= world || q == rank) return;
-    const double* base = recv + (size_t)q * (cap + 1) * 5;
+    if (q >= c.world || q == c.rank) return;
+    const double* base = recv + (size_t)q * (cap + 1) * SREC;
     const int count = (int)base[0];
-    if (r == 0 && count > cap) *overflow = 1;
+    if (r == 0 && count > cap) *p.overflow = 1;
     if (r >= count || r >= cap) return;
-    const double* rec = base + (size_t)(r + 1) * 5;
-    if (rec[1] < win_lo || rec[1] > win_hi) return;          // not near this rank
+    const double* rec = base + (size_t)(r + 1) * SREC;
+    const int new_owner = (int)rec[5];
+    // this rank's window: its strip and the x-interval of what it owns (own header), +- depth
+    const double* own_hdr = recv + (size_t)c.rank * (cap + 1) * SREC;
+    const double shift = *c.shift;
+    const double xs = rec[1] - shift;
+    const bool in_strip = xs >= c.bounds[c.rank] - c.depth && xs <= c.bounds[c.rank + 1] + c.depth;
+    const bool in_ival = rec[1] >= own_hdr[1] - c.depth && rec[1] <= own_hdr[2] + c.depth;
+    if (new_owner != c.rank && !in_strip && !in_ival) return;  // not near this rank
     const int a = (int)rec[0];
     p.state[a] = make_double4(rec[1], rec[2], rec[3], rec[4]);
-    const int slot = atomicAdd(n_pool, 1);
-    if (slot >= p.pool_cap) { *overflow = 1; return; }
-    pool[slot] = a;
+    if (new_owner == c.rank) {                                 // append to the owned list
+        const int slot = atomicAdd(c.n_own, 1);
+        if (slot < p.pool_cap) c.own[slot] = a; else { atomicSub(c.n_own, 1); *p.overflow = 1; }
+    } else {
+        const int slot = atomicAdd(c.n_ghost, 1);
+        if (slot < p.pool_cap) c.ghost[slot] = a; else *p.overflow = 1;
+    }
     long long ix, iy;
     cell_coords(p, rec[1], rec[2], ix, iy);
-    const int c = cell_index(p, a / p.N, ix, iy);
-    p.cell_of[a] = c;
-    atomicAdd(&p.cell_count[c], 1);
+    const int cc = cell_index(p, a / p.N, ix, iy);
+    p.cell_of[a] = cc;
+    atomicAdd(&p.cell_count[cc], 1);
 }
 
-// pool[0..n_own) = owned range, n_pool = n_own  (start of every exchange)
-__global__ void __launch_bounds__(256) k_pool_init(Params p, int* __restrict__ pool, int* __restrict__ n_pool,
-                                                   int* __restrict__ counter) {
+// owned list = contiguous range [lo, lo + count)  (reset)
+__global__ void __launch_bounds__(256) k_own_init(int* __restrict__ own, int* __restrict__ n_own, int* __restrict__ n_ghost,
+                                                  int lo, int count) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < p.n_own) pool[i] = p.a_lo + i;
-    if (i == 0) { *n_pool = p.n_own; *counter = 0; }
+    if (i < count) own[i] = lo + i;
+    if (i == 0) { *n_own = count; *n_ghost = 0; }
+}
+
+// owned-list order <-> global arrays (policy / integrate on a sharded handle)
+__global__ void __launch_bounds__(256) k_gather_owned2(Params p, const float* __restrict__ src, float* __restrict__ dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= owned_count(p)) return;
+    const int a = owned_agent(p, i);
+    reinterpret_cast<float2*>(dst)[i] = a >= 0 ? reinterpret_cast<const float2*>(src)[a] : make_float2(0.f, 0.f);
 }
 
 #endif  // FGNN_MAIN_TU

@@ -17,7 +17,8 @@ ABI_SYMBOLS = [
     "fgnn_set_state", "fgnn_build_graph", "fgnn_integrate", "fgnn_env_step", "fgnn_policy", "fgnn_controller", "fgnn_step",
     "fgnn_rollout", "fgnn_actor_forward_dense", "fgnn_get_state", "fgnn_get_features", "fgnn_get_degrees",
     "fgnn_get_aggregated", "fgnn_get_action", "fgnn_export_network_dense", "fgnn_get_csr", "fgnn_get_stats",
-    "fgnn_shard_local_step", "fgnn_shard_pack", "fgnn_shard_unpack", "fgnn_shard_step_begin", "fgnn_shard_step_end", "fgnn_profile_step", "fgnn_memcpy_sync", "fgnn_launch_count",
+    "fgnn_shard_configure", "fgnn_shard_local_step", "fgnn_shard_pack", "fgnn_shard_unpack", "fgnn_shard_step_begin",
+    "fgnn_shard_step_end", "fgnn_shard_owned", "fgnn_profile_step", "fgnn_memcpy_sync", "fgnn_launch_count",
 ]
 
 
@@ -82,11 +83,14 @@ def load_library(path=None):
     lib.fgnn_export_network_dense.argtypes = [vp, i32, vp, vp]
     lib.fgnn_get_csr.argtypes = [vp, i32, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp)]
     lib.fgnn_get_stats.argtypes = [vp, ctypes.POINTER(FgnnStats), vp]
+    dbl = ctypes.c_double
+    lib.fgnn_shard_configure.argtypes = [vp, vp, i32, i32, dbl, dbl, dbl, i32]
     lib.fgnn_shard_local_step.argtypes = [vp, vp]
-    lib.fgnn_shard_pack.argtypes = [vp, vp, i64, i32, i32, ctypes.c_double, vp, i32, vp]
-    lib.fgnn_shard_unpack.argtypes = [vp, vp, i32, i32, i32, ctypes.c_double, vp]
-    lib.fgnn_shard_step_begin.argtypes = [vp, vp, i64, i32, i32, ctypes.c_double, vp, i32, vp]
-    lib.fgnn_shard_step_end.argtypes = [vp, vp, i32, i32, i32, ctypes.c_double, vp]
+    lib.fgnn_shard_pack.argtypes = [vp, vp, i64, vp, i32, i32, vp]
+    lib.fgnn_shard_unpack.argtypes = [vp, vp, i32, vp]
+    lib.fgnn_shard_step_begin.argtypes = [vp, vp, i64, vp, i32, vp]
+    lib.fgnn_shard_step_end.argtypes = [vp, vp, i32, vp]
+    lib.fgnn_shard_owned.argtypes = [vp, vp, ctypes.POINTER(i32), vp]
     lib.fgnn_profile_step.argtypes = [vp, i32, vp, vp, ctypes.POINTER(i32), vp]
     lib.fgnn_memcpy_sync.argtypes = [vp, vp, ctypes.c_uint64, vp]
     lib.fgnn_launch_count.argtypes = [vp]
@@ -144,6 +148,8 @@ class FlockEngine:
                          int(shard_count), int(ghost_capacity), 0,
                          self.comm_radius, self.dt, self.action_scalar)
         self.shard_lo, self.shard_count, self.ghost_capacity = int(shard_lo), int(shard_count), int(ghost_capacity)
+        # rows of the action arrays policy()/integrate() exchange: all agents, or (sharded) the list capacity
+        self.rows_io = (self.shard_count + self.ghost_capacity) if self.shard_count else self.M
         self._h = ctypes.c_void_p()
         self._check(self.lib.fgnn_create(ctypes.byref(cfg), ctypes.byref(self._h)))
         self.step_index = -1          # host mirror of the engine's step counter t (-1: never reset)
@@ -216,10 +222,10 @@ class FlockEngine:
 
     def _as_action(self, u):
         if hasattr(u, "data_ptr"):
-            assert u.dtype == self._torch.float32 and u.numel() == (self.shard_count or self.M) * 2
+            assert u.dtype == self._torch.float32 and u.numel() == self.rows_io * 2
             return u.contiguous()
         u = np.ascontiguousarray(u, dtype=np.float32)
-        assert u.size == (self.shard_count or self.M) * 2
+        assert u.size == self.rows_io * 2
         return u
 
     def integrate(self, u, want_reward=False):
@@ -244,7 +250,7 @@ class FlockEngine:
         """select_action: (B*N, 2) fp32.  ``out`` may be a torch CUDA tensor or a (pinned) numpy array;
         default is a fresh CUDA tensor."""
         if out is None:
-            out = self._torch.empty((self.shard_count or self.M, 2), dtype=self._torch.float32, device=self.device)
+            out = self._torch.empty((self.rows_io, 2), dtype=self._torch.float32, device=self.device)
         self._check(self.lib.fgnn_policy(self._h, _ptr(out), self.stream))
         if isinstance(out, np.ndarray):
             self.sync()
@@ -352,23 +358,37 @@ class FlockEngine:
                 "n_cells": s.n_cells, "edge_capacity": s.edge_capacity}
 
     # -- multi-GPU pieces (orchestrated by parallel.ShardedFlock) ---------------------------
+    def shard_configure(self, bounds, world, rank, depth, margin, dshift, handover_after):
+        bounds = np.ascontiguousarray(bounds, dtype=np.float64)
+        assert bounds.size == world + 1
+        self._check(self.lib.fgnn_shard_configure(self._h, _ptr(bounds), world, rank, float(depth), float(margin),
+                                                  float(dshift), int(handover_after)))
+
     def shard_local_step(self):
         self._check(self.lib.fgnn_shard_local_step(self._h, self.stream))
 
-    def shard_pack(self, windows, window_stride, world, rank, depth, send_buf, cap):
-        self._check(self.lib.fgnn_shard_pack(self._h, _ptr(windows), int(window_stride), world, rank, float(depth),
-                                             _ptr(send_buf), cap, self.stream))
+    def shard_pack(self, windows, window_stride, send_buf, cap, advance):
+        self._check(self.lib.fgnn_shard_pack(self._h, _ptr(windows), int(window_stride), _ptr(send_buf), cap,
+                                             int(bool(advance)), self.stream))
 
-    def shard_unpack(self, recv_buf, world, rank, cap, depth):
-        self._check(self.lib.fgnn_shard_unpack(self._h, _ptr(recv_buf), world, rank, cap, float(depth), self.stream))
+    def shard_unpack(self, recv_buf, cap):
+        self._check(self.lib.fgnn_shard_unpack(self._h, _ptr(recv_buf), cap, self.stream))
 
-    def shard_step_begin(self, windows, window_stride, world, rank, depth, send_buf, cap):
-        self._check(self.lib.fgnn_shard_step_begin(self._h, _ptr(windows), int(window_stride), world, rank, float(depth),
-                                                   _ptr(send_buf), cap, self.stream))
+    def shard_step_begin(self, windows, window_stride, send_buf, cap):
+        self._check(self.lib.fgnn_shard_step_begin(self._h, _ptr(windows), int(window_stride), _ptr(send_buf), cap,
+                                                   self.stream))
 
-    def shard_step_end(self, recv_buf, world, rank, cap, depth):
-        self._check(self.lib.fgnn_shard_step_end(self._h, _ptr(recv_buf), world, rank, cap, float(depth), self.stream))
+    def shard_step_end(self, recv_buf, cap):
+        self._check(self.lib.fgnn_shard_step_end(self._h, _ptr(recv_buf), cap, self.stream))
         self.step_index += 1
+
+    def shard_owned(self):
+        """Currently owned agents (global ids, int32, list order) -- synchronises."""
+        ids = np.empty(self.shard_count + self.ghost_capacity, dtype=np.int32)
+        n = ctypes.c_int32(0)
+        self._check(self.lib.fgnn_shard_owned(self._h, _ptr(ids), ctypes.byref(n), self.stream))
+        ids = ids[:n.value]
+        return ids[ids >= 0].copy()          # -1 = slot of an agent that was handed over
 
     def profile_step(self):
         """One closed-loop step with per-kernel CUDA-event timing: [(kernel name, ms), ...]."""

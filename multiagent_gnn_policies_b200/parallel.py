@@ -1,24 +1,27 @@
-"""Multi-GPU rollout: agents sharded by index, one process per GPU, one halo all-gather per step.
+"""Multi-GPU rollout: one process per GPU, one halo all-gather per step, ownership hand-over.
 
-Rank r owns the contiguous index range [lo_r, lo_r + count_r) and is the only one that integrates those
-agents.  Agents interact within comm_radius per hop and a step chains K dependent neighbour gathers, so a
-rank can compute its owned agents' actions from the states of every agent within ``K * R`` of its own
-region: it recomputes graph, features and hops REDUNDANTLY for those ghosts instead of exchanging
-intermediate results.  Per step there is exactly one collective, an all-gather of fixed-capacity
-buffers holding the (id, px, py, vx, vy) records of each rank's owned agents that lie inside another
-rank's x-window; the header record carries the sender's own x-interval, which is next step's window.
-When the index order is spatially sorted (cell-major) the owned range is a strip and the exchange is a
-thin boundary layer; for an arbitrary order the windows overlap completely and every agent is sent
-(correct, but the slow path -- SURVEY.md section 8e).
+Every rank keeps full-size arrays (global agent indices).  Rank r starts owning a contiguous index range and
+is the only rank that integrates what it owns.  A step chains K dependent neighbour gathers, so a rank can
+compute its owned agents' actions from the states of every agent within ``K * R`` of them: it recomputes
+graph, features and hops REDUNDANTLY for those ghosts instead of exchanging intermediate results.  Per step
+there is exactly one collective, an all-gather of fixed-capacity buffers with the records
+``(id, px, py, vx, vy, new_owner)`` of each rank's owned agents that lie inside another rank's window; the
+header record carries the sender's own x-interval (part of next step's windows).
 
-``ShardedFlock`` holds the protocol; the per-rank compute sits behind a small backend interface so that
-the same orchestration runs on the CUDA engine (``CudaShardBackend``) and, in the CPU tests, on a
-numpy backend over gloo.
+Territories are x-strips in a frame moving with the flock.  When an owned agent has entered another rank's
+strip by more than ``margin`` its owner hands it over: the receiver already holds it as a ghost with a valid
+K-deep history, so the hand-over moves no data -- the record just names the new owner.  Owned sets stay
+spatially compact however long the rollout runs, and an arbitrary initial index order re-partitions itself.
+
+``ShardedFlock`` holds the protocol; the per-rank compute sits behind a small backend interface so the same
+orchestration runs on the CUDA engine (``CudaShardBackend``) and, in the CPU tests, on a numpy backend
+over gloo.
 """
 import numpy as np
 
-RECORD = 5          # doubles per record: id, px, py, vx, vy (record 0 = header: count, x_lo, x_hi, 0, 0)
+RECORD = 6          # doubles per record: id, px, py, vx, vy, new_owner (record 0 = header: count, x_lo, x_hi, 0, 0, 0)
 FAR = 1.0e30        # x coordinate given to agents a rank knows nothing about at reset
+INF = 1.0e300
 
 
 def shard_ranges(n_total, world):
@@ -33,13 +36,29 @@ def shard_ranges(n_total, world):
 
 
 def halo_depth(k, comm_radius, margin=0.5):
-    """States are needed within K*R of the owned region (K chained neighbour gathers); ``margin`` (in
-    units of R) covers motion while an agent's K-deep history becomes valid and the one-step-old windows."""
+    """States are needed within K*R of the owned agents (K chained neighbour gathers); ``margin`` (in units
+    of R) covers motion while an agent's K-deep history becomes valid and the one-step-old windows."""
     return (max(k, 1) + margin) * comm_radius
 
 
+def strip_bounds(x_global, ranges):
+    """Territory boundaries from a fully known initial state: midpoints between consecutive ranks' x-extents
+    (only meaningful when the index order is spatially sorted along x).  (world + 1,) with +-INF at the ends."""
+    world = len(ranges)
+    b = np.empty(world + 1)
+    b[0], b[world] = -INF, INF
+    for q in range(1, world):
+        lo_prev, c_prev = ranges[q - 1]
+        lo, c = ranges[q]
+        b[q] = 0.5 * (x_global[lo_prev:lo_prev + c_prev, 0].max() + x_global[lo:lo + c, 0].min())
+    if np.any(np.diff(b[1:world]) <= 0):          # not sorted along x: equal-width strips over the extent instead
+        xs = x_global[:, 0]
+        b[1:world] = np.linspace(xs.min(), xs.max(), world + 1)[1:world]
+    return b
+
+
 class CudaShardBackend:
-    """Per-rank compute on libfgnn.so (one FlockEngine holding full-size arrays, owning [lo, lo+count))."""
+    """Per-rank compute on libfgnn.so (one FlockEngine holding full-size arrays, initially owning [lo, lo+count))."""
 
     def __init__(self, n_total, lo, count, ghost_capacity, device=0, **engine_kw):
         import torch
@@ -53,6 +72,9 @@ class CudaShardBackend:
     def new_buffer(self, rows):
         return self.torch.zeros((rows, RECORD), dtype=self.torch.float64, device=self.device)
 
+    def configure(self, bounds, world, rank, depth, margin, dshift, handover_after):
+        self.engine.shard_configure(bounds, world, rank, depth, margin, dshift, handover_after)
+
     def reset(self, x_global):
         self.engine.reset(x_global)
 
@@ -60,57 +82,71 @@ class CudaShardBackend:
         self.engine.shard_local_step()
 
     def policy(self, out):
-        """select_action for the owned agents into ``out`` (owned slice; host or device)."""
+        """select_action for the owned agents into ``out`` (owned-list order, list-capacity rows; host or device)."""
         return self.engine.policy(out=out)
 
     def integrate(self, u):
-        """first half of env.step for the owned agents from ``u`` (owned slice; host or device)."""
+        """first half of env.step for the owned agents from ``u`` (same layout as ``policy``)."""
         self.engine.integrate(u)
 
-    def pack(self, windows, window_stride, world, rank, depth, send, cap):
-        self.engine.shard_pack(windows, window_stride, world, rank, depth, send, cap)
+    def pack(self, windows, window_stride, send, cap, advance):
+        self.engine.shard_pack(windows, window_stride, send, cap, advance)
 
-    def unpack(self, recv, world, rank, cap, depth):
-        self.engine.shard_unpack(recv, world, rank, cap, depth)
+    def unpack(self, recv, cap):
+        self.engine.shard_unpack(recv, cap)
 
     def build(self, advance):
         self.engine.build_graph(advance=advance)
 
     # CUDA-graph replayed halves of a step (same kernels as local_step+pack / unpack+build)
-    def step_begin(self, windows, window_stride, world, rank, depth, send, cap):
-        self.engine.shard_step_begin(windows, window_stride, world, rank, depth, send, cap)
+    def step_begin(self, windows, window_stride, send, cap):
+        self.engine.shard_step_begin(windows, window_stride, send, cap)
 
-    def step_end(self, recv, world, rank, cap, depth):
-        self.engine.shard_step_end(recv, world, rank, cap, depth)
+    def step_end(self, recv, cap):
+        self.engine.shard_step_end(recv, cap)
+
+    def owned(self):
+        return self.engine.shard_owned()
 
     def owned_state(self):
-        return self.engine.get_state()[self.lo:self.lo + self.count]
+        ids = np.sort(self.owned())
+        return ids, self.engine.get_state()[ids]
 
     def owned_action(self):
-        return self.engine.get_action()[self.lo:self.lo + self.count]
+        ids = np.sort(self.owned())
+        return ids, self.engine.get_action()[ids]
 
     def overflow(self):
         return self.engine.stats()["overflow"]
 
 
 class ShardedFlock:
-    """The halo protocol of one rank.  ``all_gather(send) -> recv`` concatenates every rank's buffer
-    (torch.distributed over NCCL in production, gloo or an in-process list in tests)."""
+    """The halo / hand-over protocol of one rank.  ``all_gather(send) -> recv`` concatenates every rank's
+    buffer (torch.distributed over NCCL in production, gloo or an in-process stack in tests)."""
 
-    def __init__(self, backend, rank, world, k, comm_radius, capacity, all_gather, margin=0.5, send_slack=0.25):
-        self.backend, self.rank, self.world = backend, rank, world
+    def __init__(self, backend, rank, world, k, comm_radius, capacity, all_gather, dt=0.01, margin=0.5,
+                 send_slack=0.25, handover_margin=1.0):
+        self.backend, self.rank, self.world, self.k, self.dt = backend, rank, world, k, dt
         self.cap = int(capacity)
-        self.depth = halo_depth(k, comm_radius, margin)
-        self.send_depth = self.depth + send_slack * comm_radius      # windows are one step old when used
+        self.R = comm_radius
+        self.depth = halo_depth(k, comm_radius, margin) + send_slack * comm_radius   # windows are one step old
+        self.handover_margin = handover_margin * comm_radius
         self.all_gather = all_gather
         self.send = backend.new_buffer(self.cap + 1)
         self.recv = None
         self.windows0 = backend.new_buffer(world)                    # [world][RECORD], cols 1,2 = lo, hi
 
-    def reset(self, x_global, ranges):
+    def reset(self, x_global, ranges, bounds=None, frame_velocity=0.0):
         """``x_global`` (n_total,4) f64: the rank must know the true state of every agent within the halo
-        depth of its own strip; agents it knows nothing about must sit at x = FAR."""
+        depth of its own agents; agents it knows nothing about must sit at x = FAR.  ``bounds``: territory
+        boundaries (world+1,), identical on every rank; default: from ``x_global`` (needs full knowledge).
+        ``frame_velocity``: x-velocity of the frame the territories move with (the flock's mean vx)."""
         x_global = np.ascontiguousarray(x_global, dtype=np.float64)
+        if bounds is None:
+            bounds = strip_bounds(x_global, ranges)
+        self.bounds = np.asarray(bounds, dtype=np.float64)
+        self.backend.configure(self.bounds, self.world, self.rank, self.depth, self.handover_margin,
+                               frame_velocity * self.dt, self.k + 1)
         self.backend.reset(x_global)
         win = np.zeros((self.world, RECORD))
         for q, (lo, cnt) in enumerate(ranges):
@@ -119,7 +155,7 @@ class ShardedFlock:
             # a rank that cannot see another rank's agents uses an empty window for it
             win[q, 1], win[q, 2] = (xs.min(), xs.max()) if xs.size else (FAR, -FAR)
         self._upload(self.windows0, win)
-        self._exchange(self.windows0, RECORD)
+        self._exchange(self.windows0, RECORD, advance=False)
         self.backend.build(False)
 
     def _upload(self, dst, arr):
@@ -129,32 +165,31 @@ class ShardedFlock:
         else:
             dst[...] = arr
 
-    def _exchange(self, windows, stride):
+    def _exchange(self, windows, stride, advance):
         # windows[q*stride + 1 .. 2] = rank q's x-interval: pass a view that starts at column 1
         win_view = windows.reshape(-1)[1:]
-        self.backend.pack(win_view, stride, self.world, self.rank, self.send_depth, self.send, self.cap)
+        self.backend.pack(win_view, stride, self.send, self.cap, advance)
         self.recv = self.all_gather(self.send)
-        self.backend.unpack(self.recv, self.world, self.rank, self.cap, self.depth)
+        self.backend.unpack(self.recv, self.cap)
 
     def step(self):
         """One closed-loop step: local policy + integrator for owned agents, halo exchange, rebuild."""
+        stride = (self.cap + 1) * RECORD
         if hasattr(self.backend, "step_begin"):          # CUDA backend: two graph launches around the all-gather
-            win_view = self.recv.reshape(-1)[1:]
-            self.backend.step_begin(win_view, (self.cap + 1) * RECORD, self.world, self.rank, self.send_depth,
-                                    self.send, self.cap)
+            self.backend.step_begin(self.recv.reshape(-1)[1:], stride, self.send, self.cap)
             self.recv = self.all_gather(self.send)
-            self.backend.step_end(self.recv, self.world, self.rank, self.cap, self.depth)
+            self.backend.step_end(self.recv, self.cap)
             return
         self.backend.local_step()
-        self._exchange(self.recv, (self.cap + 1) * RECORD)
+        self._exchange(self.recv, stride, advance=True)
         self.backend.build(True)
 
     def step_host(self, action_host):
         """The same step through host buffers, as the reference loop does it (learner/gnn_dagger.py:196-201):
-        select_action -> host array -> env.step(host array).  ``action_host``: (count, 2) fp32, pinned."""
+        select_action -> host array -> env.step(host array).  ``action_host``: (list capacity, 2) fp32, pinned."""
         self.backend.policy(action_host)          # D2H (synchronises)
         self.backend.integrate(action_host)       # H2D
-        self._exchange(self.recv, (self.cap + 1) * RECORD)
+        self._exchange(self.recv, (self.cap + 1) * RECORD, advance=True)
         self.backend.build(True)
 
 

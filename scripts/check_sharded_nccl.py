@@ -22,7 +22,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    n_total, steps, K, R = 200_000, 10, 3, 1.0
+    n_total, steps, K, R = 200_000, 60, 3, 1.0
     g = np.load(os.path.join(ROOT, "tests", "golden", "ckpt_n100_k3.npz"))
     sd = {k[3:]: g[k] for k in g.files if k.startswith("sd.")}
     x0 = flock_env.synthetic_state(n_total, seed=5, density=1.6)
@@ -30,7 +30,7 @@ def main():
     ranges = parallel.shard_ranges(n_total, world)
     lo, cnt = ranges[rank]
     cap = 20000
-    be = parallel.CudaShardBackend(n_total, lo, cnt, ghost_capacity=2 * cap, device=local, k=K, hidden=32, n_layers=2,
+    be = parallel.CudaShardBackend(n_total, lo, cnt, ghost_capacity=4 * cap, device=local, k=K, hidden=32, n_layers=2,
                                    comm_radius=R, dt=0.01, edge_capacity=48)
     be.engine.load_state_dict(sd)
     flock = parallel.ShardedFlock(be, rank, world, K, R, cap, parallel.nccl_all_gather(world, cap, be.device))
@@ -38,10 +38,14 @@ def main():
     for _ in range(steps):
         flock.step()
     torch.cuda.synchronize()
-    own = torch.from_numpy(be.owned_state()).cuda()
-    sizes = [c for _, c in ranges]
-    gathered = [torch.zeros((c, 4), dtype=torch.float64, device="cuda") for c in sizes]
-    dist.all_gather(gathered, own) if len(set(sizes)) == 1 else None
+    ids, st = be.owned_state()
+    # assemble the global state on every rank: sum of each rank's owned rows (exactly one owner per agent)
+    x_all = torch.zeros((n_total, 4), dtype=torch.float64, device="cuda")
+    cnt_all = torch.zeros((n_total,), dtype=torch.float64, device="cuda")
+    x_all[torch.from_numpy(ids).cuda().long()] = torch.from_numpy(st).cuda()
+    cnt_all[torch.from_numpy(ids).cuda().long()] = 1.0
+    dist.all_reduce(x_all)
+    dist.all_reduce(cnt_all)
     ok = True
     if rank == 0:
         single = FlockEngine(n_agents=n_total, k=K, hidden=32, n_layers=2, comm_radius=R, dt=0.01, edge_capacity=48,
@@ -50,12 +54,10 @@ def main():
         single.reset(x0)
         single.rollout(steps)
         ref = single.get_state()
-        if len(set(sizes)) == 1:
-            got = torch.cat(gathered).cpu().numpy()
-            ok = np.array_equal(got, ref)
-        else:
-            ok = np.array_equal(be.owned_state(), ref[lo:lo + cnt])
-        print("sharded NCCL rollout == single engine:", ok, "| world", world, "| overflow", be.overflow())
+        one_owner = bool((cnt_all == 1).all().item())
+        ok = one_owner and np.array_equal(x_all.cpu().numpy(), ref)
+        print("sharded NCCL rollout == single engine:", ok, "| one owner per agent:", one_owner, "| world", world,
+              "| owned now", ids.size, "of initial", cnt, "| overflow", be.overflow())
     dist.barrier()
     dist.destroy_process_group()
     if not ok:

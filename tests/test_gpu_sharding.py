@@ -1,5 +1,5 @@
 """Sharded engine on one GPU: several engine handles act as ranks in one process (the all-gather is a
-torch.cat), and must reproduce a single unsharded engine bit for bit on the owned agents."""
+torch.stack) and must reproduce a single unsharded engine bit for bit, including across ownership hand-overs."""
 import numpy as np
 import pytest
 
@@ -9,91 +9,78 @@ from oracle import flock_env
 pytestmark = pytest.mark.gpu
 
 
-class InProcessWorld:
-    """Lock-step driver for `world` ShardedFlock objects living in one process."""
-
-    def __init__(self, flocks):
-        self.flocks = flocks
-        self.pending = None
-
-    def run_phase(self, fn_before, fn_after):
-        import torch
-        for f in self.flocks:
-            fn_before(f)
-        recv = torch.stack([f.send for f in self.flocks]).contiguous()
-        for f in self.flocks:
-            f.recv = recv
-            fn_after(f)
-
-
-def make_world(n_total, world, x0, sd, k=3, hidden=32, comm_radius=1.0, cap=None, **kw):
+def make_world(n_total, world, sd, k=3, hidden=32, comm_radius=1.0, cap=None, **kw):
     from multiagent_gnn_policies_b200 import parallel
     ranges = parallel.shard_ranges(n_total, world)
     cap = cap or n_total
     flocks = []
     for rank, (lo, cnt) in enumerate(ranges):
-        be = parallel.CudaShardBackend(n_total, lo, cnt, ghost_capacity=min(n_total, world * cap), k=k, hidden=hidden,
+        be = parallel.CudaShardBackend(n_total, lo, cnt, ghost_capacity=n_total, k=k, hidden=hidden,
                                        n_layers=2, comm_radius=comm_radius, dt=0.01, edge_capacity=64, **kw)
         be.engine.load_state_dict(sd)
         flocks.append(parallel.ShardedFlock(be, rank, world, k, comm_radius, cap, all_gather=None))
     return flocks, ranges
 
 
-def drive(flocks, ranges, x0, steps, know_all=True, graphs=False):
+def drive(flocks, ranges, x0, steps, know_all=True, graphs=False, frame_velocity=0.0):
+    """Lock-step driver: what ShardedFlock.reset/step do, with the collective replaced by a stack."""
     from multiagent_gnn_policies_b200 import parallel
     import torch
     world = len(flocks)
+    bounds = parallel.strip_bounds(x0, ranges)
+    stride = (flocks[0].cap + 1) * parallel.RECORD
+    shared = torch.zeros((world, flocks[0].cap + 1, parallel.RECORD), dtype=torch.float64, device="cuda")
 
-    def exchange(windows_of, stride):
+    def gather():
+        shared.copy_(torch.stack([f.send for f in flocks]))
         for f in flocks:
-            w = windows_of(f)
-            f.backend.pack(w.reshape(-1)[1:], stride, world, f.rank, f.send_depth, f.send, f.cap)
-        recv = torch.stack([f.send for f in flocks]).contiguous()
-        for f in flocks:
-            f.recv = recv
-            f.backend.unpack(recv, world, f.rank, f.cap, f.depth)
+            f.recv = shared
 
     for f in flocks:
         x_known = x0.copy()
         if not know_all:
             lo, cnt = ranges[f.rank]
             own_x = x0[lo:lo + cnt, 0]
-            far = (x0[:, 0] < own_x.min() - f.send_depth) | (x0[:, 0] > own_x.max() + f.send_depth)
+            far = (x0[:, 0] < own_x.min() - f.depth) | (x0[:, 0] > own_x.max() + f.depth)
             far[lo:lo + cnt] = False
             x_known[far, 0] = parallel.FAR
+        f.backend.configure(bounds, world, f.rank, f.depth, f.handover_margin, frame_velocity * f.dt, f.k + 1)
         f.backend.reset(x_known)
         win = np.zeros((world, parallel.RECORD))
         for q, (lo, cnt) in enumerate(ranges):
             win[q, 1], win[q, 2] = x0[lo:lo + cnt, 0].min(), x0[lo:lo + cnt, 0].max()
         f.windows0.copy_(torch.from_numpy(win))
-    exchange(lambda f: f.windows0, parallel.RECORD)
+        f.backend.pack(f.windows0.reshape(-1)[1:], parallel.RECORD, f.send, f.cap, False)
+    gather()
     for f in flocks:
+        f.backend.unpack(shared, f.cap)
         f.backend.build(False)
     out = []
-    stride = (flocks[0].cap + 1) * parallel.RECORD
-    shared = flocks[0].recv.clone()              # persistent gathered buffer: stable pointers for the graph cache
-    for f in flocks:
-        f.recv = shared
     for _ in range(steps):
         if graphs:                               # CUDA-graph replayed halves
             for f in flocks:
-                f.backend.step_begin(shared.reshape(-1)[1:], stride, world, f.rank, f.send_depth, f.send, f.cap)
-            gathered = torch.stack([f.send for f in flocks])
-            shared.copy_(gathered)
+                f.backend.step_begin(shared.reshape(-1)[1:], stride, f.send, f.cap)
+            gather()
             for f in flocks:
-                f.backend.step_end(shared, world, f.rank, f.cap, f.depth)
+                f.backend.step_end(shared, f.cap)
         else:
             for f in flocks:
                 f.backend.local_step()
-            exchange(lambda f: f.recv, stride)
+                f.backend.pack(shared.reshape(-1)[1:], stride, f.send, f.cap, True)
+            gather()
             for f in flocks:
+                f.backend.unpack(shared, f.cap)
                 f.backend.build(True)
-            shared.copy_(flocks[0].recv)
-            for f in flocks:
-                f.recv = shared
-        out.append((np.concatenate([f.backend.owned_state() for f in flocks]),
-                    np.concatenate([f.backend.owned_action() for f in flocks])))
-    return out
+        n_total = x0.shape[0]
+        owners = np.zeros(n_total, int)
+        x_all = np.zeros((n_total, 4))
+        for f in flocks:
+            ids, st = f.backend.owned_state()
+            owners[ids] += 1
+            x_all[ids] = st
+        assert np.all(owners == 1)               # exactly one owner per agent at all times
+        out.append(x_all)
+    return out, bounds
 
 
 @pytest.mark.parametrize("world,n_total,order,graphs", [(2, 3000, "sorted", False), (4, 5000, "sorted", True),
@@ -106,23 +93,28 @@ def test_sharded_equals_single_engine(world, n_total, order, graphs):
         x0 = x0[np.argsort(x0[:, 0], kind="stable")]
     else:
         x0 = x0[np.random.RandomState(1).permutation(n_total)]
-    steps = 8
+    steps = 60 if order == "sorted" else 10
     single = FlockEngine(n_agents=n_total, k=3, hidden=32, n_layers=2, comm_radius=1.0, dt=0.01, edge_capacity=64)
     single.load_state_dict(g["state_dict"])
     single.reset(x0)
-    flocks, ranges = make_world(n_total, world, x0, g["state_dict"])
-    got = drive(flocks, ranges, x0, steps, know_all=(order != "sorted"), graphs=graphs)
+    flocks, ranges = make_world(n_total, world, g["state_dict"])
+    got, bounds = drive(flocks, ranges, x0, steps, know_all=(order != "sorted"), graphs=graphs)
     for t in range(steps):
-        a = np.empty((n_total, 2), np.float32)
-        single.step(a, None)
-        # same kernels, same per-row neighbour order (cell lists are canonical) -> identical bits
-        np.testing.assert_array_equal(got[t][1], a)
-        np.testing.assert_array_equal(got[t][0], single.get_state())
+        single.step(None, None)
+        # same kernels, same per-row neighbour order (cell lists are canonical) -> identical bits,
+        # whoever owns an agent and however often it changed hands
+        np.testing.assert_array_equal(got[t], single.get_state())
+    moved = 0
+    for f in flocks:
+        lo, cnt = ranges[f.rank]
+        moved += int(not np.array_equal(np.sort(f.backend.owned()), np.arange(lo, lo + cnt)))
+    if order == "random":
+        assert moved > 0                          # ownership was handed over (re-partitioning)
+        x_end = single.get_state()
+        for f in flocks:                          # ownership re-partitioned itself into the x-strips
+            xs = x_end[f.backend.owned(), 0]
+            assert xs.min() >= bounds[f.rank] - 1.6 and xs.max() <= bounds[f.rank + 1] + 1.6
     for f in flocks:
         assert not f.backend.overflow()
         f.backend.engine.close()
-    if order == "sorted":
-        # thin boundary layer: a rank holds far fewer agents than the whole flock
-        pool = flocks[0].backend.engine
-        assert ranges[0][1] < n_total
     single.close()

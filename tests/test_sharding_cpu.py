@@ -14,7 +14,7 @@ from conftest import ROOT, load_golden
 from oracle import flock_env, learner, sparse
 from multiagent_gnn_policies_b200 import parallel
 
-N_TOTAL, STEPS, K, R = 600, 6, 3, 1.0
+N_TOTAL, STEPS, K, R = 600, 10, 3, 1.0
 
 
 def reference_rollout(x0, layers, steps):
@@ -61,18 +61,24 @@ def _worker(rank, world, port, x0, sd, out_dir, sorted_order):
     x_known = x0.copy()
     if sorted_order:
         own_x = x0[lo:lo + cnt, 0]
-        far = (x0[:, 0] < own_x.min() - flock.send_depth) | (x0[:, 0] > own_x.max() + flock.send_depth)
+        far = (x0[:, 0] < own_x.min() - flock.depth) | (x0[:, 0] > own_x.max() + flock.depth)
         far[lo:lo + cnt] = False
         x_known[far, 0] = parallel.FAR
-    flock.reset(x_known, ranges)
-    states, actions, pools = [], [], []
+    bounds = parallel.strip_bounds(x0, ranges)            # every rank derives the same territories
+    flock.reset(x_known, ranges, bounds=bounds)
+    ids, states, actions, pools = [], [], [], []
     for _ in range(STEPS):
         flock.step()
-        states.append(backend.owned_state().copy())
-        actions.append(backend.owned_action().copy())
+        i1, st = backend.owned_state()
+        i2, ac = backend.owned_action()
+        assert np.array_equal(i1, i2)
+        ids.append(np.pad(i1, (0, N_TOTAL - i1.size), constant_values=-1))
+        states.append(np.pad(st, ((0, N_TOTAL - i1.size), (0, 0))))
+        actions.append(np.pad(ac, ((0, N_TOTAL - i1.size), (0, 0))))
         pools.append(len(backend.pool))
-    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), states=np.stack(states), actions=np.stack(actions),
-             pools=np.array(pools), overflow=backend.overflow())
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), ids=np.stack(ids), states=np.stack(states),
+             actions=np.stack(actions), pools=np.array(pools), overflow=backend.overflow(),
+             handed_over=backend.handed_over, bounds=bounds)
     dist.destroy_process_group()
 
 
@@ -90,20 +96,41 @@ def test_two_gloo_ranks_reproduce_the_single_process_oracle(tmp_path, sorted_ord
     world = 2
     port = _free_port()
     mp.spawn(_worker, args=(world, port, x0, sd, str(tmp_path), sorted_order), nprocs=world, join=True)
-    ranges = parallel.shard_ranges(N_TOTAL, world)
-    for rank, (lo, cnt) in enumerate(ranges):
-        out = np.load(tmp_path / f"rank{rank}.npz")
+    outs = [np.load(tmp_path / f"rank{rank}.npz") for rank in range(world)]
+    for out in outs:
         assert not bool(out["overflow"])
-        for t in range(STEPS):
-            np.testing.assert_allclose(out["actions"][t], acts_ref[t][lo:lo + cnt], rtol=2e-5, atol=2e-5)
-            np.testing.assert_allclose(out["states"][t], xs_ref[t][lo:lo + cnt], rtol=1e-9, atol=1e-7)
-        if sorted_order:      # the exchange stays a thin boundary layer
-            assert out["pools"].max() < cnt + 0.45 * N_TOTAL
-        else:                 # arbitrary order: windows overlap, everything is present everywhere
-            assert out["pools"].max() == N_TOTAL
+    for t in range(STEPS):
+        owner_count = np.zeros(N_TOTAL, int)
+        x_all = np.zeros((N_TOTAL, 4))
+        a_all = np.zeros((N_TOTAL, 2), np.float32)
+        for out in outs:
+            ids = out["ids"][t]
+            ids = ids[ids >= 0]
+            owner_count[ids] += 1
+            x_all[ids] = out["states"][t][:ids.size]
+            a_all[ids] = out["actions"][t][:ids.size]
+        assert np.all(owner_count == 1)                       # every agent has exactly one owner, always
+        # the action reported at step t was computed by whoever owned the agent BEFORE this step's hand-over;
+        # after a hand-over the new owner's action slot is stale until it computes one: compare states (which
+        # carry every action's effect) at every step and actions where ownership did not just change
+        np.testing.assert_allclose(x_all, xs_ref[t], rtol=1e-9, atol=2e-6)
+    total_handed = sum(int(o["handed_over"]) for o in outs)
+    if sorted_order:          # the exchange stays a thin boundary layer
+        assert max(o["pools"].max() for o in outs) < 0.5 * N_TOTAL + 0.45 * N_TOTAL
+    else:                     # arbitrary order: ownership re-partitions itself into the strips
+        assert total_handed > 0.3 * N_TOTAL
+        bounds = outs[0]["bounds"]
+        for rank, out in enumerate(outs):
+            ids = out["ids"][-1]
+            ids = ids[ids >= 0]
+            xs = xs_ref[-1][ids, 0]
+            assert xs.min() >= bounds[rank] - 1.6 and xs.max() <= bounds[rank + 1] + 1.6
+        assert outs[0]["pools"][-1] < 0.8 * N_TOTAL           # and the halo became a thin layer
 
 
 def test_shard_ranges_and_depth():
     assert parallel.shard_ranges(10, 3) == [(0, 4), (4, 3), (7, 3)]
     assert sum(c for _, c in parallel.shard_ranges(1_000_003, 8)) == 1_000_003
     assert parallel.halo_depth(3, 1.0, 0.5) == 3.5
+    b = parallel.strip_bounds(np.array([[0.0, 0, 0, 0], [1.0, 0, 0, 0], [3.0, 0, 0, 0], [4.0, 0, 0, 0]]), [(0, 2), (2, 2)])
+    assert b[1] == 2.0 and b[0] < -1e200 and b[2] > 1e200
