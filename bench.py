@@ -364,7 +364,7 @@ def run_sharded(args, rank, world, local_rank, N, side, sd, weights_note, edge_c
                                                                                bias_seed=11)
     depth = parallel.halo_depth(args.k, args.radius)
     # both boundaries of a strip; ownership hand-over keeps the layer thin for any run length
-    halo_cap = int(2.0 * (depth + 2 * args.radius) * side * DENSITY * 2) + 1024
+    halo_cap = int(1.5 * (depth + 2 * args.radius) * side * DENSITY * 2) + 1024
     cell = args.radius
     gx = int(np.ceil((side + 2 * depth + 4) / cell)) + 2
     gy = int(np.ceil(side / cell)) + 4

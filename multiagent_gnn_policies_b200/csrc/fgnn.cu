@@ -63,7 +63,10 @@ struct fgnn_handle {
     ShardCtl ctl;
     int* d_own = nullptr;
     int* d_ghost = nullptr;
-    int* d_counts = nullptr;         // [n_own, n_new, n_ghost, record counter]
+    int* d_counts = nullptr;         // [n_own, n_free, n_ghost, record counter]
+    int* d_free = nullptr;
+    ShardFuse* d_fuse = nullptr;     // device copy of the fused-pack arguments
+    ShardFuse fuse_host;             // what d_fuse currently holds
     long long* d_xminmax = nullptr;
     double* d_shift = nullptr;
     double* d_bounds = nullptr;      // [world + 1], allocated by fgnn_shard_configure
@@ -213,8 +216,11 @@ extern "C" int fgnn_create(const fgnn_config* cfg, fgnn_handle** out) {
     if (h->sharded) {
         rc |= dalloc(h, &h->d_own, (size_t)p.pool_cap);
         rc |= dalloc(h, &h->d_ghost, (size_t)p.pool_cap);
+        rc |= dalloc(h, &h->d_free, (size_t)p.pool_cap);
+        rc |= dalloc(h, &h->d_fuse, 1);
+        memset(&h->fuse_host, 0, sizeof h->fuse_host);
         rc |= dalloc(h, &h->d_counts, 4);
-        rc |= dalloc(h, &h->d_xminmax, 2);
+        rc |= dalloc(h, &h->d_xminmax, (size_t)2 * (blocks_for(p.pool_cap, FINAL_THREADS) + 1));
         rc |= dalloc(h, &h->d_shift, 1);
         p.own = h->d_own;
         p.n_own_d = h->d_counts + 0;
@@ -222,6 +228,7 @@ extern "C" int fgnn_create(const fgnn_config* cfg, fgnn_handle** out) {
         p.n_ghost_d = h->d_counts + 2;
         memset(&h->ctl, 0, sizeof h->ctl);
         h->ctl.own = h->d_own; h->ctl.n_own = h->d_counts + 0;
+        h->ctl.free_slots = h->d_free; h->ctl.n_free = h->d_counts + 1;
         h->ctl.ghost = h->d_ghost; h->ctl.n_ghost = h->d_counts + 2;
         h->ctl.counter = h->d_counts + 3;
         h->ctl.xminmax = h->d_xminmax;
@@ -444,9 +451,10 @@ static int enqueue_hops(fgnn_handle* h, cudaStream_t st) {
     return 0;
 }
 
-static int enqueue_final(fgnn_handle* h, bool closed, int write_z, cudaStream_t st) {
+static int enqueue_final(fgnn_handle* h, bool closed, int write_z, cudaStream_t st, bool fuse_pack = false) {
     Params p = h->p;
     p.write_z_last = write_z;
+    p.fuse = fuse_pack ? h->d_fuse : nullptr;
     if (h->use_tc) {
         final_tc_kernel_t fk = final_tc_kernel(p.K, h->HP, closed);
         const int grid = closed ? h->tc_grid_closed : h->tc_grid_open;
@@ -508,7 +516,8 @@ extern "C" int fgnn_reset(fgnn_handle* h, const double* x, void* stream) {
     CK(cudaMemcpyAsync(p.state, x, M * sizeof(double4), cudaMemcpyDefault, st));
     if (h->sharded) {
         // owned agents are binned here; ghosts arrive through fgnn_shard_pack/unpack, then fgnn_build_graph(0)
-        k_own_init<<<blocks_for(p.n_own, 256), 256, 0, st>>>(h->d_own, h->d_counts + 0, h->d_counts + 2, p.a_lo, p.n_own);
+        k_own_init<<<blocks_for(p.n_own, 256), 256, 0, st>>>(h->d_own, h->d_counts + 0, h->d_counts + 2, h->d_counts + 1, p.a_lo,
+                                                             p.n_own);
         if (launch_check(h, "own_init")) return 1;
         CK(cudaMemsetAsync(h->d_shift, 0, sizeof(double), st));
         k_bin<<<blocks_for(p.n_own, 256), 256, 0, st>>>(p);
@@ -791,7 +800,7 @@ static int enqueue_shard_pack(fgnn_handle* h, const double* windows, int64_t win
     if (launch_check(h, "shard_prepare")) return 1;
     k_shard_pack<<<blocks_for(p.pool_cap, 256), 256, 0, st>>>(p, h->ctl, windows, (long long)window_stride, send_buf, cap);
     if (launch_check(h, "shard_pack")) return 1;
-    k_shard_header<<<1, 32, 0, st>>>(h->ctl, send_buf);
+    k_shard_header<<<1, 256, 0, st>>>(h->ctl, send_buf, blocks_for(p.pool_cap, 256));
     return launch_check(h, "shard_header");
 }
 
@@ -918,11 +927,24 @@ extern "C" int fgnn_shard_step_begin(fgnn_handle* h, const double* windows, int6
     cudaStream_t st = (cudaStream_t)stream;
     CK(cudaSetDevice(h->cfg.device));
     if (h->binned) return fail("fgnn_shard_step_begin: graph not rebuilt since the last step");
+    // the pack step runs inside the closed final kernel; its arguments live in device memory, so the cached
+    // graph stays valid when the buffers change
+    ShardFuse f;
+    memset(&f, 0, sizeof f);
+    f.ctl = h->ctl; f.windows = windows; f.wstride = window_stride; f.buf = send_buf; f.cap = cap;
+    if (memcmp(&f, &h->fuse_host, sizeof f) != 0) {
+        h->fuse_host = f;
+        CK(cudaMemcpyAsync(h->d_fuse, &h->fuse_host, sizeof f, cudaMemcpyHostToDevice, st));
+    }
+    const int final_grid = h->use_tc ? h->tc_grid_closed : h->final_grid_closed;
     ShardGraph& g = shard_graphs(h)[0];
-    int rc = run_cached_graph(h, g, windows, send_buf, window_stride, cap, h->shard_epoch, 0, 0.0, st, [&](cudaStream_t cs) {
+    int rc = run_cached_graph(h, g, nullptr, send_buf, h->shard_epoch, final_grid, 0, 0, 0.0, st, [&](cudaStream_t cs) {
         if (enqueue_hops(h, cs)) return 1;
-        if (enqueue_final(h, true, 0, cs)) return 1;
-        return enqueue_shard_pack(h, windows, window_stride, send_buf, cap, 1, cs);
+        k_shard_prepare<<<1, 32, 0, cs>>>(h->ctl, 1);
+        if (launch_check(h, "shard_prepare")) return 1;
+        if (enqueue_final(h, true, 0, cs, true)) return 1;
+        k_shard_header<<<1, 256, 0, cs>>>(h->ctl, send_buf, final_grid);
+        return launch_check(h, "shard_header");
     });
     if (rc) return 1;
     h->binned = true;

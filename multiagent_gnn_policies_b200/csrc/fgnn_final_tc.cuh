@@ -171,6 +171,7 @@ __global__ void __launch_bounds__(FINAL_THREADS) k_final_tc(Params p, const uint
     const int n_owned = owned_count(p);
     const int n_tiles = (n_owned + FINAL_THREADS - 1) / FINAL_THREADS;
     double racc[4] = {0, 0, 0, 0};
+    long long klo = 0x7fffffffffffffffll, khi = -0x7fffffffffffffffll - 1;     // kept x-interval (sharded, fused pack)
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int oi = tile * FINAL_THREADS + tid;
         const int a = oi < n_owned ? owned_agent(p, oi) : -1;     // -1: beyond the list or a handed-over slot
@@ -301,10 +302,15 @@ __global__ void __launch_bounds__(FINAL_THREADS) k_final_tc(Params p, const uint
         }
         if (valid) {
             reinterpret_cast<float2*>(p.action)[a] = make_float2(o0, o1);
-            if (CLOSED) integrate_and_bin(p, a, st_own, o0, o1, racc);
+            if (CLOSED) {
+                const double4 st_new = integrate_and_bin(p, a, st_own, o0, o1, racc);
+                if (p.fuse) shard_pack_agent(p, p.fuse->ctl, p.fuse->windows, p.fuse->wstride, p.fuse->buf, p.fuse->cap, oi, a,
+                                             st_new, klo, khi);
+            }
         }
     }
     if (CLOSED) reward_block_flush<FINAL_THREADS>(p, racc);
+    if (CLOSED && p.fuse) shard_interval_flush<FINAL_THREADS>(p.fuse->ctl, klo, khi);
     tc::fence_before_sync();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc<TM_COLS>(tmem_base);

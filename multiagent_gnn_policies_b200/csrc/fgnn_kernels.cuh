@@ -43,6 +43,7 @@ struct Params {
     const int* n_own_d;       // device count of owned agents
     const int* ghost;         // [pool_cap] agents received from other ranks this step
     const int* n_ghost_d;     // device count of ghosts
+    const struct ShardFuse* fuse;   // non-null: the closed final kernel also packs the halo records (fgnn_shard_step_begin)
     int mean_pooling;
     int half_accel;
     int write_z_last;         // final kernel also stores z_{K-1} (debug / fgnn_get_aggregated)
@@ -225,7 +226,7 @@ __global__ void __launch_bounds__(256) k_finalize_reward(Params p) { finalize_re
 //      decoupled look-back), zeroes cell_count; tile 0 also advances t and finalises the reward.
 // ------------------------------------------------------------------------------------------
 constexpr int SCAN_THREADS = 256;
-constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_ITEMS = 16;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 constexpr unsigned FLAG_AGG = 1u << 30, FLAG_INC = 2u << 30, VAL_MASK = (1u << 30) - 1;
 
@@ -237,13 +238,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(Params p, int advance) {
     if (tid == 0) s_tile = atomicAdd(p.tile_counter, 1);
     __syncthreads();
     const int tile = s_tile;
-    if (tile == 0) {
-        if (tid == 0) {
-            const int tn = *p.t + (advance ? 1 : 0);
-            *p.t = tn;
-            p.nnz_cursor[slot_of(tn, p.K)] = 0;      // edge cursor of the slot about to be rebuilt
-        }
-        finalize_reward(p);
+    if (tile == 0 && tid == 0) {
+        const int tn = *p.t + (advance ? 1 : 0);
+        *p.t = tn;
+        p.nnz_cursor[slot_of(tn, p.K)] = 0;          // edge cursor of the slot about to be rebuilt
     }
     const int n = p.C + 1;
     const int base = tile * SCAN_TILE + tid * SCAN_ITEMS;
@@ -318,6 +316,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(Params p, int advance) {
         if (idx < n) p.cell_start[idx] = run;
         run += v[i];
     }
+    // off the critical path: every other tile's look-back waits for tile 0's prefix, published above
+    if (tile == 0) finalize_reward(p);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -596,9 +596,113 @@ __global__ void __launch_bounds__(256) k_hop(Params p, int j) {
     }
 }
 
+// ---- multi-GPU halo / hand-over control block (see the k_shard_* kernels at the end of this file) ----
+constexpr int SREC = 6;
+
+struct ShardCtl {
+    const double* bounds;     // [world + 1] strip boundaries at shift = 0 (bounds[0] = -inf, bounds[world] = +inf)
+    double* shift;            // device scalar: frame displacement so far
+    double dshift;            // per step
+    double depth;             // halo depth for the windows
+    double margin;            // hand-over hysteresis
+    int world, rank;
+    int handover_after;       // first step index at which hand-overs are allowed (histories must be valid)
+    int* own;                 // [pool_cap] owned list: order kept, -1 = handed over, appended at n_own
+    int* n_own;               // high-water mark
+    int* free_slots;          // [pool_cap] stack of tombstoned positions, reused by the next agents received
+    int* n_free;
+    int* ghost;               // [pool_cap]
+    int* n_ghost;
+    int* counter;             // records written
+    long long* xminmax;       // [pack blocks][2] order-preserving keys of min / max px over the agents kept, per block
+};
+
+// order-preserving map double <-> signed 64-bit integer (for atomicMin / atomicMax on coordinates)
+__device__ __forceinline__ long long dkey(double x) {
+    long long b = __double_as_longlong(x);
+    return b >= 0 ? b : b ^ 0x7fffffffffffffffll;
+}
+__device__ __forceinline__ double dunkey(long long k) {
+    return __longlong_as_double(k >= 0 ? k : k ^ 0x7fffffffffffffffll);
+}
+
+__device__ __forceinline__ int strip_of(const ShardCtl& c, double xs) {
+    int s = 0;
+    for (int q = 1; q < c.world; ++q) s += (xs >= c.bounds[q]) ? 1 : 0;
+    return s;
+}
+
+
+// Hand-over decision and halo record of ONE owned agent whose (new) state is `st` (used by k_shard_pack and,
+// fused, by the epilogue of the closed final kernel).  i = position in the owned list.
+__device__ __forceinline__ void shard_pack_agent(const Params& p, const ShardCtl& c, const double* __restrict__ windows,
+                                                 long long wstride, double* __restrict__ buf, int cap, int i, int a,
+                                                 const double4 st, long long& klo, long long& khi) {
+    const double shift = *c.shift;
+    const double xs = st.x - shift;
+    int new_owner = -1;
+    if (*p.t >= c.handover_after) {
+        const int sp = strip_of(c, xs);
+        if (sp > c.rank && xs - c.bounds[c.rank + 1] > c.margin) new_owner = sp;
+        if (sp < c.rank && c.bounds[c.rank] - xs > c.margin) new_owner = sp;
+    }
+    if (new_owner < 0) {
+        const long long k = dkey(st.x);
+        klo = min(klo, k);
+        khi = max(khi, k);
+    } else {                                              // tombstone; stays here as a ghost for this step (already binned)
+        c.own[i] = -1;
+        c.free_slots[atomicAdd(c.n_free, 1)] = i;         // at most pool_cap tombstones can exist
+        const int slot = atomicAdd(c.n_ghost, 1);
+        if (slot < p.pool_cap) c.ghost[slot] = a; else *p.overflow = 1;
+    }
+    bool wanted = new_owner >= 0;                         // who needs this agent's state?
+    for (int q = 0; q < c.world && !wanted; ++q) {
+        if (q == c.rank) continue;
+        const bool in_strip = xs >= c.bounds[q] - c.depth && xs <= c.bounds[q + 1] + c.depth;
+        const bool in_ival = st.x >= windows[q * wstride] - c.depth && st.x <= windows[q * wstride + 1] + c.depth;
+        wanted = in_strip || in_ival;
+    }
+    if (wanted) {
+        const int slot = atomicAdd(c.counter, 1);
+        if (slot < cap) {                                  // overflow is reported through the header count
+            double* rec = buf + (size_t)(slot + 1) * SREC;
+            rec[0] = (double)a; rec[1] = st.x; rec[2] = st.y; rec[3] = st.z; rec[4] = st.w; rec[5] = (double)new_owner;
+        }
+    }
+}
+
+// per-block reduction of the kept x-interval into slot blockIdx.x (k_shard_header reduces the slots)
+template <int THREADS>
+__device__ __forceinline__ void shard_interval_flush(const ShardCtl& c, long long klo, long long khi) {
+    __shared__ long long s_klo[THREADS / 32], s_khi[THREADS / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        klo = min(klo, __shfl_xor_sync(0xffffffffu, klo, o));
+        khi = max(khi, __shfl_xor_sync(0xffffffffu, khi, o));
+    }
+    if ((threadIdx.x & 31) == 0) { s_klo[threadIdx.x >> 5] = klo; s_khi[threadIdx.x >> 5] = khi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < THREADS / 32; ++w) { klo = min(klo, s_klo[w]); khi = max(khi, s_khi[w]); }
+        c.xminmax[2 * blockIdx.x] = klo;
+        c.xminmax[2 * blockIdx.x + 1] = khi;
+    }
+}
+
+// arguments of the pack step when it is fused into the closed final kernel (device-resident: the CUDA graph
+// of a step stays valid when buffers change)
+struct ShardFuse {
+    ShardCtl ctl;
+    const double* windows;
+    long long wstride;
+    double* buf;
+    int cap;
+};
+
 // double integrator exactly in numpy's evaluation order (no FMA contraction), then bin the new position
-__device__ __forceinline__ void integrate_and_bin(const Params& p, int a, const double4 s, float u0, float u1,
-                                                  double (&racc)[4]) {
+__device__ __forceinline__ double4 integrate_and_bin(const Params& p, int a, const double4 s, float u0, float u1,
+                                                     double (&racc)[4]) {
     const double ax = __dmul_rn((double)u0, p.gain), ay = __dmul_rn((double)u1, p.gain);
     double nx = __dadd_rn(s.x, __dmul_rn(s.z, p.dt));
     double ny = __dadd_rn(s.y, __dmul_rn(s.w, p.dt));
@@ -640,6 +744,7 @@ __device__ __forceinline__ void integrate_and_bin(const Params& p, int a, const 
         }
     }
     if (threadIdx.x == 0 && blockIdx.x == 0) *p.reward_pending = 1;
+    return make_double4(nx, ny, nvx, nvy);
 }
 
 // B == 1: sum the block's thread-local reward sums in a fixed order and store them as this block's partial.
@@ -790,89 +895,30 @@ __global__ void __launch_bounds__(128) k_controller(Params p, int centralized, i
 //   k_shard_unpack  : install received states; new owner -> appended to the owned list, otherwise ghost list; bin
 // A rank's window = its strip +- depth, united with the x-interval of what it still owns +- depth.
 // ------------------------------------------------------------------------------------------
-constexpr int SREC = 6;
-
-struct ShardCtl {
-    const double* bounds;     // [world + 1] strip boundaries at shift = 0 (bounds[0] = -inf, bounds[world] = +inf)
-    double* shift;            // device scalar: frame displacement so far
-    double dshift;            // per step
-    double depth;             // halo depth for the windows
-    double margin;            // hand-over hysteresis
-    int world, rank;
-    int handover_after;       // first step index at which hand-overs are allowed (histories must be valid)
-    int* own;                 // [pool_cap] owned list: order kept, -1 = handed over, appended at n_own
-    int* n_own;               // high-water mark
-    int* ghost;               // [pool_cap]
-    int* n_ghost;
-    int* counter;             // records written
-    long long* xminmax;       // order-preserving keys of min / max px over the agents kept
-};
-
-// order-preserving map double <-> signed 64-bit integer (for atomicMin / atomicMax on coordinates)
-__device__ __forceinline__ long long dkey(double x) {
-    long long b = __double_as_longlong(x);
-    return b >= 0 ? b : b ^ 0x7fffffffffffffffll;
-}
-__device__ __forceinline__ double dunkey(long long k) {
-    return __longlong_as_double(k >= 0 ? k : k ^ 0x7fffffffffffffffll);
-}
-
 __global__ void k_shard_prepare(ShardCtl c, int advance) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         *c.n_ghost = 0; *c.counter = 0;
-        c.xminmax[0] = 0x7fffffffffffffffll;
-        c.xminmax[1] = -0x7fffffffffffffffll - 1;
         if (advance) *c.shift += c.dshift;
     }
 }
 
-__device__ __forceinline__ int strip_of(const ShardCtl& c, double xs) {
-    int s = 0;
-    for (int q = 1; q < c.world; ++q) s += (xs >= c.bounds[q]) ? 1 : 0;
-    return s;
-}
-
 __global__ void __launch_bounds__(256) k_shard_pack(Params p, ShardCtl c, const double* __restrict__ windows, long long wstride,
                                                     double* __restrict__ buf, int cap) {
-    __shared__ long long s_lo[8], s_hi[8];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     long long klo = 0x7fffffffffffffffll, khi = -0x7fffffffffffffffll - 1;
     const int a = i < owned_count(p) ? owned_agent(p, i) : -1;
-    if (a >= 0) {
-        const double4 s = p.state[a];
-        const double shift = *c.shift;
-        const double xs = s.x - shift;
-        // hand-over decision
-        int new_owner = -1;
-        if (*p.t >= c.handover_after) {
-            const int st = strip_of(c, xs);
-            if (st > c.rank && xs - c.bounds[c.rank + 1] > c.margin) new_owner = st;
-            if (st < c.rank && c.bounds[c.rank] - xs > c.margin) new_owner = st;
-        }
-        if (new_owner < 0) {
-            klo = khi = dkey(s.x);
-        } else {                                              // tombstone; stays here as a ghost for this step (already binned)
-            c.own[i] = -1;
-            const int slot = atomicAdd(c.n_ghost, 1);
-            if (slot < p.pool_cap) c.ghost[slot] = a; else *p.overflow = 1;
-        }
-        // who needs this agent's state?
-        bool wanted = new_owner >= 0;
-        for (int q = 0; q < c.world && !wanted; ++q) {
-            if (q == c.rank) continue;
-            const bool in_strip = xs >= c.bounds[q] - c.depth && xs <= c.bounds[q + 1] + c.depth;
-            const bool in_ival = s.x >= windows[q * wstride] - c.depth && s.x <= windows[q * wstride + 1] + c.depth;
-            wanted = in_strip || in_ival;
-        }
-        if (wanted) {
-            const int slot = atomicAdd(c.counter, 1);
-            if (slot < cap) {                                  // overflow is reported through the header count
-                double* rec = buf + (size_t)(slot + 1) * SREC;
-                rec[0] = (double)a; rec[1] = s.x; rec[2] = s.y; rec[3] = s.z; rec[4] = s.w; rec[5] = (double)new_owner;
-            }
-        }
+    if (a >= 0) shard_pack_agent(p, c, windows, wstride, buf, cap, i, a, p.state[a], klo, khi);
+    shard_interval_flush<256>(c, klo, khi);
+}
+
+// header record [count, x_lo, x_hi, 0, 0, 0]: reduce the per-block intervals written by k_shard_pack
+__global__ void __launch_bounds__(256) k_shard_header(ShardCtl c, double* __restrict__ buf, int n_blocks) {
+    __shared__ long long s_lo[8], s_hi[8];
+    long long klo = 0x7fffffffffffffffll, khi = -0x7fffffffffffffffll - 1;
+    for (int i = threadIdx.x; i < n_blocks; i += blockDim.x) {
+        klo = min(klo, c.xminmax[2 * i]);
+        khi = max(khi, c.xminmax[2 * i + 1]);
     }
-    // x-interval of what this rank keeps: block reduce, one atomic pair per block
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         klo = min(klo, __shfl_xor_sync(0xffffffffu, klo, o));
@@ -882,15 +928,7 @@ __global__ void __launch_bounds__(256) k_shard_pack(Params p, ShardCtl c, const 
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int w = 1; w < 8; ++w) { klo = min(klo, s_lo[w]); khi = max(khi, s_hi[w]); }
-        atomicMin(&c.xminmax[0], klo);
-        atomicMax(&c.xminmax[1], khi);
-    }
-}
-
-// header record [count, x_lo, x_hi, 0, 0, 0]
-__global__ void k_shard_header(ShardCtl c, double* __restrict__ buf) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        buf[0] = (double)*c.counter; buf[1] = dunkey(c.xminmax[0]); buf[2] = dunkey(c.xminmax[1]);
+        buf[0] = (double)*c.counter; buf[1] = dunkey(klo); buf[2] = dunkey(khi);
         buf[3] = 0.0; buf[4] = 0.0; buf[5] = 0.0;
     }
 }
@@ -915,9 +953,15 @@ __global__ void __launch_bounds__(256) k_shard_unpack(Params p, ShardCtl c, cons
     if (new_owner != c.rank && !in_strip && !in_ival) return;  // not near this rank
     const int a = (int)rec[0];
     p.state[a] = make_double4(rec[1], rec[2], rec[3], rec[4]);
-    if (new_owner == c.rank) {                                 // append to the owned list
-        const int slot = atomicAdd(c.n_own, 1);
-        if (slot < p.pool_cap) c.own[slot] = a; else { atomicSub(c.n_own, 1); *p.overflow = 1; }
+    if (new_owner == c.rank) {                                 // into a tombstoned slot if there is one, else appended
+        const int k = atomicSub(c.n_free, 1) - 1;
+        if (k >= 0) {
+            c.own[c.free_slots[k]] = a;
+        } else {
+            atomicAdd(c.n_free, 1);
+            const int slot = atomicAdd(c.n_own, 1);
+            if (slot < p.pool_cap) c.own[slot] = a; else { atomicSub(c.n_own, 1); *p.overflow = 1; }
+        }
     } else {
         const int slot = atomicAdd(c.n_ghost, 1);
         if (slot < p.pool_cap) c.ghost[slot] = a; else *p.overflow = 1;
@@ -931,10 +975,10 @@ __global__ void __launch_bounds__(256) k_shard_unpack(Params p, ShardCtl c, cons
 
 // owned list = contiguous range [lo, lo + count)  (reset)
 __global__ void __launch_bounds__(256) k_own_init(int* __restrict__ own, int* __restrict__ n_own, int* __restrict__ n_ghost,
-                                                  int lo, int count) {
+                                                  int* __restrict__ n_free, int lo, int count) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < count) own[i] = lo + i;
-    if (i == 0) { *n_own = count; *n_ghost = 0; }
+    if (i == 0) { *n_own = count; *n_ghost = 0; *n_free = 0; }
 }
 
 // owned-list order <-> global arrays (policy / integrate on a sharded handle)
