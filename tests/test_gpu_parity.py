@@ -287,3 +287,56 @@ def test_edge_cases():
     # bad configuration is rejected with a message
     with pytest.raises(FgnnError):
         FlockEngine(n_agents=10, k=9)
+
+
+def _random_state_dict(rng, k, hidden, n_layers, scale=0.3):
+    dims = [6] + [hidden] * n_layers + [2]
+    sd = {}
+    for i in range(len(dims) - 1):
+        step = k if i == 0 else 1
+        sd[f"conv_layers.{i}.weight"] = (rng.standard_normal((dims[i + 1], dims[i], step, 1)) * scale /
+                                         np.sqrt(dims[i] * step)).astype(np.float32)
+        sd[f"conv_layers.{i}.bias"] = (rng.standard_normal(dims[i + 1]) * 0.1).astype(np.float32)
+    return sd
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 4])
+@pytest.mark.parametrize("hidden,n_layers", [(4, 1), (16, 2), (32, 3), (64, 4), (48, 2), (128, 2)])
+@pytest.mark.parametrize("mean_pooling", [True, False])
+def test_architecture_sweep_against_dense_oracle(k, hidden, n_layers, mean_pooling):
+    """Every (K, H, L) the cfg sweeps use (cfg/hidden_size.cfg, cfg/n.cfg, k in 1..4), both pooling modes,
+    both readouts: select_action checked step by step against the dense numpy oracle."""
+    from multiagent_gnn_policies_b200.engine import FlockEngine
+    rng = np.random.default_rng(1000 * k + hidden + n_layers)
+    n = 150
+    sd = _random_state_dict(rng, k, hidden, n_layers)
+    layers = learner.weights_from_state_dict(sd)
+    x0 = flock_env.synthetic_state(n, seed=k + hidden, density=1.6)
+    for readout in (FFMA, TENSOR):
+        if readout == TENSOR and hidden > 64:
+            continue
+        eng = FlockEngine(n_agents=n, k=k, hidden=hidden, n_layers=n_layers, comm_radius=1.2, dt=0.01,
+                          mean_pooling=mean_pooling, readout_mode=readout, edge_capacity=64)
+        eng.load_state_dict(sd)
+        eng.reset(x0)
+        x, state, sstate = x0.copy(), None, None
+        for t in range(k + 3):
+            sv, sn, _, deg = flock_env.compute_helpers(x, 1.2 ** 2, mean_pooling=mean_pooling)
+            state = learner.DelayState((sv, sn), prev_state=state, k=k)
+            a_ref = learner.select_action(layers, state)
+            assert np.array_equal(eng.get_degrees(), deg)
+            a = eng.policy().cpu().numpy()
+            # yardstick: the same fp32 inputs evaluated in float64.  These random actors have |a| ~ 0.3 from
+            # |features| ~ 1e2..1e3, so fp32 rounding alone is ~1e-5 of ||a||: the CUDA path must be as close to
+            # the float64 value as the reference arithmetic (fp32 oracle) is, or within the 1e-5 bar.
+            sv_s, deg_s, ei, ej = sparse.compute_helpers_sparse(x, 1.2)
+            sstate = sparse.SparseDelayState(sv_s, sparse.network_csr(n, deg_s, ei, ej, mean_pooling), prev_state=sstate, k=k)
+            truth = sparse.readout(layers, sstate.aggregate(np.float64), np.float64)
+            assert rel_inf(a, truth) <= max(TOL_ACTION, 3.0 * rel_inf(a_ref, truth)), (readout, t)
+            assert rel_inf(a, a_ref) <= max(3.0 * TOL_ACTION, 6.0 * rel_inf(a_ref, truth)), (readout, t)
+            # the expert drives (a random policy lets agents collide, |features| -> 1e6, fp32 ill-conditioned)
+            u = flock_env.controller(x, 1.2, 1.2 ** 2, centralized=False).astype(np.float32)
+            eng.env_step(u)
+            x = flock_env.integrate(x, u, 0.01)
+            np.testing.assert_array_equal(eng.get_state(), x)
+        eng.close()
