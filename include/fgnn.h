@@ -155,6 +155,37 @@ int fgnn_shard_step_begin(fgnn_handle* h, const double* windows, int64_t window_
 int fgnn_shard_step_end(fgnn_handle* h, const double* recv_buf, int32_t cap, void* stream);
 int fgnn_shard_owned(fgnn_handle* h, int32_t* ids, int32_t* count, void* stream);   /* synchronises */
 
+/* ---- environment variants named by the reference's cfgs (gym_flock, un-vendored) ----
+ * FlockingLeader-v0 (cfg/dagger_leader.cfg:24): mask_bn (B*N,) bytes [h/d], 0 = leader -- the integrator ignores
+ * its action (u * mask), in every integrator path including the fused closed-loop kernel.  NULL removes the mask.
+ * FlockingStochastic-v0 (cfg/dagger_stoch.cfg:24, no `dt` key): the time step is drawn by the env every step;
+ * fgnn_set_dt installs it for the following integrations (cached CUDA graphs are re-captured). */
+int fgnn_set_agent_mask(fgnn_handle* h, const uint8_t* mask_bn, void* stream);
+int fgnn_set_dt(fgnn_handle* h, double dt);
+
+/* ---- imitation-learning update ----
+ * DAGGER.gradient_step (learner/gnn_dagger.py:76-96) / Cloning.gradient_step: Actor.forward on a batch of stored
+ * states, F.mse_loss against the expert actions, backward, Adam step (learner/gnn_dagger.py:49, torch defaults).
+ * With ind_agg = 0 (gnn_dagger.py:43) only the readout is trainable and it sits behind the aggregation, so the
+ * batch is given as the aggregated features of each stored state, z = delay_state @ delay_gso (actor.py:70):
+ *   z_bkn6      (batch, K, N, 6)  fp32 DEVICE  (what fgnn_get_aggregated returns per state)
+ *   target_b2n  (batch, 2, N)     fp32 DEVICE  (torch.cat(batch.action), gnn_dagger.py:86)
+ *   params / exp_avg / exp_avg_sq: HOST arrays of 2(L+1) DEVICE pointers in the order W_0, b_0, ..., W_L, b_L, each
+ *     tensor in the reference's conv layout (learner/actor.py:30-40) -- the torch parameters and the torch.optim.Adam
+ *     state tensors themselves, updated in place.  step = 1-based count of this update (Adam bias correction).
+ *   apply = 0: loss / gradients only, nothing is modified (exp_avg* may be NULL).
+ *   loss_out (1,) fp32 [h/d] or NULL; grads_out (fgnn_trainer_param_count,) fp32 [h/d] or NULL: the gradients packed
+ *     in the same order as `params`. */
+typedef struct fgnn_trainer fgnn_trainer;
+int fgnn_trainer_create(int32_t k, int32_t hidden, int32_t n_layers, int32_t device, fgnn_trainer** out);
+int fgnn_trainer_destroy(fgnn_trainer* tr);
+int32_t fgnn_trainer_param_count(fgnn_trainer* tr);
+int64_t fgnn_trainer_launch_count(fgnn_trainer* tr);
+int fgnn_trainer_step(fgnn_trainer* tr, int32_t batch, int32_t n_agents, const float* z_bkn6, const float* target_b2n,
+                      float* const* params, float* const* exp_avg, float* const* exp_avg_sq, int64_t step, double lr,
+                      double beta1, double beta2, double eps, int32_t apply, float* loss_out, float* grads_out,
+                      void* stream);
+
 /* One closed-loop step (same work as fgnn_step) with a CUDA event after every kernel: ms_out[i] is the
  * device time of kernel i, names_out (16 bytes each, may be NULL) its name.  For bench.py's roofline. */
 int fgnn_profile_step(fgnn_handle* h, int32_t max_kernels, float* ms_out, char* names_out, int32_t* n_out,

@@ -37,6 +37,8 @@ def _units():
     units = [(os.path.join(OBJ, "fgnn.o"), os.path.join(CSRC, "fgnn.cu"), [],
               common_deps + [os.path.join(INCLUDE, "fgnn.h"), os.path.join(CSRC, "fgnn_final.cuh"),
                              os.path.join(CSRC, "fgnn_final_tc.cuh")])]
+    units.append((os.path.join(OBJ, "fgnn_train.o"), os.path.join(CSRC, "fgnn_train.cu"), [],
+                  [os.path.join(INCLUDE, "fgnn.h")]))
     for k in KS:
         for hp in HPS:
             units.append((os.path.join(OBJ, f"fgnn_final_k{k}_hp{hp}.o"), os.path.join(CSRC, "fgnn_final.cu"),

@@ -52,9 +52,10 @@ class EngineState(tuple):
     """``(state_values, state_network)`` tuple that also remembers which engine / step produced it, so
     the learner-side shims can stay on the device-resident sparse history."""
 
-    def __new__(cls, values, network, engine, step):
+    def __new__(cls, values, network, engine, step, record_aggregated=False):
         obj = super().__new__(cls, (values, network))
         obj.engine, obj.step = engine, step
+        obj.record_aggregated = record_aggregated
         return obj
 
 
@@ -80,6 +81,8 @@ class FlockingRelativeEnv:
         # learner architecture the engine is built for (read from the cfg when present)
         self.k, self.hidden_size, self.n_layers = 3, 32, 2
         self.device_index = 0
+        # training loops set this: states then carry the aggregated features the native gradient step consumes
+        self.record_aggregated = False
         self._engine = None
         self._engine_key = None
         self._step = 0
@@ -93,7 +96,7 @@ class FlockingRelativeEnv:
         self.r_max = self.r_max0 * np.sqrt(self.n_agents)
         self.v_max = args.getfloat('v_max')
         self.v_bias = self.v_max
-        self.dt = args.getfloat('dt')
+        self.dt = args.getfloat('dt', fallback=None) or self.dt        # the *_stoch / airsim cfgs carry no dt
         self.k = args.getint('k', fallback=self.k)
         self.hidden_size = args.getint('hidden_size', fallback=self.hidden_size)
         self.n_layers = args.getint('n_layers', fallback=None) or 2
@@ -142,7 +145,8 @@ class FlockingRelativeEnv:
     def _observe(self):
         eng = self.engine
         values = eng.get_features().astype(np.float64)
-        return EngineState(values, LazyNetwork(eng, self.n_agents, self._step), eng, self._step)
+        return EngineState(values, LazyNetwork(eng, self.n_agents, self._step), eng, self._step,
+                           self.record_aggregated)
 
     def reset(self, x0=None):
         self.x = self._sample_initial_state() if x0 is None else np.array(x0, dtype=np.float64)

@@ -31,6 +31,7 @@ class Actor(nn.Module):
         self.conv_layers = nn.ModuleList(convs)
         self._engine = None
         self._engine_versions = None
+        self.native_updates = 0        # bumped by the native gradient step (it bypasses torch's version counters)
 
     # -- engine plumbing --------------------------------------------------------------------
     def _engine_supported(self):
@@ -39,7 +40,7 @@ class Actor(nn.Module):
                 and len(set(hidden)) == 1 and hidden[0] <= 128 and 1 <= self.k <= 4)
 
     def weight_versions(self):
-        return tuple(p._version for p in self.parameters())
+        return (self.native_updates,) + tuple(p._version for p in self.parameters())
 
     def sync_engine(self, engine):
         """Push the current parameters into ``engine`` if they changed since the last push."""

@@ -24,6 +24,9 @@ def train_cloning(env, args, device):
     test_interval = args.getint('test_interval')
     n_test_episodes = args.getint('n_test_episodes')
 
+    if hasattr(env, 'env') and hasattr(env.env, 'record_aggregated'):
+        env.env.record_aggregated = True          # states carry what the native gradient step consumes
+
     total_numsteps, updates = 0, 0
     stats = {'mean': -1.0 * np.inf, 'std': 0}
     for episode in range(n_train_episodes):

@@ -3,7 +3,10 @@
 ``select_action`` is the inference hot path: for a state that came from the engine-backed env it runs
 the sparse CUDA kernels on the history the engine already holds (no dense N x N tensors at all);
 otherwise it evaluates ``Actor.forward`` on the dense tensors through the dense CUDA kernel.
-``gradient_step`` (training, SURVEY.md 8f "next" row) uses torch autograd on the GPU.
+``gradient_step`` (training) runs natively (libfgnn.so: fused MLP forward / MSE /
+backward kernel + Adam kernel, updating the torch parameters and the torch Adam state in place) whenever every
+sampled state carries its aggregated features (states recorded by ``train_dagger`` / ``train_cloning`` on the
+engine-backed env); states built from dense tensors fall back to torch autograd on the GPU.
 """
 import os
 
@@ -15,6 +18,7 @@ from torch.optim import Adam
 from learner.actor import Actor
 from learner.replay_buffer import ReplayBuffer, Transition
 from learner.state_with_delay import MultiAgentStateWithDelay
+from multiagent_gnn_policies_b200.engine import ActorTrainer
 
 
 class DAGGER(object):
@@ -33,6 +37,47 @@ class DAGGER(object):
         self.actor_optim = Adam(self.actor.parameters(), lr=args.getfloat('actor_lr'))
         self.gamma = args.getfloat('gamma')
         self.tau = args.getfloat('tau')
+        self._trainer = None
+
+    # -- native update ------------------------------------------------------------------------
+    def _adam_tensors(self):
+        """The torch.optim.Adam state of every parameter (created like Adam.step would on first use), as
+        lists in parameter order: the native kernel updates these tensors in place, so ``actor_optim``
+        (state_dict, a later torch-side ``step``) stays consistent."""
+        params = [p for g in self.actor_optim.param_groups for p in g['params']]
+        m, v = [], []
+        for p in params:
+            st = self.actor_optim.state[p]
+            if len(st) == 0:
+                st['step'] = torch.tensor(0.0, dtype=torch.float32)
+                st['exp_avg'] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                st['exp_avg_sq'] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            m.append(st['exp_avg'])
+            v.append(st['exp_avg_sq'])
+        return params, m, v
+
+    def _native_gradient_step(self, batch):
+        if self._trainer is None:
+            self._trainer = ActorTrainer(self.actor.k, self.actor.layers[1], self.actor.n_layers - 1,
+                                         device=torch.device(self.device).index or 0)
+        z = torch.stack([s.aggregated for s in batch.state])                    # (B,K,N,6)
+        target = torch.cat(batch.action).to(self.device)                          # (B,1,nA,N)
+        params, m, v = self._adam_tensors()
+        group = self.actor_optim.param_groups[0]
+        step = int(self.actor_optim.state[params[0]]['step'].item()) + 1
+        loss, _ = self._trainer.step(z, target, [p.data for p in params], m, v, step=step, lr=group['lr'],
+                                     betas=group['betas'], eps=group['eps'])
+        for p in params:
+            self.actor_optim.state[p]['step'] += 1
+        self.actor.native_updates += 1            # the engine-side weight cache keys on this
+        return loss.item()
+
+    def _native_supported(self, batch):
+        group = self.actor_optim.param_groups
+        return (len(group) == 1 and not group[0].get('amsgrad') and not group[0].get('weight_decay')
+                and not group[0].get('maximize') and self.actor._engine_supported()
+                and torch.device(self.device).type == "cuda"
+                and all(getattr(s, "aggregated", None) is not None for s in batch.state))
 
     def select_action(self, state):
         """(N, n_actions) tensor on ``self.device`` -- callers do ``.cpu().numpy()`` (gnn_dagger.py:161)."""
@@ -50,6 +95,8 @@ class DAGGER(object):
         return mu.data
 
     def gradient_step(self, batch):
+        if self._native_supported(batch):
+            return self._native_gradient_step(batch)
         delay_gso_batch = torch.cat(tuple(s.delay_gso for s in batch.state)).to(self.device)
         delay_state_batch = torch.cat(tuple(s.delay_state for s in batch.state)).to(self.device)
         actor_batch = self.actor(delay_state_batch, delay_gso_batch)
@@ -76,6 +123,20 @@ class DAGGER(object):
 def _evaluate(env, learner, args, device, n_episodes):
     """Learner-only rollouts (gnn_dagger.py:190-231): list of episode rewards."""
     rewards = []
+    raw = getattr(env, 'env', None)
+    recording = getattr(raw, 'record_aggregated', False)
+    if recording:
+        raw.record_aggregated = False            # evaluation states are never stored
+    try:
+        rewards = _evaluate_episodes(env, learner, args, device, n_episodes)
+    finally:
+        if recording:
+            raw.record_aggregated = True
+    return rewards
+
+
+def _evaluate_episodes(env, learner, args, device, n_episodes):
+    rewards = []
     for _ in range(n_episodes):
         total = 0
         state = MultiAgentStateWithDelay(device, args, env.reset(), prev_state=None)
@@ -100,6 +161,9 @@ def train_dagger(env, args, device):
     beta_coeff = args.getfloat('beta_coeff')
     test_interval = args.getint('test_interval')
     n_test_episodes = args.getint('n_test_episodes')
+
+    if hasattr(env, 'env') and hasattr(env.env, 'record_aggregated'):
+        env.env.record_aggregated = True          # states carry what the native gradient step consumes
 
     total_numsteps, updates, beta = 0, 0, 1
     stats = {'mean': -1.0 * np.inf, 'std': 0}

@@ -3,7 +3,10 @@
 
 When ``env_state`` comes from the engine-backed env (an ``EngineState``) nothing dense is built: the
 K-deep history already lives on the device as CSR graphs + feature rows, and ``DAGGER.select_action``
-runs the sparse kernels.  The dense attributes are materialised lazily, on first access, from short
+runs the sparse kernels.  When the env is in training mode (``env.record_aggregated``, set by
+``train_dagger`` / ``train_cloning``) the state also captures ``aggregated``: the K-hop aggregated features
+z (K,N,6) on the device -- all that ``gradient_step`` needs from a stored state (ind_agg = 0), 6K floats per
+agent instead of the reference's dense (K,N,N) operator.  The dense attributes are materialised lazily, on first access, from short
 per-state histories of device tensors (never from ``prev_state`` itself, so episodes do not leak) --
 that is what the replay buffer / ``gradient_step`` read.  A plain ``(ndarray, ndarray)`` tuple (e.g.
 from another env) takes the dense route immediately, like the reference.
@@ -30,6 +33,10 @@ class MultiAgentStateWithDelay(object):
 
         self.engine = getattr(env_state, "engine", None)
         self.step = getattr(env_state, "step", None)
+        self.aggregated = None
+        if (self.engine is not None and getattr(env_state, "record_aggregated", False)
+                and self.engine.step_index == self.step and self.engine.k == k):
+            self.aggregated = self.engine.aggregate()          # (K,N,6) CUDA tensor, hops on the sparse history
         self._values = self._network = self._curr_gso = self._delay_gso = self._delay_state = None
 
         x_t = torch.as_tensor(np.asarray(state_value), dtype=torch.float32, device=self.device).t().contiguous()   # (F,N)

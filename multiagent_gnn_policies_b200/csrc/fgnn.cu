@@ -15,6 +15,7 @@ using namespace fgnn;
 
 static thread_local std::string g_err;
 static int fail(const std::string& msg) { g_err = msg; return 1; }
+namespace fgnn { void set_error(const char* msg) { g_err = msg ? msg : ""; } }     // for the other translation units
 
 #define CK(call)                                                                                     \
     do {                                                                                             \
@@ -34,6 +35,7 @@ struct fgnn_handle {
     size_t weights_floats = 0;
     std::vector<float> w_host;       // packed weights, host mirror
     float* d_weights = nullptr;
+    unsigned char* d_amask = nullptr; // [M] leader mask (allocated by fgnn_set_agent_mask)
     float* d_u_in = nullptr;         // [M][2] staged external action
     float* d_staging = nullptr;      // read-back staging (K*M*6 floats)
     double* d_reward_log = nullptr;
@@ -1002,6 +1004,39 @@ extern "C" int fgnn_profile_step(fgnn_handle* h, int32_t max_kernels, float* ms_
     CK(cudaEventDestroy(e0));
     for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
     h->prof_events.clear();
+    return 0;
+}
+
+// cached CUDA graphs bake the kernel arguments (Params by value): drop them when an argument changes
+static void invalidate_graphs(fgnn_handle* h) {
+    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+    if (h->graph) { cudaGraphDestroy(h->graph); h->graph = nullptr; }
+    h->shard_epoch += 1;
+}
+
+extern "C" int fgnn_set_dt(fgnn_handle* h, double dt) {
+    if (!h) return fail("fgnn_set_dt: null handle");
+    if (!(dt > 0.0)) return fail("fgnn_set_dt: dt must be > 0");
+    if (dt != h->p.dt) {
+        CK(cudaSetDevice(h->cfg.device));
+        h->p.dt = dt;
+        h->cfg.dt = dt;
+        invalidate_graphs(h);
+    }
+    return 0;
+}
+
+extern "C" int fgnn_set_agent_mask(fgnn_handle* h, const uint8_t* mask, void* stream) {
+    if (!h) return fail("fgnn_set_agent_mask: null handle");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(h->cfg.device));
+    if (!mask) {
+        if (h->p.amask) { h->p.amask = nullptr; invalidate_graphs(h); }
+        return 0;
+    }
+    if (!h->d_amask && dalloc(h, &h->d_amask, (size_t)h->p.M, false)) return 1;
+    CK(cudaMemcpyAsync(h->d_amask, mask, (size_t)h->p.M, cudaMemcpyDefault, st));
+    if (h->p.amask != h->d_amask) { h->p.amask = h->d_amask; invalidate_graphs(h); }
     return 0;
 }
 

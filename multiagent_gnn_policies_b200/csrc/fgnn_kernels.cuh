@@ -78,6 +78,7 @@ struct Params {
     float* ybuf;              // [2][K][M][ROW] hop intermediates (ping-pong)
     float* action;            // [M][2]
     const float* weights;     // packed, see WeightLayout
+    const unsigned char* amask;   // [M] or null; 0 = leader: the integrator ignores its action (FlockingLeader-v0)
 
     double* racc;             // [RSLOTS][B][4] sum vx, vy, vx^2, vy^2 (slotted atomics, B > 1)
     double* racc_part;        // [max grid][4] per-block partial sums (B == 1: no atomics, fixed order)
@@ -703,7 +704,8 @@ struct ShardFuse {
 // double integrator exactly in numpy's evaluation order (no FMA contraction), then bin the new position
 __device__ __forceinline__ double4 integrate_and_bin(const Params& p, int a, const double4 s, float u0, float u1,
                                                      double (&racc)[4]) {
-    const double ax = __dmul_rn((double)u0, p.gain), ay = __dmul_rn((double)u1, p.gain);
+    double ax = __dmul_rn((double)u0, p.gain), ay = __dmul_rn((double)u1, p.gain);
+    if (p.amask && p.amask[a] == 0) { ax = 0.0; ay = 0.0; }      // u * mask (leaders keep their velocity)
     double nx = __dadd_rn(s.x, __dmul_rn(s.z, p.dt));
     double ny = __dadd_rn(s.y, __dmul_rn(s.w, p.dt));
     if (p.half_accel) {

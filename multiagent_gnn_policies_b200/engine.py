@@ -19,6 +19,9 @@ ABI_SYMBOLS = [
     "fgnn_get_aggregated", "fgnn_get_action", "fgnn_export_network_dense", "fgnn_get_csr", "fgnn_get_stats",
     "fgnn_shard_configure", "fgnn_shard_local_step", "fgnn_shard_pack", "fgnn_shard_unpack", "fgnn_shard_step_begin",
     "fgnn_shard_step_end", "fgnn_shard_owned", "fgnn_profile_step", "fgnn_memcpy_sync", "fgnn_launch_count",
+    "fgnn_set_agent_mask", "fgnn_set_dt",
+    "fgnn_trainer_create", "fgnn_trainer_destroy", "fgnn_trainer_param_count", "fgnn_trainer_launch_count",
+    "fgnn_trainer_step",
 ]
 
 
@@ -95,8 +98,18 @@ def load_library(path=None):
     lib.fgnn_memcpy_sync.argtypes = [vp, vp, ctypes.c_uint64, vp]
     lib.fgnn_launch_count.argtypes = [vp]
     lib.fgnn_launch_count.restype = i64
+    lib.fgnn_set_agent_mask.argtypes = [vp, vp, vp]
+    lib.fgnn_set_dt.argtypes = [vp, dbl]
+    lib.fgnn_trainer_create.argtypes = [i32, i32, i32, i32, ctypes.POINTER(vp)]
+    lib.fgnn_trainer_destroy.argtypes = [vp]
+    lib.fgnn_trainer_param_count.argtypes = [vp]
+    lib.fgnn_trainer_param_count.restype = i32
+    lib.fgnn_trainer_launch_count.argtypes = [vp]
+    lib.fgnn_trainer_launch_count.restype = i64
+    lib.fgnn_trainer_step.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, i64, dbl, dbl, dbl, dbl, i32, vp, vp, vp]
     for name in ABI_SYMBOLS:
-        if name not in ("fgnn_last_error", "fgnn_launch_count", "fgnn_version"):
+        if name not in ("fgnn_last_error", "fgnn_launch_count", "fgnn_version", "fgnn_trainer_param_count",
+                        "fgnn_trainer_launch_count"):
             getattr(lib, name).restype = ctypes.c_int
     if path == LIB_PATH:
         _lib = lib
@@ -310,11 +323,36 @@ class FlockEngine:
         self.sync()
         return d
 
-    def get_aggregated(self):
+    def get_aggregated(self, device=False):
+        """(K, B*N, 6) aggregated features z_k of the last policy call (numpy, or a CUDA tensor)."""
+        if device:
+            z = self._torch.empty((self.k, self.M, 6), dtype=self._torch.float32, device=self.device)
+            self._check(self.lib.fgnn_get_aggregated(self._h, _ptr(z), self.stream))
+            return z
         z = np.empty((self.k, self.M, 6), dtype=np.float32)
         self._check(self.lib.fgnn_get_aggregated(self._h, _ptr(z), self.stream))
         self.sync()
         return z
+
+    def aggregate(self):
+        """K-hop aggregation of the current history (actor.py:68-71 on the sparse graphs): (K, B*N, 6) CUDA
+        tensor.  This is everything ``gradient_step`` needs from a state (ind_agg = 0)."""
+        self._check(self.lib.fgnn_policy(self._h, None, self.stream))
+        return self.get_aggregated(device=True)
+
+    # -- env variants (SURVEY.md 8f row f3) ---------------------------------------------------
+    def set_agent_mask(self, mask):
+        """FlockingLeader: ``mask`` (B*N,) with 0 for leaders (their action is ignored); None removes it."""
+        if mask is not None:
+            mask = np.ascontiguousarray(np.asarray(mask) != 0, dtype=np.uint8)
+            assert mask.size == self.M
+        self._check(self.lib.fgnn_set_agent_mask(self._h, _ptr(mask), self.stream))
+        self.sync()
+
+    def set_dt(self, dt):
+        """FlockingStochastic: the time step of the following integrations."""
+        self._check(self.lib.fgnn_set_dt(self._h, float(dt)))
+        self.dt = float(dt)
 
     def get_action(self):
         a = np.empty((self.M, 2), dtype=np.float32)
@@ -402,3 +440,67 @@ class FlockEngine:
 
     def launch_count(self):
         return int(self.lib.fgnn_launch_count(self._h))
+
+
+class ActorTrainer:
+    """Native ``gradient_step`` (learner/gnn_dagger.py:76-96): MLP forward, MSE loss, backward and Adam on the
+    device, updating the torch parameters and the torch.optim.Adam state tensors IN PLACE.
+
+    ``params`` / ``exp_avg`` / ``exp_avg_sq`` are lists of CUDA tensors in the order W_0, b_0, ..., W_L, b_L
+    (conv layout of learner/actor.py:30-40)."""
+
+    def __init__(self, k, hidden, n_layers, device=0):
+        import torch
+        if not torch.cuda.is_available():
+            raise FgnnError("no CUDA device: the trainer has no CPU fallback")
+        self._torch = torch
+        self.lib = load_library()
+        self.k, self.hidden, self.n_layers = int(k), int(hidden), int(n_layers)
+        self.device = torch.device("cuda", int(device))
+        self._h = ctypes.c_void_p()
+        self._check(self.lib.fgnn_trainer_create(self.k, self.hidden, self.n_layers, int(device), ctypes.byref(self._h)))
+        self.n_params = int(self.lib.fgnn_trainer_param_count(self._h))
+
+    def _check(self, rc):
+        if rc != 0:
+            raise FgnnError(self.lib.fgnn_last_error().decode())
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self.lib.fgnn_trainer_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def launch_count(self):
+        return int(self.lib.fgnn_trainer_launch_count(self._h))
+
+    def _ptr_array(self, tensors):
+        n = 2 * (self.n_layers + 1)
+        assert len(tensors) == n, f"expected {n} tensors (W_0, b_0, ..., W_L, b_L)"
+        for t in tensors:
+            assert t.is_cuda and t.dtype == self._torch.float32 and t.is_contiguous()
+        return (ctypes.c_void_p * n)(*[t.data_ptr() for t in tensors])
+
+    def step(self, z, target, params, exp_avg=None, exp_avg_sq=None, step=1, lr=1e-3, betas=(0.9, 0.999), eps=1e-8,
+             apply=True, want_grads=False):
+        """z (B,K,N,6), target (B,1,2,N) or (B,2,N): CUDA fp32.  Returns (loss tensor (1,), grads tensor or None)."""
+        torch = self._torch
+        z = z.to(self.device, torch.float32).contiguous()
+        target = target.to(self.device, torch.float32).contiguous()
+        B, K, N, Fd = z.shape
+        assert K == self.k and Fd == 6 and target.numel() == B * 2 * N
+        loss = torch.empty(1, dtype=torch.float32, device=self.device)
+        grads = torch.empty(self.n_params, dtype=torch.float32, device=self.device) if want_grads else None
+        pp = self._ptr_array(params)
+        mm = self._ptr_array(exp_avg) if apply else None
+        vv = self._ptr_array(exp_avg_sq) if apply else None
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        self._check(self.lib.fgnn_trainer_step(self._h, B, N, _ptr(z), _ptr(target), pp, mm, vv, int(step), float(lr),
+                                               float(betas[0]), float(betas[1]), float(eps), int(bool(apply)),
+                                               _ptr(loss), _ptr(grads), stream))
+        return loss, grads

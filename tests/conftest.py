@@ -16,8 +16,28 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
-def golden_names():
+def _all_golden():
     return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+
+
+def golden_names():
+    """Rollout fixtures (oracle/gen_golden.py)."""
+    return [n for n in _all_golden() if not n.startswith("train_")]
+
+
+def train_golden_names():
+    """gradient_step fixtures (oracle/gen_golden_train.py)."""
+    return [n for n in _all_golden() if n.startswith("train_")]
+
+
+def load_train_golden(name):
+    g = dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz")))
+    for tag in ("sd0", "sd1", "sdT", "grad1"):
+        g[tag] = {k[len(tag) + 1:]: v for k, v in g.items() if k.startswith(tag + ".")}
+    for key in ("n_agents", "k", "hidden", "n_layers", "batch", "steps", "seed"):
+        g[key] = int(g[key])
+    g["lr"] = float(g["lr"])
+    return g
 
 
 def load_golden(name):
@@ -34,6 +54,11 @@ def load_golden(name):
 @pytest.fixture(params=golden_names())
 def golden(request):
     return load_golden(request.param)
+
+
+@pytest.fixture(params=train_golden_names())
+def train_golden(request):
+    return load_train_golden(request.param)
 
 
 def rel_inf(a, b):
