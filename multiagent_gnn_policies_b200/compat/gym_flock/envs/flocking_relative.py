@@ -121,18 +121,23 @@ class FlockingRelativeEnv:
         return self._engine
 
     # -- episode ----------------------------------------------------------------------------
+    def _draw_configuration(self, x):
+        """One candidate initial configuration into x (N,4), from the global numpy RNG (train.py:27 seeds it)."""
+        n = self.n_agents
+        length = np.sqrt(np.random.uniform(0, self.r_max, size=(n,)))
+        angle = np.pi * np.random.uniform(0, 2, size=(n,))
+        x[:, 0] = length * np.cos(angle)
+        x[:, 1] = length * np.sin(angle)
+        bias = np.random.uniform(low=-self.v_bias, high=self.v_bias, size=(2,))
+        x[:, 2] = np.random.uniform(low=-self.v_max, high=self.v_max, size=(n,)) + bias[0]
+        x[:, 3] = np.random.uniform(low=-self.v_max, high=self.v_max, size=(n,)) + bias[1]
+
     def _sample_initial_state(self):
         n = self.n_agents
         x = np.zeros((n, self.nx_system))
         from scipy.spatial import cKDTree
         for _ in range(100000):
-            length = np.sqrt(np.random.uniform(0, self.r_max, size=(n,)))
-            angle = np.pi * np.random.uniform(0, 2, size=(n,))
-            x[:, 0] = length * np.cos(angle)
-            x[:, 1] = length * np.sin(angle)
-            bias = np.random.uniform(low=-self.v_bias, high=self.v_bias, size=(2,))
-            x[:, 2] = np.random.uniform(low=-self.v_max, high=self.v_max, size=(n,)) + bias[0]
-            x[:, 3] = np.random.uniform(low=-self.v_max, high=self.v_max, size=(n,)) + bias[1]
+            self._draw_configuration(x)
             if n < 2:
                 return x
             tree = cKDTree(x[:, 0:2])
@@ -148,8 +153,16 @@ class FlockingRelativeEnv:
         return EngineState(values, LazyNetwork(eng, self.n_agents, self._step), eng, self._step,
                            self.record_aggregated)
 
+    def _configure_engine(self, engine):
+        """Variant hook, called after every engine reset (leader mask, ...)."""
+        engine.set_agent_mask(None)
+
+    def _before_step(self, engine):
+        """Variant hook, called before every env.step (stochastic time step, ...)."""
+
     def reset(self, x0=None):
         self.x = self._sample_initial_state() if x0 is None else np.array(x0, dtype=np.float64)
+        self._configure_engine(self.engine)
         self.engine.reset(self.x)
         self._step = 0
         return self._observe()
@@ -157,6 +170,7 @@ class FlockingRelativeEnv:
     def step(self, u):
         u = np.asarray(u)
         assert u.shape == (self.n_agents, self.nu)
+        self._before_step(self.engine)
         reward = self.engine.env_step(np.ascontiguousarray(u, dtype=np.float32))
         self._step += 1
         return self._observe(), float(reward[0]), False, {}

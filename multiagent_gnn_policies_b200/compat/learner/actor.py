@@ -73,12 +73,19 @@ class Actor(nn.Module):
         if not needs_grad and self._engine_supported():
             eng = self._dense_engine(delay_state.device)
             return eng.actor_forward_dense(delay_state, delay_gso)
-        # autograd path (training): same arithmetic, torch ops on the GPU
-        x = delay_state.permute(0, 2, 1, 3)                        # (B,F,K,N)
-        for i in range(self.n_layers):
-            if i == self.ind_agg:
-                x = torch.matmul(x.permute(0, 2, 1, 3), delay_gso).permute(0, 2, 1, 3)
-            x = self.conv_layers[i](x)
-            if i < self.n_layers - 1:
-                x = torch.tanh(x)
-        return x.view((batch_size, 1, self.n_a, n_agents))
+        # autograd path (training on dense tensors, ind_agg > 0): same arithmetic, torch ops on the GPU.  TF32 is
+        # switched off for it (cuDNN convolutions default to TF32): the reference computes in fp32 on the CPU.
+        matmul_tf32 = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+        try:
+            with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+                x = delay_state.permute(0, 2, 1, 3)                        # (B,F,K,N)
+                for i in range(self.n_layers):
+                    if i == self.ind_agg:
+                        x = torch.matmul(x.permute(0, 2, 1, 3), delay_gso).permute(0, 2, 1, 3)
+                    x = self.conv_layers[i](x)
+                    if i < self.n_layers - 1:
+                        x = torch.tanh(x)
+                return x.view((batch_size, 1, self.n_a, n_agents))
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = matmul_tf32

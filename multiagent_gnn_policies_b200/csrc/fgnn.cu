@@ -52,6 +52,8 @@ struct fgnn_handle {
     int final_grid_closed = 0, final_grid_open = 0;
     size_t final_smem = 0;
     int adj_stage = 16;              // neighbour ids staged per thread in k_adjacency
+    bool adj_warp_staged = false;    // k_adjacency_t<true>: candidates staged per warp in shared memory
+    bool last_hop_separate = false;  // last hop as its own launch instead of inside the final kernel
     // tensor-core readout (tcgen05, 3xTF32)
     bool use_tc = false;
     std::vector<uint8_t> tc_host;    // TcLayout pack, host mirror
@@ -93,6 +95,14 @@ static int dalloc(fgnn_handle* h, T** ptr, size_t count, bool zero = true) {
     *ptr = reinterpret_cast<T*>(q);
     return 0;
 }
+
+// kernel-variant defaults (each can be overridden per process by the environment variable named in fgnn_create)
+#ifndef FGNN_ADJ_DEFAULT_WS
+#define FGNN_ADJ_DEFAULT_WS false
+#endif
+#ifndef FGNN_LAST_HOP_SEPARATE_DEFAULT
+#define FGNN_LAST_HOP_SEPARATE_DEFAULT false
+#endif
 
 static int pad_hidden(int H) { return H <= 16 ? 16 : H <= 32 ? 32 : H <= 64 ? 64 : 128; }
 
@@ -180,6 +190,16 @@ extern "C" int fgnn_create(const fgnn_config* cfg, fgnn_handle** out) {
     if (cap < 1024) cap = 1024;
     p.nnz_cap = (unsigned)cap;
     h->adj_stage = (int)(cap_per < 8 ? 8 : cap_per > 64 ? 64 : cap_per);
+    {   // warp-staged adjacency: pays when a warp's three row ranges fit its tile (moderate degree); FGNN_ADJ_MODE=0/1 overrides
+        const char* mode = getenv("FGNN_ADJ_MODE");
+        h->adj_warp_staged = mode ? atoi(mode) != 0 : FGNN_ADJ_DEFAULT_WS;
+        const char* lh = getenv("FGNN_LAST_HOP_SEPARATE");
+        h->last_hop_separate = lh ? atoi(lh) != 0 : FGNN_LAST_HOP_SEPARATE_DEFAULT;
+        CK(cudaFuncSetAttribute((const void*)k_adjacency_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)((size_t)WS_STAGE * ADJ_THREADS * sizeof(int) + WS_SMEM)));
+        CK(cudaFuncSetAttribute((const void*)k_adjacency_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)((size_t)64 * ADJ_THREADS * sizeof(int))));
+    }
     p.inv_cell = 1.0 / (cfg->comm_radius * (1.0 + 1.0 / 1048576.0));
     p.R2 = cfg->comm_radius * cfg->comm_radius;
     p.dt = cfg->dt;
@@ -432,23 +452,40 @@ static int enqueue_build(fgnn_handle* h, int advance, cudaStream_t st) {
     if (launch_check(h, "scatter")) return 1;
     k_canon<<<gb, 256, 0, st>>>(p);
     if (launch_check(h, "canon")) return 1;
-    k_adjacency<<<blocks_for(h->launch_pool, ADJ_THREADS), ADJ_THREADS, (size_t)h->adj_stage * ADJ_THREADS * sizeof(int), st>>>(p, h->adj_stage);
+    if (h->adj_warp_staged) {
+        const int stage = h->adj_stage < WS_STAGE ? h->adj_stage : WS_STAGE;
+        k_adjacency_t<true><<<blocks_for(h->launch_pool, ADJ_THREADS), ADJ_THREADS,
+                              (size_t)stage * ADJ_THREADS * sizeof(int) + WS_SMEM, st>>>(p, stage);
+    } else {
+        k_adjacency_t<false><<<blocks_for(h->launch_pool, ADJ_THREADS), ADJ_THREADS,
+                               (size_t)h->adj_stage * ADJ_THREADS * sizeof(int), st>>>(p, h->adj_stage);
+    }
     if (launch_check(h, "adjacency")) return 1;
     h->binned = false;
     if (advance) h->t_host += 1;
     return 0;
 }
 
+template <int NB, bool FIRST>
+static void launch_hop(fgnn_handle* h, int j, cudaStream_t st) {
+    k_hop<NB, FIRST><<<blocks_for(h->launch_pool, 256), 256, 0, st>>>(h->p, j);
+}
+
 static int enqueue_hops(fgnn_handle* h, cudaStream_t st) {
     Params& p = h->p;
-    const int gb = blocks_for(h->launch_pool, 256);
-    for (int j = 0; j + 2 < p.K; ++j) {     // hops 0 .. K-3 ; hop K-2 lives in the final kernel
+    for (int j = 0; j + 2 < p.K; ++j) {     // hops 0 .. K-3 ; hop K-2 lives in the final kernel (or below)
         const int nb = p.K - 1 - j;
-        if (nb == 3) k_hop<3, true><<<gb, 256, 0, st>>>(p, j);              // K = 4, hop 0
-        else if (nb == 2 && j == 0) k_hop<2, true><<<gb, 256, 0, st>>>(p, j);   // K = 3, hop 0
-        else if (nb == 2) k_hop<2, false><<<gb, 256, 0, st>>>(p, j);           // K = 4, hop 1
+        if (nb == 3) launch_hop<3, true>(h, j, st);                   // K = 4, hop 0
+        else if (nb == 2 && j == 0) launch_hop<2, true>(h, j, st);    // K = 3, hop 0
+        else if (nb == 2) launch_hop<2, false>(h, j, st);             // K = 4, hop 1
         else return fail("internal: unexpected hop shape");
         if (launch_check(h, j == 0 ? "hop0" : "hop1")) return 1;
+    }
+    if (h->last_hop_separate && p.K >= 2) {  // tap K-1 through graph t-(K-2), written to zbuf[K-1] for the final kernel
+        const int j = p.K - 2;
+        if (j == 0) launch_hop<1, true>(h, j, st);
+        else launch_hop<1, false>(h, j, st);
+        if (launch_check(h, "hop_last")) return 1;
     }
     return 0;
 }
@@ -456,6 +493,7 @@ static int enqueue_hops(fgnn_handle* h, cudaStream_t st) {
 static int enqueue_final(fgnn_handle* h, bool closed, int write_z, cudaStream_t st, bool fuse_pack = false) {
     Params p = h->p;
     p.write_z_last = write_z;
+    p.last_hop_done = (h->last_hop_separate && p.K >= 2) ? 1 : 0;
     p.fuse = fuse_pack ? h->d_fuse : nullptr;
     if (h->use_tc) {
         final_tc_kernel_t fk = final_tc_kernel(p.K, h->HP, closed);
@@ -832,9 +870,7 @@ extern "C" int fgnn_shard_configure(fgnn_handle* h, const double* bounds, int32_
     h->ctl.world = world; h->ctl.rank = rank;
     h->ctl.depth = depth; h->ctl.margin = margin; h->ctl.dshift = dshift; h->ctl.handover_after = handover_after;
     h->shard_configured = true;
-    void* store = h->shard_graph_store;      // cached graphs bake the control block: drop them
-    if (store) { ShardGraph* g = reinterpret_cast<ShardGraph*>(store); (void)g; }
-    h->shard_epoch += 1;
+    h->shard_epoch += 1;                     // cached graphs bake the control block: they are re-captured
     return 0;
 }
 

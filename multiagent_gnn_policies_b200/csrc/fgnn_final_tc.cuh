@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(FINAL_THREADS) k_final_tc(Params p, const uint
 #pragma unroll
         for (int i = 0; i < K0; ++i) in[i] = 0.f;
         double4 st_own = make_double4(0, 0, 0, 0);         // integrator input, fetched early: its latency hides behind the gather
-        if (CLOSED && valid) st_own = p.state[a];
+        if (CLOSED && valid) st_own = ldg256(&p.state[a]);
         if (valid) {
             {   // z_0 = x_t
                 float v[F];
@@ -195,7 +195,12 @@ __global__ void __launch_bounds__(FINAL_THREADS) k_final_tc(Params p, const uint
 #pragma unroll
                 for (int f = 0; f < F; ++f) in[k * F + f] = v[f];
             }
-            if (K >= 2) {
+            if (K >= 2 && p.last_hop_done) {          // tap K-1 finished by a separate hop launch
+                float v[F];
+                load_row6(p.zbuf + (size_t)(K - 1) * M * ROW, a, v);
+#pragma unroll
+                for (int f = 0; f < F; ++f) in[(K - 1) * F + f] = v[f];
+            } else if (K >= 2) {
                 constexpr int j = K - 2;
                 const int g = slot_of(t - j, K);
                 const float* __restrict__ src = (j == 0) ? p.xhist + (size_t)slot_of(t - (K - 1), K) * M * ROW

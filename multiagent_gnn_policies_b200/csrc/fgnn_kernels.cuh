@@ -11,6 +11,7 @@ namespace fgnn {
 
 constexpr int F = 6;          // features per agent (n_states)
 constexpr int ROW = 8;        // padded feature row: 8 floats = one 32-byte sector
+constexpr int SINV_PAD = 7;   // x_{t-1}[m][7] holds the source scale of graph t, 1/max(deg_t(m),1) (written by k_adjacency at step t)
 constexpr int KMAX = 4;       // filter taps supported
 constexpr int LMAX = 4;       // hidden layers supported
 constexpr int FINAL_THREADS = 128;   // block size of the fused final kernel and the dense Actor kernel
@@ -47,6 +48,7 @@ struct Params {
     int mean_pooling;
     int half_accel;
     int write_z_last;         // final kernel also stores z_{K-1} (debug / fgnn_get_aggregated)
+    int last_hop_done;        // z_{K-1} was already written by a separate hop launch: the final kernel reads it
     unsigned nnz_cap;         // directed-edge capacity per ring slot
     double inv_cell;          // 1 / cell size  (cell size = R * (1 + 2^-20))
     double R2;                // comm_radius^2
@@ -107,9 +109,16 @@ struct WeightLayout {
 // helpers
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ int wrap(long long v, int G) {
-    int r = (int)(v % G);
+    if (v == (long long)(int)v) {                 // 32-bit remainder: ~5x fewer instructions than the emulated 64-bit one
+        const int r = (int)v % G;
+        return r < 0 ? r + G : r;
+    }
+    const int r = (int)(v % G);
     return r < 0 ? r + G : r;
 }
+
+// episode of agent a (B == 1: no division)
+__device__ __forceinline__ int episode_of(const Params& p, int a) { return p.B == 1 ? 0 : a / p.N; }
 
 __device__ __forceinline__ void cell_coords(const Params& p, double px, double py, long long& ix, long long& iy) {
     ix = (long long)floor(px * p.inv_cell);
@@ -140,16 +149,52 @@ __device__ __forceinline__ double r2_exact(double dx, double dy) {
     return __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
 }
 
+// ---- 256-bit global accesses (sm_100: LDG.E.256 / STG.E.256) ----
+// Every per-agent record here is one aligned 32-byte sector (feature row, ELL head, double4 state).  The gathers are
+// bound by the L1TEX wavefront pipe, which charges per instruction AND per line touched: one 256-bit access per
+// record instead of a 128-bit + 64-bit (or two 128-bit) pair halves the wavefronts of every scattered record read.
+// `.nc` variants: data written by an EARLIER kernel only.
+__device__ __forceinline__ void ldg256_nc(const float* p, float (&v)[8]) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "l"(p));
+}
+__device__ __forceinline__ void ldg256_nc(const int* p, int (&v)[8]) {
+    asm volatile("ld.global.nc.v8.s32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "l"(p));
+}
+__device__ __forceinline__ double4 ldg256_nc(const double4* p) {
+    double4 v;
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double4 ldg256(const double4* p) {            // coherent: the kernel also writes this array
+    double4 v;
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void stg256(double4* p, const double4 v) {
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" :: "l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w) : "memory");
+}
+__device__ __forceinline__ void stg256(float* p, float a, float b, float c, float d, float e, float f, float g, float h) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "l"(p), "f"(a), "f"(b), "f"(c), "f"(d), "f"(e), "f"(f), "f"(g), "f"(h) : "memory");
+}
+__device__ __forceinline__ void stg256(int* p, const int (&v)[8]) {
+    asm volatile("st.global.v8.s32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+
 __device__ __forceinline__ void load_row6(const float* __restrict__ base, int idx, float (&v)[F]) {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(base + (size_t)idx * ROW));
-    const float2 b = __ldg(reinterpret_cast<const float2*>(base + (size_t)idx * ROW + 4));
-    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y;
+    float r[8];
+    ldg256_nc(base + (size_t)idx * ROW, r);
+#pragma unroll
+    for (int f = 0; f < F; ++f) v[f] = r[f];
 }
 
 __device__ __forceinline__ void store_row6(float* base, int idx, const float (&v)[F]) {
-    float4* dst = reinterpret_cast<float4*>(base + (size_t)idx * ROW);
-    dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-    dst[1] = make_float4(v[4], v[5], 0.f, 0.f);
+    stg256(base + (size_t)idx * ROW, v[0], v[1], v[2], v[3], v[4], v[5], 0.f, 0.f);
 }
 
 #ifdef FGNN_MAIN_TU
@@ -164,7 +209,7 @@ __global__ void __launch_bounds__(256) k_bin(Params p) {      // owned agents (g
     double4 s = p.state[a];
     long long ix, iy;
     cell_coords(p, s.x, s.y, ix, iy);
-    int c = cell_index(p, a / p.N, ix, iy);
+    int c = cell_index(p, episode_of(p, a), ix, iy);
     p.cell_of[a] = c;
     atomicAdd(&p.cell_count[c], 1);
 }
@@ -229,11 +274,12 @@ __global__ void __launch_bounds__(256) k_finalize_reward(Params p) { finalize_re
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 16;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
-constexpr unsigned FLAG_AGG = 1u << 30, FLAG_INC = 2u << 30, VAL_MASK = (1u << 30) - 1;
+constexpr unsigned FLAG_AGG = 1u << 30, VAL_MASK = (1u << 30) - 1;
 
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan(Params p, int advance) {
     __shared__ int s_tile;
     __shared__ int s_warp[SCAN_THREADS / 32];
+    __shared__ int s_part[SCAN_THREADS / 32];
     __shared__ int s_excl;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_tile = atomicAdd(p.tile_counter, 1);
@@ -278,36 +324,34 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(Params p, int advance) {
         }
         if (lane < SCAN_THREADS / 32) s_warp[lane] = winc - w;      // exclusive per-warp offsets
         const int total = __shfl_sync(0xffffffffu, winc, SCAN_THREADS / 32 - 1);
-        // publish the tile aggregate, then look back over predecessor tiles 32 at a time
-        volatile unsigned* status = p.tile_status;
-        int excl = 0;
-        if (tile == 0) {
-            if (lane == 0) status[0] = FLAG_INC | (unsigned)total;
-        } else {
-            if (lane == 0) status[tile] = FLAG_AGG | (unsigned)total;
-            __threadfence();
-            int look = tile - 1;
-            while (true) {
-                int idx = look - lane;
-                unsigned w32 = FLAG_INC;        // out-of-range lanes act as a zero inclusive prefix
-                if (idx >= 0) {
-                    do { w32 = status[idx]; } while ((w32 >> 30) == 0);
-                }
-                unsigned inc_mask = __ballot_sync(0xffffffffu, (w32 >> 30) == 2u);
-                int first_inc = inc_mask ? __ffs(inc_mask) - 1 : 32;     // nearest tile with an inclusive prefix
-                int contrib = (lane <= first_inc) ? (int)(w32 & VAL_MASK) : 0;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
-                excl += contrib;
-                if (inc_mask) break;
-                look -= 32;
-            }
-            if (lane == 0) {
-                __threadfence();
-                status[tile] = FLAG_INC | (unsigned)(excl + total);
-            }
+        // publish this tile's aggregate right away: nobody waits for a prefix
+        if (lane == 0) {
+            volatile unsigned* status = p.tile_status;
+            status[tile] = FLAG_AGG | (unsigned)total;
         }
-        if (lane == 0) s_excl = excl;
+    }
+    // Look-back without a dependency chain: the tile count is small (C / 4096), so every thread fetches the
+    // aggregates of a few predecessor tiles directly -- ONE round trip to L2 for the whole prefix instead of
+    // one per 32 tiles (ncu: the chained form spent its time in `barrier`, 23 us for 1M cells).  Tile ids
+    // are handed out by an atomic counter, so every predecessor is already running and will publish.
+    {
+        volatile unsigned* status = p.tile_status;
+        int part = 0;
+        for (int idx = tid; idx < tile; idx += SCAN_THREADS) {
+            unsigned w32;
+            do { w32 = status[idx]; } while ((w32 >> 30) == 0);
+            part += (int)(w32 & VAL_MASK);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if (lane == 0) s_part[warp] = part;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int excl = 0;
+#pragma unroll
+        for (int w = 0; w < SCAN_THREADS / 32; ++w) excl += s_part[w];
+        s_excl = excl;
     }
     __syncthreads();
     int run = s_excl + s_warp[warp] + (inc - sum);
@@ -347,7 +391,7 @@ __global__ void __launch_bounds__(256) k_canon(Params p) {
     for (int q = q0; q < q1; ++q) rank += (p.tmp_id[q] < a) ? 1 : 0;
     int dst = q0 + rank;
     p.sorted_id[dst] = a;
-    p.sorted_state[dst] = p.state[a];
+    stg256(&p.sorted_state[dst], ldg256_nc(&p.state[a]));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -362,12 +406,36 @@ __global__ void __launch_bounds__(256) k_canon(Params p) {
 //      re-scan their tail.
 // ------------------------------------------------------------------------------------------
 constexpr int ADJ_THREADS = 128;
+constexpr int WS_CAP = 64;            // warp-staged variant: candidate slots per grid row and warp
+constexpr int WS_STAGE = 16;          // ... and neighbour ids staged per thread (longer rows re-scan shared memory)
+constexpr size_t WS_SMEM = (size_t)(ADJ_THREADS / 32) * 3 * WS_CAP * (sizeof(double4) + sizeof(int));
 
-__global__ void __launch_bounds__(ADJ_THREADS) k_adjacency(Params p, int stage_cap) {
-    extern __shared__ int s_stage[];                      // [stage_cap][ADJ_THREADS] slots of accepted neighbours
+// One accepted pair: feature sums in float64 (numpy's evaluation order per term)
+#define FGNN_ADJ_ACCEPT(o, dx, dy, r2)                                                                \
+    {                                                                                                 \
+        const double inv = 1.0 / (r2);                                                                \
+        const double inv2 = inv * inv;                                                                \
+        f0 += me.z - (o).z;                                                                           \
+        f1 += (dx) * inv2;                                                                            \
+        f2 += (dx) * inv;                                                                             \
+        f3 += me.w - (o).w;                                                                           \
+        f4 += (dy) * inv2;                                                                            \
+        f5 += (dy) * inv;                                                                             \
+    }
+
+// WS = true: the 32 agents of a warp are consecutive in cell order, so (when the warp sits inside one grid row)
+// the candidates of all its lanes are three contiguous slot ranges.  The warp copies them ONCE into shared memory
+// with coalesced loads and every lane scans its own sub-range there: the per-lane dependent global loads (ncu:
+// long_scoreboard 36 %, L1 wavefronts 38 % of peak) become shared-memory reads.  Warps that straddle a row, touch
+// the grid seam or overflow the tile take the per-lane global path.  Neighbour order is identical in both paths.
+template <bool WS>
+__global__ void __launch_bounds__(ADJ_THREADS) k_adjacency_t(Params p, int stage_cap) {
+    extern __shared__ __align__(16) unsigned char s_adj_raw[];
+    int* s_stage = reinterpret_cast<int*>(s_adj_raw);     // [stage_cap][ADJ_THREADS] accepted neighbour ids
     const int tid = threadIdx.x;
     const int s = blockIdx.x * ADJ_THREADS + tid;
     const int lane = tid & 31;
+    const int warp = tid >> 5;
     // housekeeping for the next scan
     for (int i = s; i < p.n_tiles; i += gridDim.x * ADJ_THREADS) p.tile_status[i] = 0;
     if (s == 0) *p.tile_counter = 0;
@@ -378,22 +446,25 @@ __global__ void __launch_bounds__(ADJ_THREADS) k_adjacency(Params p, int stage_c
     int a = 0;
     double4 me = make_double4(0, 0, 0, 0);
     int q0[9], q1[9];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) q0[j] = q1[j] = 0;
     int count = 0;
     double f0 = 0, f1 = 0, f2 = 0, f3 = 0, f4 = 0, f5 = 0;
+    int ep = 0, cxw = 0, wy = 0;
     if (valid) {
         a = p.sorted_id[s];
-        me = p.sorted_state[s];
-        const int ep = a / p.N;
+        me = ldg256_nc(&p.sorted_state[s]);
+        ep = episode_of(p, a);
         long long ix, iy;
         cell_coords(p, me.x, me.y, ix, iy);
-        const int cxw = wrap(ix, p.G);
+        cxw = wrap(ix, p.G);
+        wy = wrap(iy, p.Gy);
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
             const int rowbase = (ep * p.Gy + wrap(iy + r - 1, p.Gy)) * p.G;
             if (cxw >= 1 && cxw <= p.G - 2) {            // the row's three cells are contiguous slots
                 q0[3 * r] = __ldg(&p.cell_start[rowbase + cxw - 1]);
                 q1[3 * r] = __ldg(&p.cell_start[rowbase + cxw + 2]);
-                q0[3 * r + 1] = q1[3 * r + 1] = q0[3 * r + 2] = q1[3 * r + 2] = 0;
             } else {
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
@@ -403,23 +474,80 @@ __global__ void __launch_bounds__(ADJ_THREADS) k_adjacency(Params p, int stage_c
                 }
             }
         }
+    }
+    // ---- warp-staged fast path? (warp-uniform decision) ----
+    bool fast = false;
+    int lo[3] = {0, 0, 0};
+    double4* w_cand = nullptr;
+    int* w_cid = nullptr;
+    if (WS) {
+        unsigned char* base = s_adj_raw + (size_t)stage_cap * ADJ_THREADS * sizeof(int);
+        w_cand = reinterpret_cast<double4*>(base) + warp * 3 * WS_CAP;
+        w_cid = reinterpret_cast<int*>(base + (size_t)(ADJ_THREADS / 32) * 3 * WS_CAP * sizeof(double4)) + warp * 3 * WS_CAP;
+        const unsigned vm = __ballot_sync(0xffffffffu, valid);
+        if (vm) {
+            const int src = __ffs(vm) - 1;
+            const int ep0 = __shfl_sync(0xffffffffu, ep, src);
+            const int wy0 = __shfl_sync(0xffffffffu, wy, src);
+            const bool ok = !valid || (ep == ep0 && wy == wy0 && cxw >= 1 && cxw <= p.G - 2);
+            fast = __all_sync(0xffffffffu, ok);
+            if (fast) {
+                int n[3];
 #pragma unroll
-        for (int j = 0; j < 9; ++j) {
-            for (int q = q0[j]; q < q1[j]; ++q) {
-                const double4 o = p.sorted_state[q];
-                const double dx = me.x - o.x, dy = me.y - o.y;
-                const double r2 = r2_exact(dx, dy);
-                if (q != s && r2 < p.R2) {
-                    const double inv = 1.0 / r2;
-                    const double inv2 = inv * inv;
-                    f0 += me.z - o.z;
-                    f1 += dx * inv2;
-                    f2 += dx * inv;
-                    f3 += me.w - o.w;
-                    f4 += dy * inv2;
-                    f5 += dy * inv;
-                    if (count < stage_cap) s_stage[count * ADJ_THREADS + tid] = __ldg(&p.sorted_id[q]);
-                    ++count;
+                for (int r = 0; r < 3; ++r) {
+                    int l = valid ? q0[3 * r] : 0x7fffffff;
+                    int h = valid ? q1[3 * r] : -1;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        l = min(l, __shfl_xor_sync(0xffffffffu, l, o));
+                        h = max(h, __shfl_xor_sync(0xffffffffu, h, o));
+                    }
+                    lo[r] = l;
+                    n[r] = h - l;
+                }
+                fast = n[0] <= WS_CAP && n[1] <= WS_CAP && n[2] <= WS_CAP;
+                if (fast) {
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) {
+                        for (int i = lane; i < n[r]; i += 32) {
+                            w_cand[r * WS_CAP + i] = ldg256_nc(&p.sorted_state[lo[r] + i]);
+                            w_cid[r * WS_CAP + i] = __ldg(&p.sorted_id[lo[r] + i]);
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (valid) {
+        if (WS && fast) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const double4* cand = w_cand + r * WS_CAP - lo[r];
+                const int* cid = w_cid + r * WS_CAP - lo[r];
+                for (int q = q0[3 * r]; q < q1[3 * r]; ++q) {
+                    const double4 o = cand[q];
+                    const double dx = me.x - o.x, dy = me.y - o.y;
+                    const double r2 = r2_exact(dx, dy);
+                    if (q != s && r2 < p.R2) {
+                        FGNN_ADJ_ACCEPT(o, dx, dy, r2)
+                        if (count < stage_cap) s_stage[count * ADJ_THREADS + tid] = cid[q];
+                        ++count;
+                    }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 9; ++j) {
+                for (int q = q0[j]; q < q1[j]; ++q) {
+                    const double4 o = ldg256_nc(&p.sorted_state[q]);
+                    const double dx = me.x - o.x, dy = me.y - o.y;
+                    const double r2 = r2_exact(dx, dy);
+                    if (q != s && r2 < p.R2) {
+                        FGNN_ADJ_ACCEPT(o, dx, dy, r2)
+                        if (count < stage_cap) s_stage[count * ADJ_THREADS + tid] = __ldg(&p.sorted_id[q]);
+                        ++count;
+                    }
                 }
             }
         }
@@ -456,29 +584,46 @@ __global__ void __launch_bounds__(ADJ_THREADS) k_adjacency(Params p, int stage_c
     }
     if (count > stage_cap) {                              // long row: re-scan for the ids beyond the stage (same order)
         int w = 0;
+        if (WS && fast) {
 #pragma unroll
-        for (int j = 0; j < 9; ++j) {
-            for (int q = q0[j]; q < q1[j]; ++q) {
-                const double2 o = *reinterpret_cast<const double2*>(&p.sorted_state[q]);
-                const double r2 = r2_exact(me.x - o.x, me.y - o.y);
-                if (q != s && r2 < p.R2) {
-                    if (w >= stage_cap) cols[w] = __ldg(&p.sorted_id[q]);
-                    ++w;
+            for (int r = 0; r < 3; ++r) {
+                const double4* cand = w_cand + r * WS_CAP - lo[r];
+                const int* cid = w_cid + r * WS_CAP - lo[r];
+                for (int q = q0[3 * r]; q < q1[3 * r]; ++q) {
+                    const double4 o = cand[q];
+                    const double r2 = r2_exact(me.x - o.x, me.y - o.y);
+                    if (q != s && r2 < p.R2) {
+                        if (w >= stage_cap) cols[w] = cid[q];
+                        ++w;
+                    }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 9; ++j) {
+                for (int q = q0[j]; q < q1[j]; ++q) {
+                    const double2 o = *reinterpret_cast<const double2*>(&p.sorted_state[q]);
+                    const double r2 = r2_exact(me.x - o.x, me.y - o.y);
+                    if (q != s && r2 < p.R2) {
+                        if (w >= stage_cap) cols[w] = __ldg(&p.sorted_id[q]);
+                        ++w;
+                    }
                 }
             }
         }
     }
     const size_t ga = (size_t)g * p.M + a;
-    int4* ellp = reinterpret_cast<int4*>(p.ell + ga * ELLW);
-    ellp[0] = make_int4(head[0], head[1], head[2], head[3]);
-    ellp[1] = make_int4(head[4], head[5], head[6], head[7]);
-    float* xr = p.xhist + ga * ROW;
-    reinterpret_cast<float4*>(xr)[0] = make_float4((float)f0, (float)f1, (float)f2, (float)f3);
-    reinterpret_cast<float4*>(xr)[1] = make_float4((float)f4, (float)f5, 0.f, 0.f);
+    static_assert(ELLW == 8 && ROW == 8, "one 32-byte record per agent");
+    stg256(p.ell + ga * ELLW, head);
+    stg256(p.xhist + ga * ROW, (float)f0, (float)f1, (float)f2, (float)f3, (float)f4, (float)f5, 0.f, 0.f);
     p.deg[ga] = count;
     p.row_start[ga] = row;
-    p.sinv[ga] = p.mean_pooling ? (float)(1.0 / (double)(count > 0 ? count : 1)) : 1.0f;
+    const float sv = p.mean_pooling ? (float)(1.0 / (double)(count > 0 ? count : 1)) : 1.0f;
+    p.sinv[ga] = sv;
+    // the first hop through graph t gathers x_{t-1}[m] * sinv_t[m]: keep the scale in the pad of that very row
+    if (p.K > 1) p.xhist[((size_t)slot_of(t - 1, p.K) * p.M + a) * ROW + SINV_PAD] = sv;
 }
+#undef FGNN_ADJ_ACCEPT
 
 #endif  // FGNN_MAIN_TU
 
@@ -494,36 +639,34 @@ __device__ __forceinline__ void gather_rows(const Params& p, int g, int a, const
     const size_t M = p.M;
     const int d = __ldg(&p.deg[(size_t)g * M + a]);
     const unsigned rs = __ldg(&p.row_start[(size_t)g * M + a]);
-    const int4* ellp = reinterpret_cast<const int4*>(p.ell + ((size_t)g * M + a) * ELLW);
-    const int4 c0 = __ldg(ellp), c1 = __ldg(ellp + 1);
-    const float* __restrict__ sinv = p.sinv + (size_t)g * M;
-    const int head[ELLW] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+    int head[ELLW];
+    ldg256_nc(p.ell + ((size_t)g * M + a) * ELLW, head);
 #pragma unroll
     for (int b = 0; b < NB; ++b)
 #pragma unroll
         for (int f = 0; f < F; ++f) acc[b][f] = 0.f;
+    // Un-prescaled sources (first hop): src[0] is x_{t-1}, whose pad slot carries the scale of graph t = g.
 #pragma unroll
     for (int e0 = 0; e0 < ELLW; e0 += HOP_UNROLL) {
         if (e0 < d) {
-            float sc[HOP_UNROLL];
-            float v[HOP_UNROLL][NB][F];
+            float v[HOP_UNROLL][NB][ROW];
 #pragma unroll
             for (int u = 0; u < HOP_UNROLL; ++u) {
                 const int m = head[e0 + u];
                 if (m >= 0) {
-                    sc[u] = PRESCALED ? 1.f : __ldg(&sinv[m]);
 #pragma unroll
-                    for (int b = 0; b < NB; ++b) load_row6(src[b], m, v[u][b]);
+                    for (int b = 0; b < NB; ++b) ldg256_nc(src[b] + (size_t)m * ROW, v[u][b]);
                 }
             }
 #pragma unroll
             for (int u = 0; u < HOP_UNROLL; ++u) {
                 if (head[e0 + u] >= 0) {
+                    const float sc = v[u][0][SINV_PAD];
 #pragma unroll
                     for (int b = 0; b < NB; ++b)
 #pragma unroll
                         for (int f = 0; f < F; ++f)
-                            acc[b][f] = PRESCALED ? acc[b][f] + v[u][b][f] : fmaf(v[u][b][f], sc[u], acc[b][f]);
+                            acc[b][f] = PRESCALED ? acc[b][f] + v[u][b][f] : fmaf(v[u][b][f], sc, acc[b][f]);
                 }
             }
         }
@@ -532,26 +675,25 @@ __device__ __forceinline__ void gather_rows(const Params& p, int g, int a, const
         const int* __restrict__ cols = p.cols + (size_t)g * p.nnz_cap + rs;
         for (int e = ELLW; e < d; e += HOP_UNROLL) {
             int m[HOP_UNROLL];
-            float sc[HOP_UNROLL];
-            float v[HOP_UNROLL][NB][F];
+            float v[HOP_UNROLL][NB][ROW];
 #pragma unroll
             for (int u = 0; u < HOP_UNROLL; ++u) m[u] = (e + u < d) ? __ldg(&cols[e + u]) : -1;
 #pragma unroll
             for (int u = 0; u < HOP_UNROLL; ++u) {
                 if (m[u] >= 0) {
-                    sc[u] = PRESCALED ? 1.f : __ldg(&sinv[m[u]]);
 #pragma unroll
-                    for (int b = 0; b < NB; ++b) load_row6(src[b], m[u], v[u][b]);
+                    for (int b = 0; b < NB; ++b) ldg256_nc(src[b] + (size_t)m[u] * ROW, v[u][b]);
                 }
             }
 #pragma unroll
             for (int u = 0; u < HOP_UNROLL; ++u) {
                 if (m[u] >= 0) {
+                    const float sc = v[u][0][SINV_PAD];
 #pragma unroll
                     for (int b = 0; b < NB; ++b)
 #pragma unroll
                         for (int f = 0; f < F; ++f)
-                            acc[b][f] = PRESCALED ? acc[b][f] + v[u][b][f] : fmaf(v[u][b][f], sc[u], acc[b][f]);
+                            acc[b][f] = PRESCALED ? acc[b][f] + v[u][b][f] : fmaf(v[u][b][f], sc, acc[b][f]);
                 }
             }
         }
@@ -714,10 +856,10 @@ __device__ __forceinline__ double4 integrate_and_bin(const Params& p, int a, con
     }
     const double nvx = __dadd_rn(s.z, __dmul_rn(ax, p.dt));
     const double nvy = __dadd_rn(s.w, __dmul_rn(ay, p.dt));
-    p.state[a] = make_double4(nx, ny, nvx, nvy);
+    stg256(&p.state[a], make_double4(nx, ny, nvx, nvy));
     long long ix, iy;
     cell_coords(p, nx, ny, ix, iy);
-    const int ep = a / p.N;
+    const int ep = episode_of(p, a);
     const int c = cell_index(p, ep, ix, iy);
     p.cell_of[a] = c;
     atomicAdd(&p.cell_count[c], 1);
@@ -783,7 +925,7 @@ __global__ void __launch_bounds__(256) k_integrate(Params p, const float* __rest
         const int a = owned_agent(p, i);
         if (a >= 0) {
             const float2 uu = reinterpret_cast<const float2*>(u)[i];      // u is in owned-list order
-            integrate_and_bin(p, a, p.state[a], uu.x, uu.y, racc);
+            integrate_and_bin(p, a, ldg256(&p.state[a]), uu.x, uu.y, racc);
         }
     }
     reward_block_flush<256>(p, racc);

@@ -49,10 +49,13 @@ def compute_helpers(x, comm_radius2, mean_pooling=True):
     return state_values, state_network, adj, deg.astype(np.int64)
 
 
-def integrate(x, u, dt, action_scalar=10.0, half_accel_term=True):
-    """Double integrator (Appendix B ``step``): a = u*gain; p += v dt (+ a dt^2/2); v += a dt."""
+def integrate(x, u, dt, action_scalar=10.0, half_accel_term=True, mask=None):
+    """Double integrator (Appendix B ``step``): a = u*gain; p += v dt (+ a dt^2/2); v += a dt.
+    ``mask`` (N,) of 0/1: FlockingLeader's ``u * mask`` -- agents with mask 0 ignore their action."""
     x = x.copy()
     a = np.asarray(u, dtype=np.float64) * action_scalar
+    if mask is not None:
+        a = a * np.asarray(mask, dtype=np.float64).reshape(-1, 1)
     if half_accel_term:
         x[:, 0] = x[:, 0] + x[:, 2] * dt + a[:, 0] * dt * dt * 0.5
         x[:, 1] = x[:, 1] + x[:, 3] * dt + a[:, 1] * dt * dt * 0.5
@@ -164,6 +167,94 @@ class FlockingRelativeOracle:
             centralized = True
         return controller(self.x, self.comm_radius, self.comm_radius2, centralized,
                           self.max_accel, self.action_scalar)
+
+
+class FlockingLeaderOracle(FlockingRelativeOracle):
+    """FlockingLeader-v0 (cfg/dagger_leader.cfg:24, cfg/vel_leader_baseline.cfg) [UNVERIFIED-MEMORY of gym_flock]:
+    the first ``n_leaders`` agents share one constant velocity and ignore every action (``u * mask``).
+    The observation returned by reset() is recomputed after the leaders' velocities are set."""
+
+    def __init__(self, n_leaders=2, **kw):
+        super().__init__(**kw)
+        self.n_leaders = n_leaders
+        self.mask = np.ones((self.n_agents,))
+        self.mask[0:n_leaders] = 0
+
+    def params_from_cfg(self, args):
+        super().params_from_cfg(args)
+        self.mask = np.ones((self.n_agents,))
+        self.mask[0:self.n_leaders] = 0
+
+    def reset(self, x0=None):
+        super().reset(x0)
+        if x0 is None:
+            self.x[0:self.n_leaders, 2:4] = np.ones((self.n_leaders, 2)) * self.rng.uniform(
+                low=-self.v_max, high=self.v_max, size=(1, 1))
+        return self.helpers()
+
+    def step(self, u):
+        u = np.asarray(u)
+        assert u.shape == (self.n_agents, NU)
+        self.x = integrate(self.x, u, self.dt, self.action_scalar, self.half_accel_term, mask=self.mask)
+        return self.helpers(), instant_cost(self.x), False, {}
+
+
+class FlockingTwoFlocksOracle(FlockingRelativeOracle):
+    """FlockingTwoFlocks-v0 (cfg/dagger_twoflocks.cfg:24, cfg/n_twoflocks.cfg) [UNVERIFIED-MEMORY of gym_flock]:
+    same dynamics; reset() draws two half-flocks -- discs of half the area each, so the density equals the single
+    flock's -- whose centres are ``flock_offset`` apart along x (default: tangent discs), with opposite velocity
+    biases so that they fly through each other."""
+
+    def __init__(self, flock_offset=None, **kw):
+        super().__init__(**kw)
+        self.flock_offset = flock_offset
+
+    def sample_initial_state(self, max_tries=100000):
+        n = self.n_agents
+        half = n // 2
+        x = np.zeros((n, NX))
+        offset = 2.0 * np.sqrt(0.5 * self.r_max) if self.flock_offset is None else self.flock_offset
+        for _ in range(max_tries):
+            length = np.sqrt(self.rng.uniform(0, 0.5 * self.r_max, size=(n,)))
+            angle = np.pi * self.rng.uniform(0, 2, size=(n,))
+            x[:, 0] = length * np.cos(angle)
+            x[:, 1] = length * np.sin(angle)
+            x[:half, 0] -= 0.5 * offset
+            x[half:, 0] += 0.5 * offset
+            bias = self.rng.uniform(low=-self.v_bias, high=self.v_bias, size=(2,))
+            sign = np.where(np.arange(n) < half, 1.0, -1.0)
+            x[:, 2] = self.rng.uniform(low=-self.v_max, high=self.v_max, size=(n,)) + sign * bias[0]
+            x[:, 3] = self.rng.uniform(low=-self.v_max, high=self.v_max, size=(n,)) + sign * bias[1]
+            _, r2 = pair_terms(x)
+            min_dist = np.sqrt(np.min(r2))
+            degree = np.min(np.sum((r2 < self.comm_radius2).astype(int), axis=1))
+            if degree >= self.min_degree and min_dist >= self.min_dist_thresh:
+                return x
+        raise RuntimeError("no admissible initial configuration found")
+
+
+class FlockingStochasticOracle(FlockingRelativeOracle):
+    """FlockingStochastic-v0 (cfg/dagger_stoch.cfg:24, cfg/rad_stoch.cfg, cfg/transfer_stoch.cfg -- none of which
+    carries a ``dt`` key) [UNVERIFIED-MEMORY of gym_flock]: the time step of every env.step is random,
+    dt ~ max(N(dt_mean, dt_sigma), dt_min), imitating a simulator with an irregular clock."""
+
+    def __init__(self, dt_mean=0.1, dt_sigma=0.02, dt_min=1e-3, **kw):
+        kw.setdefault("dt", dt_mean)
+        super().__init__(**kw)
+        self.dt_mean, self.dt_sigma, self.dt_min = dt_mean, dt_sigma, dt_min
+
+    def params_from_cfg(self, args):
+        dt = self.dt
+        super().params_from_cfg(args)
+        if self.dt is None:
+            self.dt = dt
+
+    def draw_dt(self):
+        return float(max(self.rng.normal(self.dt_mean, self.dt_sigma), self.dt_min))
+
+    def step(self, u):
+        self.dt = self.draw_dt()
+        return super().step(u)
 
 
 def synthetic_state(n_agents, seed=11, density=1.6, v_max=3.0, sort_cells=True, cell=1.0, min_dist=0.1,

@@ -92,6 +92,8 @@ def test_gradients_match_torch_autograd_at_scale(batch, n, k, hidden, layers):
     autograd evaluation of the same readout on the GPU is the reference here."""
     import torch
     from multiagent_gnn_policies_b200.engine import ActorTrainer
+    torch.backends.cudnn.allow_tf32 = False            # the torch side must really be fp32 (conv defaults to TF32)
+    torch.backends.cuda.matmul.allow_tf32 = False
     dev = torch.device("cuda:0")
     gen = torch.Generator(device="cpu").manual_seed(5)
     dims = [6 * k] + [hidden] * layers + [2]
@@ -102,7 +104,7 @@ def test_gradients_match_torch_autograd_at_scale(batch, n, k, hidden, layers):
         params.append((0.1 * torch.randn(dims[i + 1], generator=gen)).to(dev).requires_grad_(True))
     z = torch.randn((batch, k, n, 6), generator=gen).to(dev)
     y = torch.randn((batch, 1, 2, n), generator=gen).to(dev)
-    x = z.permute(0, 3, 2, 1)                                    # (B,F,K,N): actor.py:65
+    x = z.permute(0, 3, 1, 2)                                    # (B,K,N,6) -> (B,F,K,N): actor.py:65
     for i in range(layers + 1):
         x = torch.nn.functional.conv2d(x, params[2 * i], params[2 * i + 1], stride=(k if i == 0 else 1, 1))
         if i < layers:

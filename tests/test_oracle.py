@@ -103,3 +103,44 @@ def test_controller_shapes_and_clip():
     for c in (True, False, None):
         u = env.controller(c)
         assert u.shape == (30, 2) and np.all(np.abs(u) <= 1.0 + 1e-12)
+
+
+# ---- environment variants (parity unpinned like the base env) ----------------------
+
+def test_leader_variant_masks_the_action():
+    rng = np.random.RandomState(4)
+    env = flock_env.FlockingLeaderOracle(n_agents=40, rng=rng)
+    env.reset()
+    v_lead = env.x[0:2, 2:4].copy()
+    assert np.all(v_lead == v_lead[0, 0])                      # one shared scalar velocity
+    x0 = env.x.copy()
+    u = rng.uniform(-1, 1, size=(40, 2))
+    env.step(u)
+    np.testing.assert_array_equal(env.x[0:2, 2:4], v_lead)     # leaders keep their velocity exactly
+    np.testing.assert_array_equal(env.x[0:2, 0:2], x0[0:2, 0:2] + v_lead * env.dt)
+    free = flock_env.integrate(x0, u, env.dt)
+    np.testing.assert_array_equal(env.x[2:], free[2:])         # followers: the plain double integrator
+
+
+def test_two_flocks_variant_initial_state():
+    env = flock_env.FlockingTwoFlocksOracle(n_agents=100, rng=np.random.RandomState(2))
+    env.reset()
+    half = 50
+    assert env.x[:half, 0].mean() < 0 < env.x[half:, 0].mean()
+    d = env.x[:half, 2:4].mean(axis=0) + env.x[half:, 2:4].mean(axis=0)     # opposite biases cancel
+    assert np.abs(d).max() < 4 * env.v_max / np.sqrt(half)
+    sv, sn = env.helpers()
+    assert (np.asarray(sn) != 0).sum(axis=1).min() >= 2
+
+
+def test_stochastic_variant_draws_dt_per_step():
+    env = flock_env.FlockingStochasticOracle(n_agents=30, v_max=0.5, comm_radius=1.5, rng=np.random.RandomState(3))
+    env.reset()
+    dts = []
+    for _ in range(5):
+        x0 = env.x.copy()
+        u = env.controller(False)
+        env.step(u)
+        dts.append(env.dt)
+        np.testing.assert_array_equal(env.x, flock_env.integrate(x0, u, env.dt))
+    assert len(set(dts)) == 5 and min(dts) >= env.dt_min
