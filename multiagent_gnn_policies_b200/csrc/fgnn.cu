@@ -98,10 +98,10 @@ static int dalloc(fgnn_handle* h, T** ptr, size_t count, bool zero = true) {
 
 // kernel-variant defaults (each can be overridden per process by the environment variable named in fgnn_create)
 #ifndef FGNN_ADJ_DEFAULT_WS
-#define FGNN_ADJ_DEFAULT_WS false
+#define FGNN_ADJ_DEFAULT_WS true                 // measured: 120 -> 112 us at N=1M, d~5 (profiles/r1_bench_history.md)
 #endif
 #ifndef FGNN_LAST_HOP_SEPARATE_DEFAULT
-#define FGNN_LAST_HOP_SEPARATE_DEFAULT false
+#define FGNN_LAST_HOP_SEPARATE_DEFAULT true      // measured: 312 -> 307 us/step (high-occupancy gather + streaming readout)
 #endif
 
 static int pad_hidden(int H) { return H <= 16 ? 16 : H <= 32 ? 32 : H <= 64 ? 64 : 128; }

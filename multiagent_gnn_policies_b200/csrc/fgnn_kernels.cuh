@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(256) k_finalize_reward(Params p) { finalize_re
 
 // ------------------------------------------------------------------------------------------
 // K_B  scan: exclusive prefix sum of cell_count[0..C] -> cell_start[0..C] (single pass,
-//      decoupled look-back), zeroes cell_count; tile 0 also advances t and finalises the reward.
+//      direct look-back), zeroes cell_count; tile 0 also advances t.  (The reward is finalised by k_scatter.)
 // ------------------------------------------------------------------------------------------
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 16;
@@ -279,7 +279,6 @@ constexpr unsigned FLAG_AGG = 1u << 30, VAL_MASK = (1u << 30) - 1;
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan(Params p, int advance) {
     __shared__ int s_tile;
     __shared__ int s_warp[SCAN_THREADS / 32];
-    __shared__ int s_part[SCAN_THREADS / 32];
     __shared__ int s_excl;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_tile = atomicAdd(p.tile_counter, 1);
@@ -330,28 +329,21 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(Params p, int advance) {
             status[tile] = FLAG_AGG | (unsigned)total;
         }
     }
-    // Look-back without a dependency chain: the tile count is small (C / 4096), so every thread fetches the
-    // aggregates of a few predecessor tiles directly -- ONE round trip to L2 for the whole prefix instead of
-    // one per 32 tiles (ncu: the chained form spent its time in `barrier`, 23 us for 1M cells).  Tile ids
-    // are handed out by an atomic counter, so every predecessor is already running and will publish.
-    {
+    // Look-back without a dependency chain: the tile count is small (C / 4096), so warp 0 fetches the aggregates of
+    // ALL predecessor tiles directly -- one round trip to L2 for the whole prefix instead of one per 32 tiles.  Tile
+    // ids are handed out by an atomic counter, so every predecessor is already running and will publish.  Only one
+    // warp per tile polls (with a back-off): 62 k threads spinning on the status words slowed the publishers down.
+    if (warp == 0) {
         volatile unsigned* status = p.tile_status;
         int part = 0;
-        for (int idx = tid; idx < tile; idx += SCAN_THREADS) {
+        for (int idx = lane; idx < tile; idx += 32) {
             unsigned w32;
-            do { w32 = status[idx]; } while ((w32 >> 30) == 0);
+            while (((w32 = status[idx]) >> 30) == 0) __nanosleep(40);
             part += (int)(w32 & VAL_MASK);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-        if (lane == 0) s_part[warp] = part;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        int excl = 0;
-#pragma unroll
-        for (int w = 0; w < SCAN_THREADS / 32; ++w) excl += s_part[w];
-        s_excl = excl;
+        if (lane == 0) s_excl = part;
     }
     __syncthreads();
     int run = s_excl + s_warp[warp] + (inc - sum);
@@ -361,8 +353,6 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(Params p, int advance) {
         if (idx < n) p.cell_start[idx] = run;
         run += v[i];
     }
-    // off the critical path: every other tile's look-back waits for tile 0's prefix, published above
-    if (tile == 0) finalize_reward(p);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -370,12 +360,15 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(Params p, int advance) {
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_scatter(Params p) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= pool_size(p)) return;
-    const int a = pool_agent(p, i);
-    if (a < 0) return;
-    int c = p.cell_of[a];
-    int slot = p.cell_start[c] + atomicAdd(&p.cell_count[c], 1);
-    p.tmp_id[slot] = a;
+    const int a = i < pool_size(p) ? pool_agent(p, i) : -1;
+    if (a >= 0) {
+        int c = p.cell_of[a];
+        int slot = p.cell_start[c] + atomicAdd(&p.cell_count[c], 1);
+        p.tmp_id[slot] = a;
+    }
+    // Reward of the step just integrated: a chain of dependent global loads (~5 us) that used to sit on the scan
+    // kernel's critical path; here it hides behind the other blocks' scatter traffic.
+    if (blockIdx.x == 0) finalize_reward(p);
 }
 
 // K_C2 canon: order every cell's list by agent id (rank by counting), copy the state next to it.
@@ -410,10 +403,21 @@ constexpr int WS_CAP = 64;            // warp-staged variant: candidate slots pe
 constexpr int WS_STAGE = 16;          // ... and neighbour ids staged per thread (longer rows re-scan shared memory)
 constexpr size_t WS_SMEM = (size_t)(ADJ_THREADS / 32) * 3 * WS_CAP * (sizeof(double4) + sizeof(int));
 
-// One accepted pair: feature sums in float64 (numpy's evaluation order per term)
+// 1/x in float64 from the hardware seed (rcp.approx.ftz.f64: 2^-23) and two Newton steps: within ~1 ulp of the
+// IEEE quotient in 5 instructions instead of the ~30 (with a slow-path branch) of `1.0 / x`.  The feature sums
+// are rounded to fp32 afterwards, so the last float64 bit is irrelevant to parity.
+__device__ __forceinline__ double fast_rcp(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    y = fma(y, fma(-x, y, 1.0), y);
+    y = fma(y, fma(-x, y, 1.0), y);
+    return y;
+}
+
+// One accepted pair: feature sums in float64
 #define FGNN_ADJ_ACCEPT(o, dx, dy, r2)                                                                \
     {                                                                                                 \
-        const double inv = 1.0 / (r2);                                                                \
+        const double inv = fast_rcp(r2);                                                              \
         const double inv2 = inv * inv;                                                                \
         f0 += me.z - (o).z;                                                                           \
         f1 += (dx) * inv2;                                                                            \
@@ -461,14 +465,17 @@ __global__ void __launch_bounds__(ADJ_THREADS) k_adjacency_t(Params p, int stage
         wy = wrap(iy, p.Gy);
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
-            const int rowbase = (ep * p.Gy + wrap(iy + r - 1, p.Gy)) * p.G;
+            // rows wy-1, wy, wy+1 on the wrapped grid without further remainders
+            const int wr = r == 0 ? (wy == 0 ? p.Gy - 1 : wy - 1) : r == 1 ? wy : (wy == p.Gy - 1 ? 0 : wy + 1);
+            const int rowbase = (ep * p.Gy + wr) * p.G;
             if (cxw >= 1 && cxw <= p.G - 2) {            // the row's three cells are contiguous slots
                 q0[3 * r] = __ldg(&p.cell_start[rowbase + cxw - 1]);
                 q1[3 * r] = __ldg(&p.cell_start[rowbase + cxw + 2]);
             } else {
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    const int cell = rowbase + wrap(ix + c - 1, p.G);
+                    const int wc = c == 0 ? (cxw == 0 ? p.G - 1 : cxw - 1) : c == 1 ? cxw : (cxw == p.G - 1 ? 0 : cxw + 1);
+                    const int cell = rowbase + wc;
                     q0[3 * r + c] = __ldg(&p.cell_start[cell]);
                     q1[3 * r + c] = __ldg(&p.cell_start[cell + 1]);
                 }
@@ -521,18 +528,42 @@ __global__ void __launch_bounds__(ADJ_THREADS) k_adjacency_t(Params p, int stage
     }
     if (valid) {
         if (WS && fast) {
+            // Phase 1 -- filter: positions only, ~12 instructions per candidate, no divergent feature code.  The
+            // accepted candidates' tile indices go to the stage.  (Fused, the feature code ran in nearly every
+            // iteration for a handful of lanes: 19 of 32 lanes active on average.)
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
                 const double4* cand = w_cand + r * WS_CAP - lo[r];
-                const int* cid = w_cid + r * WS_CAP - lo[r];
                 for (int q = q0[3 * r]; q < q1[3 * r]; ++q) {
-                    const double4 o = cand[q];
-                    const double dx = me.x - o.x, dy = me.y - o.y;
-                    const double r2 = r2_exact(dx, dy);
+                    const double2 o = *reinterpret_cast<const double2*>(&cand[q]);
+                    const double r2 = r2_exact(me.x - o.x, me.y - o.y);
                     if (q != s && r2 < p.R2) {
-                        FGNN_ADJ_ACCEPT(o, dx, dy, r2)
-                        if (count < stage_cap) s_stage[count * ADJ_THREADS + tid] = cid[q];
+                        if (count < stage_cap) s_stage[count * ADJ_THREADS + tid] = r * WS_CAP + q - lo[r];
                         ++count;
+                    }
+                }
+            }
+            // Phase 2 -- features of the accepted pairs, in the same order
+            const int n_st = count < stage_cap ? count : stage_cap;
+            for (int e = 0; e < n_st; ++e) {
+                const double4 o = w_cand[s_stage[e * ADJ_THREADS + tid]];
+                const double dx = me.x - o.x, dy = me.y - o.y;
+                const double r2 = r2_exact(dx, dy);
+                FGNN_ADJ_ACCEPT(o, dx, dy, r2)
+            }
+            if (count > stage_cap) {                      // rare long row: the pairs beyond the stage, same order
+                int w = 0;
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    const double4* cand = w_cand + r * WS_CAP - lo[r];
+                    for (int q = q0[3 * r]; q < q1[3 * r]; ++q) {
+                        const double4 o = cand[q];
+                        const double dx = me.x - o.x, dy = me.y - o.y;
+                        const double r2 = r2_exact(dx, dy);
+                        if (q != s && r2 < p.R2) {
+                            if (w >= stage_cap) FGNN_ADJ_ACCEPT(o, dx, dy, r2)
+                            ++w;
+                        }
                     }
                 }
             }
@@ -576,7 +607,8 @@ __global__ void __launch_bounds__(ADJ_THREADS) k_adjacency_t(Params p, int stage
     for (int e = 0; e < ELLW; ++e) head[e] = -1;
     const int staged = count < stage_cap ? count : stage_cap;
     for (int e = 0; e < staged; ++e) {
-        const int id = s_stage[e * ADJ_THREADS + tid];
+        int id = s_stage[e * ADJ_THREADS + tid];
+        if (WS && fast) id = w_cid[id];                   // the fast path staged tile indices
         cols[e] = id;
 #pragma unroll
         for (int u = 0; u < ELLW; ++u)
