@@ -196,7 +196,7 @@ extern "C" int fgnn_create(const fgnn_config* cfg, fgnn_handle** out) {
         const char* lh = getenv("FGNN_LAST_HOP_SEPARATE");
         h->last_hop_separate = lh ? atoi(lh) != 0 : FGNN_LAST_HOP_SEPARATE_DEFAULT;
         CK(cudaFuncSetAttribute((const void*)k_adjacency_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)((size_t)WS_STAGE * ADJ_THREADS * sizeof(int) + WS_SMEM)));
+                                (int)((size_t)(WS_STAGE + 1) * ADJ_THREADS * sizeof(int) + WS_SMEM)));
         CK(cudaFuncSetAttribute((const void*)k_adjacency_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)((size_t)64 * ADJ_THREADS * sizeof(int))));
     }
@@ -446,7 +446,7 @@ static int enqueue_build(fgnn_handle* h, int advance, cudaStream_t st) {
         k_bin<<<gb, 256, 0, st>>>(p);
         if (launch_check(h, "bin")) return 1;
     }
-    k_scan<<<p.n_tiles, SCAN_THREADS, 0, st>>>(p, advance);
+    k_scan<<<p.n_tiles, SCAN_THREADS, 0, st>>>(p, advance, p.n_tiles <= h->sm_count * 4 ? 1 : 0);
     if (launch_check(h, "scan")) return 1;
     k_scatter<<<gb, 256, 0, st>>>(p);
     if (launch_check(h, "scatter")) return 1;
@@ -455,7 +455,7 @@ static int enqueue_build(fgnn_handle* h, int advance, cudaStream_t st) {
     if (h->adj_warp_staged) {
         const int stage = h->adj_stage < WS_STAGE ? h->adj_stage : WS_STAGE;
         k_adjacency_t<true><<<blocks_for(h->launch_pool, ADJ_THREADS), ADJ_THREADS,
-                              (size_t)stage * ADJ_THREADS * sizeof(int) + WS_SMEM, st>>>(p, stage);
+                              (size_t)(stage + 1) * ADJ_THREADS * sizeof(int) + WS_SMEM, st>>>(p, stage);
     } else {
         k_adjacency_t<false><<<blocks_for(h->launch_pool, ADJ_THREADS), ADJ_THREADS,
                                (size_t)h->adj_stage * ADJ_THREADS * sizeof(int), st>>>(p, h->adj_stage);

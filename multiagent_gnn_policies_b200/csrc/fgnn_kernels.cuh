@@ -276,14 +276,19 @@ constexpr int SCAN_ITEMS = 16;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 constexpr unsigned FLAG_AGG = 1u << 30, VAL_MASK = (1u << 30) - 1;
 
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan(Params p, int advance) {
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan(Params p, int advance, int static_ids) {
     __shared__ int s_tile;
     __shared__ int s_warp[SCAN_THREADS / 32];
     __shared__ int s_excl;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_tile = atomicAdd(p.tile_counter, 1);
-    __syncthreads();
-    const int tile = s_tile;
+    // Tile id: the block index when every tile is resident at once (the look-back below then cannot wait on a block
+    // that has not started; saves 245 serialised same-address atomics), else handed out by an atomic counter.
+    int tile = blockIdx.x;
+    if (!static_ids) {
+        if (tid == 0) s_tile = atomicAdd(p.tile_counter, 1);
+        __syncthreads();
+        tile = s_tile;
+    }
     if (tile == 0 && tid == 0) {
         const int tn = *p.t + (advance ? 1 : 0);
         *p.t = tn;
@@ -488,7 +493,7 @@ __global__ void __launch_bounds__(ADJ_THREADS) k_adjacency_t(Params p, int stage
     double4* w_cand = nullptr;
     int* w_cid = nullptr;
     if (WS) {
-        unsigned char* base = s_adj_raw + (size_t)stage_cap * ADJ_THREADS * sizeof(int);
+        unsigned char* base = s_adj_raw + (size_t)(stage_cap + 1) * ADJ_THREADS * sizeof(int);   // + the dummy stage row
         w_cand = reinterpret_cast<double4*>(base) + warp * 3 * WS_CAP;
         w_cid = reinterpret_cast<int*>(base + (size_t)(ADJ_THREADS / 32) * 3 * WS_CAP * sizeof(double4)) + warp * 3 * WS_CAP;
         const unsigned vm = __ballot_sync(0xffffffffu, valid);
@@ -534,13 +539,14 @@ __global__ void __launch_bounds__(ADJ_THREADS) k_adjacency_t(Params p, int stage
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
                 const double4* cand = w_cand + r * WS_CAP - lo[r];
+#pragma unroll 2
                 for (int q = q0[3 * r]; q < q1[3 * r]; ++q) {
                     const double2 o = *reinterpret_cast<const double2*>(&cand[q]);
                     const double r2 = r2_exact(me.x - o.x, me.y - o.y);
-                    if (q != s && r2 < p.R2) {
-                        if (count < stage_cap) s_stage[count * ADJ_THREADS + tid] = r * WS_CAP + q - lo[r];
-                        ++count;
-                    }
+                    // branch-free: always store to the next free stage row (row `stage_cap` is a dummy), advance on accept
+                    const int slot = count < stage_cap ? count : stage_cap;
+                    s_stage[slot * ADJ_THREADS + tid] = r * WS_CAP + q - lo[r];
+                    count += (q != s && r2 < p.R2) ? 1 : 0;
                 }
             }
             // Phase 2 -- features of the accepted pairs, in the same order
@@ -739,8 +745,11 @@ __device__ __forceinline__ void gather_rows(const Params& p, int g, int a, const
 //      Intermediates are stored PRE-SCALED by the source scale of the next hop's graph,
 //      sinv_{t-j-1}[n], so the consumer gathers one 32-byte row per edge and nothing else.
 // ------------------------------------------------------------------------------------------
+#ifndef FGNN_HOP_MIN_BLOCKS
+#define FGNN_HOP_MIN_BLOCKS 4
+#endif
 template <int NB, bool FIRST>
-__global__ void __launch_bounds__(256) k_hop(Params p, int j) {
+__global__ void __launch_bounds__(256, NB == 2 ? FGNN_HOP_MIN_BLOCKS : 1) k_hop(Params p, int j) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= pool_size(p)) return;
     const int a = pool_agent(p, i);
