@@ -241,3 +241,41 @@ def test_train_dagger_runs_natively():
         gnn_dagger.DAGGER = orig
     assert np.isfinite(stats['mean'])
     assert made and made[0]._trainer is not None and made[0]._trainer.launch_count() == 2 * 3 * 2
+
+
+def test_device_dagger_parallel_episodes():
+    """DAGGER for B block-diagonal episodes on the device (BASELINE config C3 in miniature): stored states are the
+    engine's aggregated features, sampled batches index (step, episode) correctly, and imitation reduces the loss."""
+    import torch
+    from multiagent_gnn_policies_b200.dagger import DeviceDagger
+    from oracle import flock_env, train as otrain, learner as olearner
+    B, N = 4, 60
+    rng = np.random.RandomState(2)
+    x0 = np.concatenate([flock_env.FlockingRelativeOracle(n_agents=N, rng=rng).sample_initial_state() for _ in range(B)])
+    dg = DeviceDagger(N, B, k=3, hidden=32, n_layers=2, lr=2e-3, buffer_steps=32, batch_size=8, seed=5)
+    w_before = [p.clone() for p in dg.params]
+    ret, loss_sum = dg.run_episode(x0, steps=12, updates=0)
+    assert dg.filled == 12 and np.isfinite(ret)
+    # the stored label of step 0 is the oracle's expert action for every episode
+    for e in range(B):
+        u_ref = flock_env.controller(x0[e * N:(e + 1) * N], 1.0, 1.0, centralized=False)
+        got = dg.label_buf[0, e * N:(e + 1) * N].cpu().numpy()
+        assert np.abs(got - u_ref).max() <= 1e-6
+    # a sampled batch is made of whole (step, episode) states
+    gen_state = dg.gen.get_state()
+    z, y = dg.sample_batch()
+    dg.gen.set_state(gen_state)
+    pick = torch.randint(0, dg.filled * B, (dg.batch_size,), generator=dg.gen, device=dg.device).cpu().numpy()
+    for i, pk in enumerate(pick):
+        st, ep = pk // B, pk % B
+        np.testing.assert_array_equal(z[i].cpu().numpy(), dg.z_buf[st, :, ep * N:(ep + 1) * N].cpu().numpy())
+        np.testing.assert_array_equal(y[i].cpu().numpy(), dg.label_buf[st, ep * N:(ep + 1) * N].cpu().numpy().T)
+    # the loss of the native step on that batch equals the oracle's on the same numbers
+    layers = olearner.weights_from_state_dict({k_: v.cpu().numpy() for k_, v in dg.state_dict().items()})
+    loss_ref, _ = otrain.loss_and_grads(layers, z.cpu().numpy().transpose(0, 1, 3, 2), y.cpu().numpy().reshape(-1, 1, 2, N))
+    loss, _ = dg.trainer.step(z, y, dg.params, apply=False)
+    assert abs(loss.item() - loss_ref) <= 2e-5 * abs(loss_ref)
+    losses = [dg.gradient_step() for _ in range(300)]
+    assert np.mean(losses[-20:]) < 0.7 * np.mean(losses[:20])
+    assert any((a - b).abs().max().item() > 0 for a, b in zip(dg.params, w_before))
+    dg.close()
