@@ -54,6 +54,7 @@ struct fgnn_handle {
     int adj_stage = 16;              // neighbour ids staged per thread in k_adjacency
     bool adj_warp_staged = false;    // k_adjacency_t<true>: candidates staged per warp in shared memory
     bool last_hop_separate = false;  // last hop as its own launch instead of inside the final kernel
+    bool scan_two_pass = false;      // tile sums in their own launch: the scan proper never waits on another block
     // tensor-core readout (tcgen05, 3xTF32)
     bool use_tc = false;
     std::vector<uint8_t> tc_host;    // TcLayout pack, host mirror
@@ -99,6 +100,9 @@ static int dalloc(fgnn_handle* h, T** ptr, size_t count, bool zero = true) {
 // kernel-variant defaults (each can be overridden per process by the environment variable named in fgnn_create)
 #ifndef FGNN_ADJ_DEFAULT_WS
 #define FGNN_ADJ_DEFAULT_WS true                 // measured: 120 -> 112 us at N=1M, d~5 (profiles/r1_bench_history.md)
+#endif
+#ifndef FGNN_SCAN_TWO_PASS_DEFAULT
+#define FGNN_SCAN_TWO_PASS_DEFAULT true           // measured: 312 -> 294 us/step; blocks spinning on other blocks' status words are slow here
 #endif
 #ifndef FGNN_LAST_HOP_SEPARATE_DEFAULT
 #define FGNN_LAST_HOP_SEPARATE_DEFAULT true      // measured: 312 -> 307 us/step (high-occupancy gather + streaming readout)
@@ -192,7 +196,11 @@ extern "C" int fgnn_create(const fgnn_config* cfg, fgnn_handle** out) {
     h->adj_stage = (int)(cap_per < 8 ? 8 : cap_per > 64 ? 64 : cap_per);
     {   // warp-staged adjacency: pays when a warp's three row ranges fit its tile (moderate degree); FGNN_ADJ_MODE=0/1 overrides
         const char* mode = getenv("FGNN_ADJ_MODE");
-        h->adj_warp_staged = mode ? atoi(mode) != 0 : FGNN_ADJ_DEFAULT_WS;
+        // default: on when the expected degree is moderate (edge-capacity hint <= 40 per agent); at larger radii a warp's
+        // row ranges outgrow the tile and the per-lane path with its deeper stage is faster (measured, C4 sweep)
+        h->adj_warp_staged = mode ? atoi(mode) != 0 : (FGNN_ADJ_DEFAULT_WS && cap_per <= 40);
+        const char* tp = getenv("FGNN_SCAN_TWO_PASS");
+        h->scan_two_pass = tp ? atoi(tp) != 0 : FGNN_SCAN_TWO_PASS_DEFAULT;
         const char* lh = getenv("FGNN_LAST_HOP_SEPARATE");
         h->last_hop_separate = lh ? atoi(lh) != 0 : FGNN_LAST_HOP_SEPARATE_DEFAULT;
         CK(cudaFuncSetAttribute((const void*)k_adjacency_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -446,7 +454,12 @@ static int enqueue_build(fgnn_handle* h, int advance, cudaStream_t st) {
         k_bin<<<gb, 256, 0, st>>>(p);
         if (launch_check(h, "bin")) return 1;
     }
-    k_scan<<<p.n_tiles, SCAN_THREADS, 0, st>>>(p, advance, p.n_tiles <= h->sm_count * 4 ? 1 : 0);
+    if (h->scan_two_pass) {
+        k_scan_sums<<<p.n_tiles, SCAN_THREADS, 0, st>>>(p);
+        if (launch_check(h, "scan_sums")) return 1;
+    }
+    k_scan<<<p.n_tiles, SCAN_THREADS, 0, st>>>(p, advance, (h->scan_two_pass || p.n_tiles <= h->sm_count * 4) ? 1 : 0,
+                                               h->scan_two_pass ? 1 : 0);
     if (launch_check(h, "scan")) return 1;
     k_scatter<<<gb, 256, 0, st>>>(p);
     if (launch_check(h, "scatter")) return 1;

@@ -272,17 +272,52 @@ __global__ void __launch_bounds__(256) k_finalize_reward(Params p) { finalize_re
 //      direct look-back), zeroes cell_count; tile 0 also advances t.  (The reward is finalised by k_scatter.)
 // ------------------------------------------------------------------------------------------
 constexpr int SCAN_THREADS = 256;
-constexpr int SCAN_ITEMS = 16;
+constexpr int SCAN_ROUNDS = 2;                                   // int4 vectors per thread
+constexpr int SCAN_ITEMS = 4 * SCAN_ROUNDS;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 constexpr unsigned FLAG_AGG = 1u << 30, VAL_MASK = (1u << 30) - 1;
 
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan(Params p, int advance, int static_ids) {
+// Accesses are COALESCED int4 vectors (vector r of thread t sits at r*256 + t inside the tile): the first version
+// gave every thread 16 consecutive counts, so each warp-wide load touched 32 different lines and the three passes
+// over the array (load, zero, store) kept the L1TEX wavefront pipe of the few SMs that run this small grid busy for
+// ~20 us (ncu: lsu wavefronts 22-27 % of peak for 12 MB of traffic, barrier/lg_throttle stalls).
+// Two-pass mode, pass 1: the sum of every tile's counts into tile_status (plain ints, no flags).  Pass 2 (k_scan with
+// two_pass = 1) then reads its predecessors' sums without waiting on anybody.
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_sums(Params p) {
+    __shared__ int s_w[SCAN_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = p.C + 1;
+    int sum = 0;
+#pragma unroll
+    for (int r = 0; r < SCAN_ROUNDS; ++r) {
+        const int e = blockIdx.x * SCAN_TILE + (r * SCAN_THREADS + tid) * 4;
+        if (e + 3 < n) {
+            const int4 v = *reinterpret_cast<const int4*>(p.cell_count + e);
+            sum += v.x + v.y + v.z + v.w;
+        } else {
+            for (int j = 0; j < 3; ++j) sum += e + j < n ? p.cell_count[e + j] : 0;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) s_w[warp] = sum;
+    __syncthreads();
+    if (tid == 0) {
+        int t = 0;
+#pragma unroll
+        for (int w = 0; w < SCAN_THREADS / 32; ++w) t += s_w[w];
+        p.tile_status[blockIdx.x] = (unsigned)t;
+    }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan(Params p, int advance, int static_ids, int two_pass) {
     __shared__ int s_tile;
-    __shared__ int s_warp[SCAN_THREADS / 32];
+    __shared__ int s_warp[SCAN_ROUNDS][SCAN_THREADS / 32];
     __shared__ int s_excl;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = SCAN_THREADS / 32;
     // Tile id: the block index when every tile is resident at once (the look-back below then cannot wait on a block
-    // that has not started; saves 245 serialised same-address atomics), else handed out by an atomic counter.
+    // that has not started; saves the serialised same-address atomics), else handed out by an atomic counter.
     int tile = blockIdx.x;
     if (!static_ids) {
         if (tid == 0) s_tile = atomicAdd(p.tile_counter, 1);
@@ -295,68 +330,76 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(Params p, int advance, in
         p.nnz_cursor[slot_of(tn, p.K)] = 0;          // edge cursor of the slot about to be rebuilt
     }
     const int n = p.C + 1;
-    const int base = tile * SCAN_TILE + tid * SCAN_ITEMS;
-    int v[SCAN_ITEMS];
-    int sum = 0;
+    int4 v[SCAN_ROUNDS];
+    int sum[SCAN_ROUNDS], inc[SCAN_ROUNDS];
 #pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; ++i) {
-        int idx = base + i;
-        v[i] = idx < n ? p.cell_count[idx] : 0;
-        sum += v[i];
-    }
+    for (int r = 0; r < SCAN_ROUNDS; ++r) {
+        const int e = tile * SCAN_TILE + (r * SCAN_THREADS + tid) * 4;      // first element of this vector
+        if (e + 3 < n) {
+            v[r] = *reinterpret_cast<const int4*>(p.cell_count + e);
+            *reinterpret_cast<int4*>(p.cell_count + e) = make_int4(0, 0, 0, 0);
+        } else {
+            v[r].x = e < n ? p.cell_count[e] : 0;
+            v[r].y = e + 1 < n ? p.cell_count[e + 1] : 0;
+            v[r].z = e + 2 < n ? p.cell_count[e + 2] : 0;
+            v[r].w = 0;                                                      // e + 3 >= n here
+            if (e < n) p.cell_count[e] = 0;
+            if (e + 1 < n) p.cell_count[e + 1] = 0;
+            if (e + 2 < n) p.cell_count[e + 2] = 0;
+        }
+        sum[r] = v[r].x + v[r].y + v[r].z + v[r].w;
+        inc[r] = sum[r];
 #pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; ++i) {
-        int idx = base + i;
-        if (idx < n) p.cell_count[idx] = 0;
+        for (int o = 1; o < 32; o <<= 1) {
+            int y = __shfl_up_sync(0xffffffffu, inc[r], o);
+            if (lane >= o) inc[r] += y;
+        }
+        if (lane == 31) s_warp[r][warp] = inc[r];
     }
-    // block exclusive scan of the per-thread sums
-    int inc = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        int y = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += y;
-    }
-    if (lane == 31) s_warp[warp] = inc;
     __syncthreads();
     if (warp == 0) {
-        int w = lane < SCAN_THREADS / 32 ? s_warp[lane] : 0;
+        // exclusive scan over the (round, warp) totals in element order; lane l <-> round l / NW, warp l % NW
+        static_assert(SCAN_ROUNDS * NW <= 32, "one warp scans the partial totals");
+        int w = lane < SCAN_ROUNDS * NW ? s_warp[lane / NW][lane % NW] : 0;
         int winc = w;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             int y = __shfl_up_sync(0xffffffffu, winc, o);
             if (lane >= o) winc += y;
         }
-        if (lane < SCAN_THREADS / 32) s_warp[lane] = winc - w;      // exclusive per-warp offsets
-        const int total = __shfl_sync(0xffffffffu, winc, SCAN_THREADS / 32 - 1);
-        // publish this tile's aggregate right away: nobody waits for a prefix
-        if (lane == 0) {
-            volatile unsigned* status = p.tile_status;
-            status[tile] = FLAG_AGG | (unsigned)total;
-        }
-    }
-    // Look-back without a dependency chain: the tile count is small (C / 4096), so warp 0 fetches the aggregates of
-    // ALL predecessor tiles directly -- one round trip to L2 for the whole prefix instead of one per 32 tiles.  Tile
-    // ids are handed out by an atomic counter, so every predecessor is already running and will publish.  Only one
-    // warp per tile polls (with a back-off): 62 k threads spinning on the status words slowed the publishers down.
-    if (warp == 0) {
-        volatile unsigned* status = p.tile_status;
+        if (lane < SCAN_ROUNDS * NW) s_warp[lane / NW][lane % NW] = winc - w;
+        const int total = __shfl_sync(0xffffffffu, winc, SCAN_ROUNDS * NW - 1);
         int part = 0;
-        for (int idx = lane; idx < tile; idx += 32) {
-            unsigned w32;
-            while (((w32 = status[idx]) >> 30) == 0) __nanosleep(40);
-            part += (int)(w32 & VAL_MASK);
+        if (two_pass) {                                   // predecessors' sums were written by k_scan_sums
+            for (int idx = lane; idx < tile; idx += 32) part += (int)__ldg(&p.tile_status[idx]);
+        } else {
+            volatile unsigned* status = p.tile_status;
+            if (lane == 0) status[tile] = FLAG_AGG | (unsigned)total;      // publish right away: nobody waits for a prefix
+            // Look-back without a dependency chain: the tile count is small, so this warp fetches the aggregates of
+            // ALL predecessor tiles directly -- one round trip to L2 for the whole prefix instead of one per 32 tiles.
+            for (int idx = lane; idx < tile; idx += 32) {
+                unsigned w32;
+                while (((w32 = status[idx]) >> 30) == 0) __nanosleep(40);
+                part += (int)(w32 & VAL_MASK);
+            }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
         if (lane == 0) s_excl = part;
     }
     __syncthreads();
-    int run = s_excl + s_warp[warp] + (inc - sum);
 #pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; ++i) {
-        int idx = base + i;
-        if (idx < n) p.cell_start[idx] = run;
-        run += v[i];
+    for (int r = 0; r < SCAN_ROUNDS; ++r) {
+        const int e = tile * SCAN_TILE + (r * SCAN_THREADS + tid) * 4;
+        const int run = s_excl + s_warp[r][warp] + (inc[r] - sum[r]);
+        const int4 o = make_int4(run, run + v[r].x, run + v[r].x + v[r].y, run + v[r].x + v[r].y + v[r].z);
+        if (e + 3 < n) {
+            *reinterpret_cast<int4*>(p.cell_start + e) = o;
+        } else {
+            if (e < n) p.cell_start[e] = o.x;
+            if (e + 1 < n) p.cell_start[e + 1] = o.y;
+            if (e + 2 < n) p.cell_start[e + 2] = o.z;
+        }
     }
 }
 

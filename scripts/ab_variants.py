@@ -17,7 +17,7 @@ from multiagent_gnn_policies_b200.engine import FlockEngine        # noqa: E402
 
 
 def run(n, steps, env, x0, sd, k=3, hidden=32):
-    for key in ("FGNN_ADJ_MODE", "FGNN_LAST_HOP_SEPARATE"):
+    for key in ("FGNN_ADJ_MODE", "FGNN_LAST_HOP_SEPARATE", "FGNN_SCAN_TWO_PASS"):
         os.environ.pop(key, None)
     os.environ.update(env)
     eng = FlockEngine(n_agents=n, k=k, hidden=hidden, n_layers=2, comm_radius=1.0, dt=0.01)
@@ -50,14 +50,16 @@ def main():
     sd, _ = make_weights(32, 3, 2)
     ref_state = None
     print(f"N={n} steps={steps}")
-    for adj, sep in itertools.product("01", "01"):
-        env = {"FGNN_ADJ_MODE": adj, "FGNN_LAST_HOP_SEPARATE": sep}
+    for adj, sep, tp in itertools.product("01", "01", "01"):
+        if adj != sep:
+            continue                      # the mixed combinations were measured earlier (profiles/r1_bench_history.md)
+        env = {"FGNN_ADJ_MODE": adj, "FGNN_LAST_HOP_SEPARATE": sep, "FGNN_SCAN_TWO_PASS": tp}
         ms, per, st = run(n, steps, env, x0, sd)
         if ref_state is None:
             ref_state = st
         same = bool(np.array_equal(st, ref_state))
         kern = " ".join(f"{k_}={v * 1e3:.1f}" for k_, v in per.items())
-        print(f"adj_ws={adj} last_sep={sep}: {ms * 1e3:.1f} us/step  {n / ms / 1e6:.3f}e9 agent-steps/s  "
+        print(f"adj_ws={adj} last_sep={sep} scan_two_pass={tp}: {ms * 1e3:.1f} us/step  {n / ms / 1e6:.3f}e9 agent-steps/s  "
               f"bit-identical={same}  [{kern}] sum={sum(per.values()) * 1e3:.1f}", flush=True)
 
 
