@@ -533,11 +533,17 @@ __global__ void __launch_bounds__(ADJ_THREADS) k_adjacency_t(Params p, int stage
     // ---- warp-staged fast path? (warp-uniform decision) ----
     bool fast = false;
     int lo[3] = {0, 0, 0};
-    double4* w_cand = nullptr;
+    // candidate tile of this warp, structure-of-arrays: lanes scanning neighbouring slots read consecutive 8-byte
+    // words (an array of double4 records put slot q in banks 8q mod 32: 4- to 8-way conflicts on every read)
+    double* w_x = nullptr;
+    double* w_y = nullptr;
+    double* w_vx = nullptr;
+    double* w_vy = nullptr;
     int* w_cid = nullptr;
     if (WS) {
         unsigned char* base = s_adj_raw + (size_t)(stage_cap + 1) * ADJ_THREADS * sizeof(int);   // + the dummy stage row
-        w_cand = reinterpret_cast<double4*>(base) + warp * 3 * WS_CAP;
+        double* wd = reinterpret_cast<double*>(base) + (size_t)warp * 4 * 3 * WS_CAP;
+        w_x = wd; w_y = wd + 3 * WS_CAP; w_vx = wd + 2 * 3 * WS_CAP; w_vy = wd + 3 * 3 * WS_CAP;
         w_cid = reinterpret_cast<int*>(base + (size_t)(ADJ_THREADS / 32) * 3 * WS_CAP * sizeof(double4)) + warp * 3 * WS_CAP;
         const unsigned vm = __ballot_sync(0xffffffffu, valid);
         if (vm) {
@@ -565,7 +571,9 @@ __global__ void __launch_bounds__(ADJ_THREADS) k_adjacency_t(Params p, int stage
 #pragma unroll
                     for (int r = 0; r < 3; ++r) {
                         for (int i = lane; i < n[r]; i += 32) {
-                            w_cand[r * WS_CAP + i] = ldg256_nc(&p.sorted_state[lo[r] + i]);
+                            const double4 c = ldg256_nc(&p.sorted_state[lo[r] + i]);
+                            w_x[r * WS_CAP + i] = c.x; w_y[r * WS_CAP + i] = c.y;
+                            w_vx[r * WS_CAP + i] = c.z; w_vy[r * WS_CAP + i] = c.w;
                             w_cid[r * WS_CAP + i] = __ldg(&p.sorted_id[lo[r] + i]);
                         }
                     }
@@ -581,11 +589,11 @@ __global__ void __launch_bounds__(ADJ_THREADS) k_adjacency_t(Params p, int stage
             // iteration for a handful of lanes: 19 of 32 lanes active on average.)
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
-                const double4* cand = w_cand + r * WS_CAP - lo[r];
+                const double* cx = w_x + r * WS_CAP - lo[r];
+                const double* cy = w_y + r * WS_CAP - lo[r];
 #pragma unroll 2
                 for (int q = q0[3 * r]; q < q1[3 * r]; ++q) {
-                    const double2 o = *reinterpret_cast<const double2*>(&cand[q]);
-                    const double r2 = r2_exact(me.x - o.x, me.y - o.y);
+                    const double r2 = r2_exact(me.x - cx[q], me.y - cy[q]);
                     // branch-free: always store to the next free stage row (row `stage_cap` is a dummy), advance on accept
                     const int slot = count < stage_cap ? count : stage_cap;
                     s_stage[slot * ADJ_THREADS + tid] = r * WS_CAP + q - lo[r];
@@ -595,7 +603,8 @@ __global__ void __launch_bounds__(ADJ_THREADS) k_adjacency_t(Params p, int stage
             // Phase 2 -- features of the accepted pairs, in the same order
             const int n_st = count < stage_cap ? count : stage_cap;
             for (int e = 0; e < n_st; ++e) {
-                const double4 o = w_cand[s_stage[e * ADJ_THREADS + tid]];
+                const int ci = s_stage[e * ADJ_THREADS + tid];
+                const double4 o = make_double4(w_x[ci], w_y[ci], w_vx[ci], w_vy[ci]);
                 const double dx = me.x - o.x, dy = me.y - o.y;
                 const double r2 = r2_exact(dx, dy);
                 FGNN_ADJ_ACCEPT(o, dx, dy, r2)
@@ -604,9 +613,9 @@ __global__ void __launch_bounds__(ADJ_THREADS) k_adjacency_t(Params p, int stage
                 int w = 0;
 #pragma unroll
                 for (int r = 0; r < 3; ++r) {
-                    const double4* cand = w_cand + r * WS_CAP - lo[r];
+                    const int off = r * WS_CAP - lo[r];
                     for (int q = q0[3 * r]; q < q1[3 * r]; ++q) {
-                        const double4 o = cand[q];
+                        const double4 o = make_double4(w_x[off + q], w_y[off + q], w_vx[off + q], w_vy[off + q]);
                         const double dx = me.x - o.x, dy = me.y - o.y;
                         const double r2 = r2_exact(dx, dy);
                         if (q != s && r2 < p.R2) {
@@ -668,13 +677,11 @@ __global__ void __launch_bounds__(ADJ_THREADS) k_adjacency_t(Params p, int stage
         if (WS && fast) {
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
-                const double4* cand = w_cand + r * WS_CAP - lo[r];
-                const int* cid = w_cid + r * WS_CAP - lo[r];
+                const int off = r * WS_CAP - lo[r];
                 for (int q = q0[3 * r]; q < q1[3 * r]; ++q) {
-                    const double4 o = cand[q];
-                    const double r2 = r2_exact(me.x - o.x, me.y - o.y);
+                    const double r2 = r2_exact(me.x - w_x[off + q], me.y - w_y[off + q]);
                     if (q != s && r2 < p.R2) {
-                        if (w >= stage_cap) cols[w] = cid[q];
+                        if (w >= stage_cap) cols[w] = w_cid[off + q];
                         ++w;
                     }
                 }
