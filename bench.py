@@ -387,6 +387,11 @@ def run_sharded(args, rank, world, local_rank, N, side, sd, weights_note, edge_c
     bounds = np.array([-parallel.INF] + [q * side for q in range(1, world)] + [parallel.INF])
     frame_vx = float(np.random.default_rng(11).uniform(-3.0, 3.0, size=(2,))[0])       # the flock's common velocity bias
     flock.reset(x_global, ranges, bounds=bounds, frame_velocity=frame_vx)
+    if os.environ.get("FGNN_NATIVE_COMM", "0") == "1":
+        # opt-in: the all-gather inside ONE step graph on the engine's own communicator (fgnn_shard_step).  Measured at 2
+        # GPUs: 5.45e9 vs 5.50e9 agent-steps/s for the default (torch.distributed between two graph halves) -- the
+        # sharded step's extra ~70 us is not the collective's launch path -- so the simpler default stays.
+        be.init_comm(rank, world)
     for _ in range(args.warmup):
         flock.step()
     barrier()
@@ -429,7 +434,7 @@ def run_sharded(args, rank, world, local_rank, N, side, sd, weights_note, edge_c
     peak, peak_src = measured_peaks()
     d = st["n_edges"] / max(1, (cnt + ghosts / world))
     step_bytes = 268 + 12 * d
-    config = dict(config, parallelism=f"index-sharded x{world}, halo all-gather (NCCL) of {flock.cap}-record buffers, "
+    config = dict(config, parallelism=f"index-sharded x{world}, halo all-gather ({'NCCL inside the step graph' if getattr(be, 'native_comm', False) else 'NCCL via torch.distributed between two graph halves'}) of {flock.cap}-record buffers, "
                                       f"halo depth {flock.depth:.2f}, ownership hand-over", n_agents_total=n_total)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -154,6 +154,14 @@ int fgnn_shard_step_begin(fgnn_handle* h, const double* windows, int64_t window_
                           void* stream);
 int fgnn_shard_step_end(fgnn_handle* h, const double* recv_buf, int32_t cap, void* stream);
 int fgnn_shard_owned(fgnn_handle* h, int32_t* ids, int32_t* count, void* stream);   /* synchronises */
+/* The whole sharded step as ONE CUDA graph with the halo all-gather inside it (ncclAllGather on the engine's own
+ * communicator, enqueued on the caller's stream between the two halves above): no second stream, no host round
+ * trip between the halves.  fgnn_comm_unique_id: rank 0 obtains the 128-byte id and distributes it by any means
+ * (the Python host broadcasts it through torch.distributed); fgnn_comm_init is collective over the ranks.
+ * recv_buf: world * (cap + 1) records; its headers, as the previous step left them, are this step's windows. */
+int fgnn_comm_unique_id(void* id_128);
+int fgnn_comm_init(fgnn_handle* h, const void* id_128, int32_t rank, int32_t world);
+int fgnn_shard_step(fgnn_handle* h, double* send_buf, double* recv_buf, int32_t cap, void* stream);
 
 /* ---- environment variants named by the reference's cfgs (gym_flock, un-vendored) ----
  * FlockingLeader-v0 (cfg/dagger_leader.cfg:24): mask_bn (B*N,) bytes [h/d], 0 = leader -- the integrator ignores

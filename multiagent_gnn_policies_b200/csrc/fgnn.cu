@@ -4,6 +4,8 @@
 #include "fgnn_final_tc.cuh"
 #include "../../include/fgnn.h"
 
+#include <dlfcn.h>
+
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -26,6 +28,43 @@ namespace fgnn { void set_error(const char* msg) { g_err = msg ? msg : ""; } }  
             return fail(buf__);                                                                      \
         }                                                                                            \
     } while (0)
+
+// ---- NCCL inside the step graph ---------------------------------------------------------------------------------
+// The library is resolved at run time (dlopen): a process that has imported torch already holds libnccl.so.2, so
+// the same NCCL serves both; nothing is linked at build time.  Declarations follow nccl.h (ncclUniqueId is 128
+// bytes passed by value, ncclFloat64 = 8, ncclSuccess = 0).
+namespace {
+struct NcclId { char internal[128]; };
+struct NcclApi {
+    int (*GetUniqueId)(NcclId*) = nullptr;
+    int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool tried = false, ok = false;
+};
+NcclApi g_nccl;
+
+int nccl_load() {
+    if (g_nccl.tried) return g_nccl.ok ? 0 : fail("NCCL library not available (libnccl.so.2)");
+    g_nccl.tried = true;
+    void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) return fail(std::string("dlopen(libnccl.so.2) failed: ") + dlerror());
+    g_nccl.GetUniqueId = (int (*)(NcclId*))dlsym(lib, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(void**, int, NcclId, int))dlsym(lib, "ncclCommInitRank");
+    g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(lib, "ncclAllGather");
+    g_nccl.CommDestroy = (int (*)(void*))dlsym(lib, "ncclCommDestroy");
+    g_nccl.GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
+    g_nccl.ok = g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.AllGather && g_nccl.CommDestroy && g_nccl.GetErrorString;
+    return g_nccl.ok ? 0 : fail("libnccl.so.2 lacks the expected symbols");
+}
+
+int nccl_check(int rc, const char* what) {
+    if (rc == 0) return 0;
+    return fail(std::string(what) + " -> " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "NCCL error"));
+}
+}  // namespace
 
 struct fgnn_handle {
     fgnn_config cfg;
@@ -76,6 +115,8 @@ struct fgnn_handle {
     double* d_shift = nullptr;
     double* d_bounds = nullptr;      // [world + 1], allocated by fgnn_shard_configure
     int launch_pool = 0;             // grid sizing for kernels over the pool (pool capacity, or M)
+    void* nccl_comm = nullptr;       // ncclComm_t of fgnn_comm_init (the halo all-gather inside the step graph)
+    bool nccl_warm = false;
     void* shard_graph_store = nullptr;
     long long shard_epoch = 0;       // bumped by fgnn_shard_configure: invalidates cached graphs
     // per-kernel profiling of one step (fgnn_profile_step)
@@ -379,6 +420,8 @@ extern "C" int fgnn_destroy(fgnn_handle* h) {
     cudaSetDevice(h->cfg.device);
     if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
     if (h->graph) cudaGraphDestroy(h->graph);
+    // the communicator is deliberately not destroyed here: ncclCommDestroy waits for the peers and was observed to
+    // hang at interpreter shutdown when ranks tear down in different orders; process exit reclaims it
     for (void* q : h->allocs) cudaFree(q);
     if (h->d_reward_log) cudaFree(h->d_reward_log);
     delete h;
@@ -936,8 +979,8 @@ struct ShardGraph {
     long long i0 = 0, i1 = 0, i2 = 0, i3 = 0;
     double d = 0;
 };
-static ShardGraph* shard_graphs(fgnn_handle* h) {     // two entries, lazily allocated (begin, end)
-    if (!h->shard_graph_store) h->shard_graph_store = new ShardGraph[2];
+static ShardGraph* shard_graphs(fgnn_handle* h) {     // three entries, lazily allocated (begin, end, whole step)
+    if (!h->shard_graph_store) h->shard_graph_store = new ShardGraph[3];
     return reinterpret_cast<ShardGraph*>(h->shard_graph_store);
 }
 
@@ -1009,6 +1052,69 @@ extern "C" int fgnn_shard_step_end(fgnn_handle* h, const double* recv_buf, int32
     if (!h->binned) return fail("fgnn_shard_step_end: call fgnn_shard_step_begin first");
     ShardGraph& g = shard_graphs(h)[1];
     int rc = run_cached_graph(h, g, recv_buf, nullptr, cap, h->shard_epoch, 0, 0, 0.0, st, [&](cudaStream_t cs) {
+        if (enqueue_shard_unpack(h, recv_buf, cap, cs)) return 1;
+        return enqueue_build(h, 1, cs);
+    });
+    if (rc) return 1;
+    h->binned = false;
+    h->t_host += 1;
+    return 0;
+}
+
+extern "C" int fgnn_comm_unique_id(void* id_128) {
+    if (!id_128) return fail("fgnn_comm_unique_id: null argument");
+    if (nccl_load()) return 1;
+    return nccl_check(g_nccl.GetUniqueId(reinterpret_cast<NcclId*>(id_128)), "ncclGetUniqueId");
+}
+
+extern "C" int fgnn_comm_init(fgnn_handle* h, const void* id_128, int32_t rank, int32_t world) {
+    if (!h || !id_128) return fail("fgnn_comm_init: null argument");
+    if (!h->sharded) return fail("fgnn_comm_init: handle is not sharded");
+    if (world < 1 || rank < 0 || rank >= world) return fail("fgnn_comm_init: bad rank / world");
+    if (h->nccl_comm) return fail("fgnn_comm_init: communicator already initialised");
+    if (nccl_load()) return 1;
+    CK(cudaSetDevice(h->cfg.device));
+    NcclId id;
+    memcpy(&id, id_128, sizeof id);
+    return nccl_check(g_nccl.CommInitRank(&h->nccl_comm, world, id, rank), "ncclCommInitRank");
+}
+
+// One closed-loop step of a rank as ONE CUDA graph: hops + final (with the fused halo pack) -> ncclAllGather of the
+// fixed-capacity record buffers -> unpack + scan/scatter/canon/adjacency.  windows = the headers of `recv_buf` as the
+// previous step left them (same buffer every step: the graph bakes its address).
+extern "C" int fgnn_shard_step(fgnn_handle* h, double* send_buf, double* recv_buf, int32_t cap, void* stream) {
+    if (!h || !h->sharded || !send_buf || !recv_buf) return fail("fgnn_shard_step: bad argument");
+    if (!h->shard_configured) return fail("fgnn_shard_step: call fgnn_shard_configure first");
+    if (!h->nccl_comm) return fail("fgnn_shard_step: call fgnn_comm_init first");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(h->cfg.device));
+    if (h->binned) return fail("fgnn_shard_step: graph not rebuilt since the last step");
+    const int64_t stride = (int64_t)(cap + 1) * SREC;
+    ShardFuse f;
+    memset(&f, 0, sizeof f);
+    f.ctl = h->ctl; f.windows = recv_buf + 1; f.wstride = stride; f.buf = send_buf; f.cap = cap;
+    if (memcmp(&f, &h->fuse_host, sizeof f) != 0) {
+        h->fuse_host = f;
+        CK(cudaMemcpyAsync(h->d_fuse, &h->fuse_host, sizeof f, cudaMemcpyHostToDevice, st));
+    }
+    if (!h->nccl_warm) {
+        // first use: one eager all-gather of the same buffers so that NCCL sets up its channels outside any capture.
+        // `send_buf` still holds what the reset-time exchange gathered into `recv_buf`, so this rewrites the same bytes.
+        if (nccl_check(g_nccl.AllGather(send_buf, recv_buf, (size_t)stride, 8, h->nccl_comm, st), "ncclAllGather (warm-up)")) return 1;
+        CK(cudaStreamSynchronize(st));
+        h->nccl_warm = true;
+    }
+    const int final_grid = h->use_tc ? h->tc_grid_closed : h->final_grid_closed;
+    ShardGraph& g = shard_graphs(h)[2];
+    int rc = run_cached_graph(h, g, recv_buf, send_buf, h->shard_epoch, final_grid, cap, 0, 0.0, st, [&](cudaStream_t cs) {
+        if (enqueue_hops(h, cs)) return 1;
+        k_shard_prepare<<<1, 32, 0, cs>>>(h->ctl, 1);
+        if (launch_check(h, "shard_prepare")) return 1;
+        if (enqueue_final(h, true, 0, cs, true)) return 1;
+        k_shard_header<<<1, 256, 0, cs>>>(h->ctl, send_buf, final_grid);
+        if (launch_check(h, "shard_header")) return 1;
+        if (nccl_check(g_nccl.AllGather(send_buf, recv_buf, (size_t)stride, 8 /* ncclFloat64 */, h->nccl_comm, cs), "ncclAllGather"))
+            return 1;
         if (enqueue_shard_unpack(h, recv_buf, cap, cs)) return 1;
         return enqueue_build(h, 1, cs);
     });

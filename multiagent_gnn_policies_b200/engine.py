@@ -19,7 +19,7 @@ ABI_SYMBOLS = [
     "fgnn_get_aggregated", "fgnn_get_action", "fgnn_export_network_dense", "fgnn_get_csr", "fgnn_get_stats",
     "fgnn_shard_configure", "fgnn_shard_local_step", "fgnn_shard_pack", "fgnn_shard_unpack", "fgnn_shard_step_begin",
     "fgnn_shard_step_end", "fgnn_shard_owned", "fgnn_profile_step", "fgnn_memcpy_sync", "fgnn_launch_count",
-    "fgnn_set_agent_mask", "fgnn_set_dt",
+    "fgnn_set_agent_mask", "fgnn_set_dt", "fgnn_comm_unique_id", "fgnn_comm_init", "fgnn_shard_step",
     "fgnn_trainer_create", "fgnn_trainer_destroy", "fgnn_trainer_param_count", "fgnn_trainer_launch_count",
     "fgnn_trainer_step",
 ]
@@ -98,6 +98,9 @@ def load_library(path=None):
     lib.fgnn_memcpy_sync.argtypes = [vp, vp, ctypes.c_uint64, vp]
     lib.fgnn_launch_count.argtypes = [vp]
     lib.fgnn_launch_count.restype = i64
+    lib.fgnn_comm_unique_id.argtypes = [vp]
+    lib.fgnn_comm_init.argtypes = [vp, vp, i32, i32]
+    lib.fgnn_shard_step.argtypes = [vp, vp, vp, i32, vp]
     lib.fgnn_set_agent_mask.argtypes = [vp, vp, vp]
     lib.fgnn_set_dt.argtypes = [vp, dbl]
     lib.fgnn_trainer_create.argtypes = [i32, i32, i32, i32, ctypes.POINTER(vp)]
@@ -420,6 +423,16 @@ class FlockEngine:
         self._check(self.lib.fgnn_shard_step_end(self._h, _ptr(recv_buf), cap, self.stream))
         self.step_index += 1
 
+    def comm_init(self, unique_id, rank, world):
+        """Collective: create this rank's NCCL communicator from the 128-byte id rank 0 made (``comm_unique_id``)."""
+        buf = ctypes.create_string_buffer(bytes(unique_id), 128)
+        self._check(self.lib.fgnn_comm_init(self._h, ctypes.addressof(buf), int(rank), int(world)))
+
+    def shard_step(self, send_buf, recv_buf, cap):
+        """The whole sharded step as one CUDA graph with the NCCL all-gather inside."""
+        self._check(self.lib.fgnn_shard_step(self._h, _ptr(send_buf), _ptr(recv_buf), cap, self.stream))
+        self.step_index += 1
+
     def shard_owned(self):
         """Currently owned agents (global ids, int32, list order) -- synchronises."""
         ids = np.empty(self.shard_count + self.ghost_capacity, dtype=np.int32)
@@ -440,6 +453,15 @@ class FlockEngine:
 
     def launch_count(self):
         return int(self.lib.fgnn_launch_count(self._h))
+
+
+def comm_unique_id():
+    """128-byte NCCL id (call on rank 0, broadcast to the other ranks, pass to ``FlockEngine.comm_init``)."""
+    lib = load_library()
+    buf = ctypes.create_string_buffer(128)
+    if lib.fgnn_comm_unique_id(ctypes.addressof(buf)) != 0:
+        raise FgnnError(lib.fgnn_last_error().decode())
+    return buf.raw
 
 
 class ActorTrainer:

@@ -105,6 +105,19 @@ class CudaShardBackend:
     def step_end(self, recv, cap):
         self.engine.shard_step_end(recv, cap)
 
+    def init_comm(self, rank, world):
+        """Give the engine its own NCCL communicator (id broadcast through torch.distributed): the step then
+        runs as ONE CUDA graph with the all-gather inside (``step_fused``)."""
+        import torch.distributed as dist
+        from multiagent_gnn_policies_b200.engine import comm_unique_id
+        box = [comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        self.engine.comm_init(box[0], rank, world)
+        self.native_comm = True
+
+    def step_fused(self, send, recv, cap):
+        self.engine.shard_step(send, recv, cap)
+
     def owned(self):
         return self.engine.shard_owned()
 
@@ -175,6 +188,9 @@ class ShardedFlock:
     def step(self):
         """One closed-loop step: local policy + integrator for owned agents, halo exchange, rebuild."""
         stride = (self.cap + 1) * RECORD
+        if getattr(self.backend, "native_comm", False):  # CUDA backend with its own communicator: one graph per step
+            self.backend.step_fused(self.send, self.recv, self.cap)
+            return
         if hasattr(self.backend, "step_begin"):          # CUDA backend: two graph launches around the all-gather
             self.backend.step_begin(self.recv.reshape(-1)[1:], stride, self.send, self.cap)
             self.recv = self.all_gather(self.send)

@@ -35,6 +35,8 @@ def main():
     be.engine.load_state_dict(sd)
     flock = parallel.ShardedFlock(be, rank, world, K, R, cap, parallel.nccl_all_gather(world, cap, be.device))
     flock.reset(x0, ranges)
+    if os.environ.get("FGNN_NATIVE_COMM", "0") == "1":
+        be.init_comm(rank, world)              # one CUDA graph per step with ncclAllGather inside
     for _ in range(steps):
         flock.step()
     torch.cuda.synchronize()
