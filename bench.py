@@ -211,9 +211,16 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        steps = max(1, min(args.steps, 5))
-        warm = max(1, min(args.warmup, 2))
-        cb, sec = run_cpu_reference(args.cpu_sample, steps, warm, args.hidden, args.k, args.n_layers)
+        # exactly --steps timed steps after --warmup untimed ones; the bounded sample (N agents of the same density) is
+        # sized so that the whole run fits ~2 minutes of host time.  The dense algorithm costs ~c N^3 per step (c from one
+        # calibration step); a smaller sample only flatters the reference (its cost per agent grows with N^2).
+        steps, warm = max(1, args.steps), max(0, args.warmup)
+        n_sample = args.cpu_sample
+        if "--cpu-sample" not in sys.argv:
+            _, sec_cal = run_cpu_reference(600, 1, 1, args.hidden, args.k, args.n_layers)
+            c = sec_cal / 600.0 ** 3
+            n_sample = int(min(1500, max(200, (120.0 / (steps + warm) / c) ** (1.0 / 3.0))))
+        cb, sec = run_cpu_reference(n_sample, steps, warm, args.hidden, args.k, args.n_layers)
         line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
                 "steps": steps, "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32 learner / f64 env", "data": "synthetic", "config": config,
