@@ -94,6 +94,7 @@ struct fgnn_handle {
     bool adj_warp_staged = false;    // k_adjacency_t<true>: candidates staged per warp in shared memory
     bool last_hop_separate = false;  // last hop as its own launch instead of inside the final kernel
     bool scan_two_pass = false;      // tile sums in their own launch: the scan proper never waits on another block
+    bool pdl = false;                // programmatic dependent launch between the step kernels
     // tensor-core readout (tcgen05, 3xTF32)
     bool use_tc = false;
     std::vector<uint8_t> tc_host;    // TcLayout pack, host mirror
@@ -142,6 +143,9 @@ static int dalloc(fgnn_handle* h, T** ptr, size_t count, bool zero = true) {
 #ifndef FGNN_ADJ_DEFAULT_WS
 #define FGNN_ADJ_DEFAULT_WS true                 // measured: 120 -> 112 us at N=1M, d~5 (profiles/r1_bench_history.md)
 #endif
+#ifndef FGNN_PDL_DEFAULT
+#define FGNN_PDL_DEFAULT false
+#endif
 #ifndef FGNN_SCAN_TWO_PASS_DEFAULT
 #define FGNN_SCAN_TWO_PASS_DEFAULT true           // measured: 312 -> 294 us/step; blocks spinning on other blocks' status words are slow here
 #endif
@@ -181,6 +185,25 @@ static size_t final_smem_bytes(const fgnn_handle* h) {
 }
 
 static inline int blocks_for(int n, int threads) { return (n + threads - 1) / threads; }
+
+// Launch one of the closed-loop step kernels, with the programmatic-serialization attribute when the handle asks for
+// it (the kernel may then become resident while its predecessor drains; it starts with pdl_prologue()).
+template <typename... KArgs, typename... Args>
+static void launch_step(const fgnn_handle* h, void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st,
+                        Args... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = h->pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 // ---- ABI --------------------------------------------------------------------------------------
 extern "C" const char* fgnn_last_error(void) { return g_err.c_str(); }
@@ -240,6 +263,8 @@ extern "C" int fgnn_create(const fgnn_config* cfg, fgnn_handle** out) {
         // default: on when the expected degree is moderate (edge-capacity hint <= 40 per agent); at larger radii a warp's
         // row ranges outgrow the tile and the per-lane path with its deeper stage is faster (measured, C4 sweep)
         h->adj_warp_staged = mode ? atoi(mode) != 0 : (FGNN_ADJ_DEFAULT_WS && cap_per <= 40);
+        const char* pd = getenv("FGNN_PDL");
+        h->pdl = pd ? atoi(pd) != 0 : FGNN_PDL_DEFAULT;
         const char* tp = getenv("FGNN_SCAN_TWO_PASS");
         h->scan_two_pass = tp ? atoi(tp) != 0 : FGNN_SCAN_TWO_PASS_DEFAULT;
         const char* lh = getenv("FGNN_LAST_HOP_SEPARATE");
@@ -498,23 +523,23 @@ static int enqueue_build(fgnn_handle* h, int advance, cudaStream_t st) {
         if (launch_check(h, "bin")) return 1;
     }
     if (h->scan_two_pass) {
-        k_scan_sums<<<p.n_tiles, SCAN_THREADS, 0, st>>>(p);
+        launch_step(h, k_scan_sums, p.n_tiles, SCAN_THREADS, 0, st, p);
         if (launch_check(h, "scan_sums")) return 1;
     }
-    k_scan<<<p.n_tiles, SCAN_THREADS, 0, st>>>(p, advance, (h->scan_two_pass || p.n_tiles <= h->sm_count * 4) ? 1 : 0,
-                                               h->scan_two_pass ? 1 : 0);
+    launch_step(h, k_scan, p.n_tiles, SCAN_THREADS, 0, st, p, (int)advance,
+                (h->scan_two_pass || p.n_tiles <= h->sm_count * 4) ? 1 : 0, h->scan_two_pass ? 1 : 0);
     if (launch_check(h, "scan")) return 1;
-    k_scatter<<<gb, 256, 0, st>>>(p);
+    launch_step(h, k_scatter, gb, 256, 0, st, p);
     if (launch_check(h, "scatter")) return 1;
-    k_canon<<<gb, 256, 0, st>>>(p);
+    launch_step(h, k_canon, gb, 256, 0, st, p);
     if (launch_check(h, "canon")) return 1;
     if (h->adj_warp_staged) {
         const int stage = h->adj_stage < WS_STAGE ? h->adj_stage : WS_STAGE;
-        k_adjacency_t<true><<<blocks_for(h->launch_pool, ADJ_THREADS), ADJ_THREADS,
-                              (size_t)(stage + 1) * ADJ_THREADS * sizeof(int) + WS_SMEM, st>>>(p, stage);
+        launch_step(h, k_adjacency_t<true>, blocks_for(h->launch_pool, ADJ_THREADS), ADJ_THREADS,
+                    (size_t)(stage + 1) * ADJ_THREADS * sizeof(int) + WS_SMEM, st, p, stage);
     } else {
-        k_adjacency_t<false><<<blocks_for(h->launch_pool, ADJ_THREADS), ADJ_THREADS,
-                               (size_t)h->adj_stage * ADJ_THREADS * sizeof(int), st>>>(p, h->adj_stage);
+        launch_step(h, k_adjacency_t<false>, blocks_for(h->launch_pool, ADJ_THREADS), ADJ_THREADS,
+                    (size_t)h->adj_stage * ADJ_THREADS * sizeof(int), st, p, h->adj_stage);
     }
     if (launch_check(h, "adjacency")) return 1;
     h->binned = false;
@@ -524,7 +549,7 @@ static int enqueue_build(fgnn_handle* h, int advance, cudaStream_t st) {
 
 template <int NB, bool FIRST>
 static void launch_hop(fgnn_handle* h, int j, cudaStream_t st) {
-    k_hop<NB, FIRST><<<blocks_for(h->launch_pool, 256), 256, 0, st>>>(h->p, j);
+    launch_step(h, k_hop<NB, FIRST>, blocks_for(h->launch_pool, 256), 256, 0, st, h->p, j);
 }
 
 static int enqueue_hops(fgnn_handle* h, cudaStream_t st) {
@@ -554,12 +579,12 @@ static int enqueue_final(fgnn_handle* h, bool closed, int write_z, cudaStream_t 
     if (h->use_tc) {
         final_tc_kernel_t fk = final_tc_kernel(p.K, h->HP, closed);
         const int grid = closed ? h->tc_grid_closed : h->tc_grid_open;
-        fk<<<grid, FINAL_THREADS, h->tc_smem, st>>>(p, h->d_tc_weights);
+        launch_step(h, fk, grid, FINAL_THREADS, h->tc_smem, st, p, (const uint8_t*)h->d_tc_weights);
         if (launch_check(h, "final")) return 1;
     } else {
         final_kernel_t fk = final_kernel(p.K, h->HP, closed);
         const int grid = closed ? h->final_grid_closed : h->final_grid_open;
-        fk<<<grid, FINAL_THREADS, h->final_smem, st>>>(p);
+        launch_step(h, fk, grid, FINAL_THREADS, h->final_smem, st, p);
         if (launch_check(h, "final")) return 1;
     }
     if (closed) h->binned = true;

@@ -108,6 +108,7 @@ __device__ __forceinline__ void mlp_ffma(const float (&in)[IN], const float* __r
 
 template <int K, int HP, bool CLOSED>
 __global__ void __launch_bounds__(FINAL_THREADS) k_final(Params p) {
+    pdl_prologue();
     extern __shared__ __align__(16) float smem[];
     WeightLayout wl;
     wl.in0 = F * K; wl.HP = HP; wl.L = p.L;

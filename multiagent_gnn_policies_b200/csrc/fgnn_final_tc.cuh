@@ -131,6 +131,7 @@ __host__ __device__ constexpr int tc_tmem_cols(int HP) { return 2 * HP < 32 ? 32
 
 template <int K, int HP, bool CLOSED>
 __global__ void __launch_bounds__(FINAL_THREADS) k_final_tc(Params p, const uint8_t* __restrict__ tcw) {
+    pdl_prologue();
     static_assert(HP == 16 || HP == 32 || HP == 64, "tensor-core readout supports HP in {16,32,64}");
     constexpr int K0 = (F * K + 7) & ~7;
     constexpr int KA = K0 > HP ? K0 : HP;                  // widest A operand

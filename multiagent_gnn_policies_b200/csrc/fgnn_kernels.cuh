@@ -91,6 +91,16 @@ struct Params {
     int* log_index;
 };
 
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-serialization attribute may become
+// resident while its predecessor drains.  Every such kernel first lets ITS successor do the same, then waits until the
+// predecessor grid has completed and its memory operations are visible.  Without the attribute both are no-ops.
+__device__ __forceinline__ void pdl_prologue() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+
 __host__ __device__ inline int slot_of(int t, int K) { int s = t % K; return s < 0 ? s + K : s; }
 
 // Packed weights (floats): w0[6K][HP] b0[HP] | (L-1) x { wh[HP][HP] bh[HP] } | wl[HP][2] bl[2] (+pad)
@@ -284,6 +294,7 @@ constexpr unsigned FLAG_AGG = 1u << 30, VAL_MASK = (1u << 30) - 1;
 // Two-pass mode, pass 1: the sum of every tile's counts into tile_status (plain ints, no flags).  Pass 2 (k_scan with
 // two_pass = 1) then reads its predecessors' sums without waiting on anybody.
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_sums(Params p) {
+    pdl_prologue();
     __shared__ int s_w[SCAN_THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = p.C + 1;
@@ -311,6 +322,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_sums(Params p) {
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan(Params p, int advance, int static_ids, int two_pass) {
+    pdl_prologue();
     __shared__ int s_tile;
     __shared__ int s_warp[SCAN_ROUNDS][SCAN_THREADS / 32];
     __shared__ int s_excl;
@@ -407,6 +419,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(Params p, int advance, in
 // K_C  scatter agent ids into their cell's slot range (atomic order, canonicalised by K_C2)
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_scatter(Params p) {
+    pdl_prologue();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int a = i < pool_size(p) ? pool_agent(p, i) : -1;
     if (a >= 0) {
@@ -422,6 +435,7 @@ __global__ void __launch_bounds__(256) k_scatter(Params p) {
 // K_C2 canon: order every cell's list by agent id (rank by counting), copy the state next to it.
 //      Makes CSR row order -- and with it every fp32 sum downstream -- run-to-run reproducible.
 __global__ void __launch_bounds__(256) k_canon(Params p) {
+    pdl_prologue();
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     for (int i = s; i <= p.C; i += gridDim.x * blockDim.x) p.cell_count[i] = 0;   // fill counters -> 0 for the next bin
     if (s >= sorted_count(p)) return;
@@ -482,6 +496,7 @@ __device__ __forceinline__ double fast_rcp(double x) {
 // the grid seam or overflow the tile take the per-lane global path.  Neighbour order is identical in both paths.
 template <bool WS>
 __global__ void __launch_bounds__(ADJ_THREADS) k_adjacency_t(Params p, int stage_cap) {
+    pdl_prologue();
     extern __shared__ __align__(16) unsigned char s_adj_raw[];
     int* s_stage = reinterpret_cast<int*>(s_adj_raw);     // [stage_cap][ADJ_THREADS] accepted neighbour ids
     const int tid = threadIdx.x;
@@ -800,6 +815,7 @@ __device__ __forceinline__ void gather_rows(const Params& p, int g, int a, const
 #endif
 template <int NB, bool FIRST>
 __global__ void __launch_bounds__(256, NB == 2 ? FGNN_HOP_MIN_BLOCKS : 1) k_hop(Params p, int j) {
+    pdl_prologue();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= pool_size(p)) return;
     const int a = pool_agent(p, i);

@@ -1,7 +1,7 @@
 """A/B the kernel variants of the closed-loop step on the bench workload (one GPU):
     python scripts/ab_variants.py [N] [steps]
 Variants are selected per engine by environment variables read in fgnn_create (FGNN_ADJ_MODE,
-FGNN_LAST_HOP_SEPARATE).  Every variant must leave the SAME state bit for bit after the same number of steps
+FGNN_LAST_HOP_SEPARATE, FGNN_SCAN_TWO_PASS, FGNN_PDL).  Every variant must leave the SAME state bit for bit after the same number of steps
 (the sums run in the same order); the script checks that, then prints graph-replay ms/step and per-kernel times."""
 import itertools
 import os
@@ -17,7 +17,7 @@ from multiagent_gnn_policies_b200.engine import FlockEngine        # noqa: E402
 
 
 def run(n, steps, env, x0, sd, k=3, hidden=32):
-    for key in ("FGNN_ADJ_MODE", "FGNN_LAST_HOP_SEPARATE", "FGNN_SCAN_TWO_PASS"):
+    for key in ("FGNN_ADJ_MODE", "FGNN_LAST_HOP_SEPARATE", "FGNN_SCAN_TWO_PASS", "FGNN_PDL"):
         os.environ.pop(key, None)
     os.environ.update(env)
     eng = FlockEngine(n_agents=n, k=k, hidden=hidden, n_layers=2, comm_radius=1.0, dt=0.01)
@@ -50,16 +50,16 @@ def main():
     sd, _ = make_weights(32, 3, 2)
     ref_state = None
     print(f"N={n} steps={steps}")
-    for adj, sep, tp in itertools.product("01", "01", "01"):
-        if adj != sep:
+    for adj, sep, tp, pdl in itertools.product("01", "01", "01", "01"):
+        if adj != sep or (pdl == "1" and tp == "0"):
             continue                      # the mixed combinations were measured earlier (profiles/r1_bench_history.md)
-        env = {"FGNN_ADJ_MODE": adj, "FGNN_LAST_HOP_SEPARATE": sep, "FGNN_SCAN_TWO_PASS": tp}
+        env = {"FGNN_ADJ_MODE": adj, "FGNN_LAST_HOP_SEPARATE": sep, "FGNN_SCAN_TWO_PASS": tp, "FGNN_PDL": pdl}
         ms, per, st = run(n, steps, env, x0, sd)
         if ref_state is None:
             ref_state = st
         same = bool(np.array_equal(st, ref_state))
         kern = " ".join(f"{k_}={v * 1e3:.1f}" for k_, v in per.items())
-        print(f"adj_ws={adj} last_sep={sep} scan_two_pass={tp}: {ms * 1e3:.1f} us/step  {n / ms / 1e6:.3f}e9 agent-steps/s  "
+        print(f"adj_ws={adj} last_sep={sep} scan_two_pass={tp} pdl={pdl}: {ms * 1e3:.1f} us/step  {n / ms / 1e6:.3f}e9 agent-steps/s  "
               f"bit-identical={same}  [{kern}] sum={sum(per.values()) * 1e3:.1f}", flush=True)
 
 
