@@ -260,9 +260,10 @@ extern "C" int fgnn_create(const fgnn_config* cfg, fgnn_handle** out) {
     h->adj_stage = (int)(cap_per < 8 ? 8 : cap_per > 64 ? 64 : cap_per);
     {   // warp-staged adjacency: pays when a warp's three row ranges fit its tile (moderate degree); FGNN_ADJ_MODE=0/1 overrides
         const char* mode = getenv("FGNN_ADJ_MODE");
-        // default: on when the expected degree is moderate (edge-capacity hint <= 40 per agent); at larger radii a warp's
-        // row ranges outgrow the tile and the per-lane path with its deeper stage is faster (measured, C4 sweep)
-        h->adj_warp_staged = mode ? atoi(mode) != 0 : (FGNN_ADJ_DEFAULT_WS && cap_per <= 40);
+        // default: on when the expected degree is moderate (edge-capacity hint <= 48 per agent, which includes the
+        // automatic capacity); at larger radii a warp's row ranges outgrow the tile and the per-lane path with its
+        // deeper stage is faster (measured, C4 sweep: R >= 1.5 at density 1.6)
+        h->adj_warp_staged = mode ? atoi(mode) != 0 : (FGNN_ADJ_DEFAULT_WS && cap_per <= 48);
         const char* pd = getenv("FGNN_PDL");
         h->pdl = pd ? atoi(pd) != 0 : FGNN_PDL_DEFAULT;
         const char* tp = getenv("FGNN_SCAN_TWO_PASS");
