@@ -461,8 +461,8 @@ __global__ void __launch_bounds__(256) k_canon(Params p) {
 //      re-scan their tail.
 // ------------------------------------------------------------------------------------------
 constexpr int ADJ_THREADS = 128;
-constexpr int WS_CAP = 64;            // warp-staged variant: candidate slots per grid row and warp
-constexpr int WS_STAGE = 16;          // ... and neighbour ids staged per thread (longer rows re-scan shared memory)
+constexpr int WS_CAP = 48;            // warp-staged variant: candidate slots per grid row and warp
+constexpr int WS_STAGE = 12;          // ... and neighbour ids staged per thread (longer rows re-scan shared memory)
 constexpr size_t WS_SMEM = (size_t)(ADJ_THREADS / 32) * 3 * WS_CAP * (sizeof(double4) + sizeof(int));
 
 // 1/x in float64 from the hardware seed (rcp.approx.ftz.f64: 2^-23) and two Newton steps: within ~1 ulp of the
@@ -495,7 +495,7 @@ __device__ __forceinline__ double fast_rcp(double x) {
 // long_scoreboard 36 %, L1 wavefronts 38 % of peak) become shared-memory reads.  Warps that straddle a row, touch
 // the grid seam or overflow the tile take the per-lane global path.  Neighbour order is identical in both paths.
 template <bool WS>
-__global__ void __launch_bounds__(ADJ_THREADS) k_adjacency_t(Params p, int stage_cap) {
+__global__ void __launch_bounds__(ADJ_THREADS, WS ? 8 : 1) k_adjacency_t(Params p, int stage_cap) {
     pdl_prologue();
     extern __shared__ __align__(16) unsigned char s_adj_raw[];
     int* s_stage = reinterpret_cast<int*>(s_adj_raw);     // [stage_cap][ADJ_THREADS] accepted neighbour ids
