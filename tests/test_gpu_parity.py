@@ -340,3 +340,56 @@ def test_architecture_sweep_against_dense_oracle(k, hidden, n_layers, mean_pooli
             x = flock_env.integrate(x, u, 0.01)
             np.testing.assert_array_equal(eng.get_state(), x)
         eng.close()
+
+
+def test_full_size_one_million_agents():
+    """BASELINE.json's headline size (N = 1M agents on one GPU, K = 3): exact edge set and degrees against the
+    edge-list oracle, features to fp32 rounding, and the size-independent properties of the path -- a symmetric
+    graph without self loops, antisymmetric pair terms that cancel over the flock, an integrator and a reward that
+    equal the numpy expressions on the very actions the engine produced, run-to-run bit reproducibility."""
+    from multiagent_gnn_policies_b200.engine import FlockEngine
+    n, R = 1_000_000, 1.0
+    g = load_golden("ckpt_n100_k3")
+    x0 = flock_env.synthetic_state(n, seed=11, density=1.6)
+
+    def new_engine():
+        e = FlockEngine(n_agents=n, k=3, hidden=32, n_layers=2, comm_radius=R, dt=0.01, edge_capacity=32)
+        e.load_state_dict(g["state_dict"])
+        e.reset(x0)
+        return e
+
+    eng = new_engine()
+    sv, deg, oi, oj = sparse.compute_helpers_sparse(x0, R)
+    assert np.array_equal(eng.get_degrees(), deg)
+    rs, dg, cols, _ = eng.csr()
+    total = int(dg.sum())
+    assert total == eng.stats()["n_edges"] == oi.size
+    rows = np.repeat(np.arange(n, dtype=np.int64), dg)
+    first = np.cumsum(dg, dtype=np.int64) - dg                              # position of each row's first edge in `rows`
+    idx = np.repeat(rs.astype(np.int64), dg) + (np.arange(total, dtype=np.int64) - np.repeat(first, dg))
+    c = cols[idx].astype(np.int64)
+    assert np.all(rows != c)                                                # no self loops
+    fwd = np.sort(rows * n + c)
+    assert np.array_equal(fwd, np.sort(c * n + rows))                       # i in N(j)  <=>  j in N(i)
+    assert np.array_equal(fwd, np.sort(oi.astype(np.int64) * n + oj.astype(np.int64)))      # the oracle's edge set
+    feats = eng.get_features()
+    assert rel_inf(feats, sv.astype(np.float32)) <= TOL_FEATURE
+    f64 = feats.astype(np.float64)
+    assert np.all(np.abs(f64.sum(axis=0)) <= 1e-6 * np.abs(f64).sum(axis=0))   # every pair term appears with both signs
+
+    other = new_engine()
+    x = x0
+    a, a2 = np.empty((n, 2), np.float32), np.empty((n, 2), np.float32)
+    r, r2 = np.empty(1, np.float64), np.empty(1, np.float64)
+    for t in range(3):
+        eng.step(a, r)
+        other.step(a2, r2)
+        assert np.array_equal(a, a2) and r[0] == r2[0]                       # bit-reproducible
+        assert np.all(np.isfinite(a))
+        x = flock_env.integrate(x, a, 0.01)
+        np.testing.assert_array_equal(eng.get_state(), x)                   # the float64 integrator, bit for bit
+        assert r[0] == pytest.approx(flock_env.instant_cost(x), rel=1e-9)
+    np.testing.assert_array_equal(other.get_state(), x)
+    assert not eng.stats()["overflow"] and not other.stats()["overflow"]
+    eng.close()
+    other.close()
