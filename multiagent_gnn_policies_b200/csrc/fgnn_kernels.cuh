@@ -1,7 +1,7 @@
 // fgnn_kernels.cuh -- device code of the flocking-GNN rollout engine (sm_100a).
 //
-// One rollout step =  [bin] -> scan -> scatter -> canon -> adjacency+features -> hop(s) -> final
-// (final = last hop + readout MLP + double integrator + binning of the new positions).
+// One rollout step =  [bin] -> scan_sums -> scan -> scatter -> canon -> adjacency+features -> hop(s) [-> last hop] -> final
+// (final = [last hop +] readout MLP + double integrator + binning of the new positions).
 // See DESIGN.md for the data layout and the per-kernel byte counts.
 #pragma once
 #include <cuda_runtime.h>
