@@ -66,6 +66,11 @@ int nccl_check(int rc, const char* what) {
 }
 }  // namespace
 
+#define FGNN_MAX_CHUNKS 8
+#ifndef FGNN_POLICY_CHUNKS_DEFAULT
+#define FGNN_POLICY_CHUNKS_DEFAULT 4              // measured: e2e 0.664 -> 0.626 ms/step at N=1M (scripts/policy_chunks_check.py)
+#endif
+
 struct fgnn_handle {
     fgnn_config cfg;
     Params p;
@@ -95,6 +100,9 @@ struct fgnn_handle {
     bool last_hop_separate = false;  // last hop as its own launch instead of inside the final kernel
     bool scan_two_pass = false;      // tile sums in their own launch: the scan proper never waits on another block
     bool pdl = false;                // programmatic dependent launch between the step kernels
+    int policy_chunks = 1;           // fgnn_policy to a host buffer: readout chunks overlapped with their D2H copies
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t chunk_event[FGNN_MAX_CHUNKS + 1] = {};
     // tensor-core readout (tcgen05, 3xTF32)
     bool use_tc = false;
     std::vector<uint8_t> tc_host;    // TcLayout pack, host mirror
@@ -264,6 +272,8 @@ extern "C" int fgnn_create(const fgnn_config* cfg, fgnn_handle** out) {
         // automatic capacity); at larger radii a warp's row ranges outgrow the tile and the per-lane path with its
         // deeper stage is faster (measured, C4 sweep: R >= 1.5 at density 1.6)
         h->adj_warp_staged = mode ? atoi(mode) != 0 : (FGNN_ADJ_DEFAULT_WS && cap_per <= 48);
+        const char* pc = getenv("FGNN_POLICY_CHUNKS");
+        h->policy_chunks = pc ? atoi(pc) : FGNN_POLICY_CHUNKS_DEFAULT;
         const char* pd = getenv("FGNN_PDL");
         h->pdl = pd ? atoi(pd) != 0 : FGNN_PDL_DEFAULT;
         const char* tp = getenv("FGNN_SCAN_TWO_PASS");
@@ -449,6 +459,10 @@ extern "C" int fgnn_destroy(fgnn_handle* h) {
     // the communicator is deliberately not destroyed here: ncclCommDestroy waits for the peers and was observed to
     // hang at interpreter shutdown when ranks tear down in different orders; process exit reclaims it
     for (void* q : h->allocs) cudaFree(q);
+    if (h->copy_stream) {
+        cudaStreamDestroy(h->copy_stream);
+        for (cudaEvent_t e : h->chunk_event) if (e) cudaEventDestroy(e);
+    }
     if (h->d_reward_log) cudaFree(h->d_reward_log);
     delete h;
     return 0;
@@ -572,19 +586,24 @@ static int enqueue_hops(fgnn_handle* h, cudaStream_t st) {
     return 0;
 }
 
-static int enqueue_final(fgnn_handle* h, bool closed, int write_z, cudaStream_t st, bool fuse_pack = false) {
+static int enqueue_final(fgnn_handle* h, bool closed, int write_z, cudaStream_t st, bool fuse_pack = false, int tile_lo = 0,
+                         int tile_hi = 0) {
     Params p = h->p;
+    p.tile_lo = tile_lo;
+    p.tile_hi = tile_hi;
     p.write_z_last = write_z;
     p.last_hop_done = (h->last_hop_separate && p.K >= 2) ? 1 : 0;
     p.fuse = fuse_pack ? h->d_fuse : nullptr;
     if (h->use_tc) {
         final_tc_kernel_t fk = final_tc_kernel(p.K, h->HP, closed);
-        const int grid = closed ? h->tc_grid_closed : h->tc_grid_open;
+        int grid = closed ? h->tc_grid_closed : h->tc_grid_open;
+        if (tile_hi > tile_lo && grid > tile_hi - tile_lo) grid = tile_hi - tile_lo;
         launch_step(h, fk, grid, FINAL_THREADS, h->tc_smem, st, p, (const uint8_t*)h->d_tc_weights);
         if (launch_check(h, "final")) return 1;
     } else {
         final_kernel_t fk = final_kernel(p.K, h->HP, closed);
-        const int grid = closed ? h->final_grid_closed : h->final_grid_open;
+        int grid = closed ? h->final_grid_closed : h->final_grid_open;
+        if (tile_hi > tile_lo && grid > tile_hi - tile_lo) grid = tile_hi - tile_lo;
         launch_step(h, fk, grid, FINAL_THREADS, h->final_smem, st, p);
         if (launch_check(h, "final")) return 1;
     }
@@ -691,6 +710,36 @@ extern "C" int fgnn_policy(fgnn_handle* h, float* action, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     CK(cudaSetDevice(h->cfg.device));
     if (enqueue_hops(h, st)) return 1;
+    // Large flock, action wanted in HOST memory: run the readout in chunks of tiles and copy every chunk's actions out
+    // on a second stream while the next chunk computes (the copy, 8 MB at N = 1M, costs twice the kernel).
+    if (!h->sharded && action && h->policy_chunks > 1 && h->p.M >= (1 << 18)) {
+        cudaPointerAttributes attr;
+        const bool on_device = cudaPointerGetAttributes(&attr, action) == cudaSuccess &&
+                               (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged);
+        cudaGetLastError();
+        if (!on_device) {
+            if (!h->copy_stream) {
+                CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+                for (int c = 0; c <= FGNN_MAX_CHUNKS; ++c) CK(cudaEventCreateWithFlags(&h->chunk_event[c], cudaEventDisableTiming));
+            }
+            const int n_tiles = blocks_for(h->p.M, FINAL_THREADS);
+            const int C = h->policy_chunks < FGNN_MAX_CHUNKS ? h->policy_chunks : FGNN_MAX_CHUNKS;
+            const int per = blocks_for(n_tiles, C);
+            for (int c = 0; c < C; ++c) {
+                const int lo = c * per, hi = (c + 1) * per < n_tiles ? (c + 1) * per : n_tiles;
+                if (lo >= hi) break;
+                if (enqueue_final(h, false, 1, st, false, lo, hi)) return 1;
+                CK(cudaEventRecord(h->chunk_event[c], st));
+                CK(cudaStreamWaitEvent(h->copy_stream, h->chunk_event[c], 0));
+                const size_t a0 = (size_t)lo * FINAL_THREADS, a1 = (size_t)hi * FINAL_THREADS < (size_t)h->p.M ? (size_t)hi * FINAL_THREADS : (size_t)h->p.M;
+                CK(cudaMemcpyAsync(action + a0 * 2, h->p.action + a0 * 2, (a1 - a0) * 2 * sizeof(float), cudaMemcpyDeviceToHost,
+                                   h->copy_stream));
+            }
+            CK(cudaEventRecord(h->chunk_event[FGNN_MAX_CHUNKS], h->copy_stream));
+            CK(cudaStreamWaitEvent(st, h->chunk_event[FGNN_MAX_CHUNKS], 0));     // the caller's stream covers the copies
+            return 0;
+        }
+    }
     if (enqueue_final(h, false, 1, st)) return 1;
     if (h->sharded) {           // owned-list order, pool_cap rows
         if (!action) return 0;

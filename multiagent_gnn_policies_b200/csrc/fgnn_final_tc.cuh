@@ -173,7 +173,8 @@ __global__ void __launch_bounds__(FINAL_THREADS) k_final_tc(Params p, const uint
     const int n_tiles = (n_owned + FINAL_THREADS - 1) / FINAL_THREADS;
     double racc[4] = {0, 0, 0, 0};
     long long klo = 0x7fffffffffffffffll, khi = -0x7fffffffffffffffll - 1;     // kept x-interval (sharded, fused pack)
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int tile_end = (p.tile_hi > 0 && p.tile_hi < n_tiles) ? p.tile_hi : n_tiles;     // chunked launches (fgnn_policy)
+    for (int tile = p.tile_lo + blockIdx.x; tile < tile_end; tile += gridDim.x) {
         const int oi = tile * FINAL_THREADS + tid;
         const int a = oi < n_owned ? owned_agent(p, oi) : -1;     // -1: beyond the list or a handed-over slot
         const bool valid = a >= 0;

@@ -49,6 +49,7 @@ struct Params {
     int half_accel;
     int write_z_last;         // final kernel also stores z_{K-1} (debug / fgnn_get_aggregated)
     int last_hop_done;        // z_{K-1} was already written by a separate hop launch: the final kernel reads it
+    int tile_lo, tile_hi;     // final kernel: range of 128-agent tiles of this launch (tile_hi <= 0: all of them)
     unsigned nnz_cap;         // directed-edge capacity per ring slot
     double inv_cell;          // 1 / cell size  (cell size = R * (1 + 2^-20))
     double R2;                // comm_radius^2
