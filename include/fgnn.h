@@ -38,7 +38,8 @@ typedef struct fgnn_config {
     int32_t device;          /* CUDA device ordinal                                           */
     int32_t grid_dim;        /* cells per side of the wrapped cell grid, 0 = auto             */
     int32_t edge_capacity;   /* directed-edge capacity per agent (mean), 0 = auto (48)        */
-    int32_t readout_mode;    /* 0 = auto, 1 = FFMA (CUDA cores), 2 = tensor cores (3xTF32)    */
+    int32_t readout_mode;    /* 0 = auto, 1 = FFMA (CUDA cores), 2 = tensor cores (3xTF32),
+                                3 = experimental two-warp tensor-core readout (unvalidated)    */
     int32_t grid_dim_y;      /* cells along y, 0 = same as grid_dim                           */
     int32_t shard_lo;        /* multi-GPU: first agent this rank owns ...                     */
     int32_t shard_count;     /* ... and how many (0 = all: single-GPU)                        */

@@ -105,6 +105,8 @@ struct fgnn_handle {
     cudaEvent_t chunk_event[FGNN_MAX_CHUNKS + 1] = {};
     // tensor-core readout (tcgen05, 3xTF32)
     bool use_tc = false;
+    bool use_tc2 = false;            // EXPERIMENTAL readout_mode 3: two warps per TMEM lane quadrant (fgnn_final_tc2.cuh)
+    int tc2_grid_closed = 0, tc2_grid_open = 0;
     std::vector<uint8_t> tc_host;    // TcLayout pack, host mirror
     uint8_t* d_tc_weights = nullptr;
     size_t tc_smem = 0;
@@ -170,7 +172,7 @@ typedef void (*dense_kernel_t)(const float*, const float*, float*, const float*,
 namespace fgnn {
 typedef void (*final_tc_kernel_t)(Params, const uint8_t*);
 #define FGNN_DECL(K, HP) final_kernel_t get_final_k##K##_hp##HP(bool closed); dense_kernel_t get_dense_k##K##_hp##HP(); \
-    final_tc_kernel_t get_final_tc_k##K##_hp##HP(bool closed);
+    final_tc_kernel_t get_final_tc_k##K##_hp##HP(bool closed); final_tc_kernel_t get_final_tc2_k##K##_hp##HP(bool closed);
 #define FGNN_DECL_K(K) FGNN_DECL(K, 16) FGNN_DECL(K, 32) FGNN_DECL(K, 64) FGNN_DECL(K, 128)
 FGNN_DECL_K(1) FGNN_DECL_K(2) FGNN_DECL_K(3) FGNN_DECL_K(4)
 }
@@ -185,6 +187,10 @@ static void* kernel_lookup(int K, int HP, int closed_or_dense) {
 static final_kernel_t final_kernel(int K, int HP, bool closed) { return (final_kernel_t)kernel_lookup(K, HP, closed ? 1 : 0); }
 static dense_kernel_t dense_kernel(int K, int HP) { return (dense_kernel_t)kernel_lookup(K, HP, 2); }
 static final_tc_kernel_t final_tc_kernel(int K, int HP, bool closed) { return (final_tc_kernel_t)kernel_lookup(K, HP, closed ? 4 : 3); }
+#define FGNN_TC2_CASE(K) case K: return HP == 32 ? get_final_tc2_k##K##_hp32(closed) : HP == 64 ? get_final_tc2_k##K##_hp64(closed) : nullptr;
+static final_tc_kernel_t final_tc2_kernel(int K, int HP, bool closed) {
+    switch (K) { FGNN_TC2_CASE(1) FGNN_TC2_CASE(2) FGNN_TC2_CASE(3) default: FGNN_TC2_CASE(4) }
+}
 
 static size_t final_smem_bytes(const fgnn_handle* h) {
     WeightLayout wl{F * h->cfg.k, h->HP, h->cfg.n_layers};
@@ -402,6 +408,28 @@ extern "C" int fgnn_create(const fgnn_config* cfg, fgnn_handle** out) {
             (closed ? h->tc_grid_closed : h->tc_grid_open) = grid;
         }
     }
+    if (cfg->readout_mode == 3) {
+        if (!h->use_tc || (h->HP != 32 && h->HP != 64)) { fgnn_destroy(h); return fail("fgnn_create: readout_mode 3 needs hidden in 17..64"); }
+        h->use_tc2 = true;
+        if (p.K >= 2) h->last_hop_separate = true;          // its inputs are plain streaming loads
+        const size_t smem2 = h->tc_smem + 1024;              // + the output partials
+        for (int closed = 0; closed < 2; ++closed) {
+            final_tc_kernel_t fk = final_tc2_kernel(p.K, h->HP, closed != 0);
+            CK(cudaFuncSetAttribute((const void*)fk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            cudaFuncAttributes fa;
+            CK(cudaFuncGetAttributes(&fa, (const void*)fk));
+            int occ = (int)((size_t)prop.sharedMemPerMultiprocessor / (smem2 + 1024));
+            const int occ_reg = 65536 / ((fa.numRegs > 0 ? ((fa.numRegs + 7) & ~7) : 64) * 2 * FINAL_THREADS);
+            if (occ > occ_reg) occ = occ_reg;
+            const int max_by_tmem = 512 / tc_tmem_cols(h->HP);
+            if (occ > max_by_tmem) occ = max_by_tmem;
+            if (occ < 1) occ = 1;
+            int grid = h->sm_count * occ;
+            int tiles = blocks_for(h->sharded ? p.pool_cap : p.n_own, FINAL_THREADS);
+            if (grid > tiles) grid = tiles;
+            (closed ? h->tc2_grid_closed : h->tc2_grid_open) = grid;
+        }
+    }
     *out = h;
     return 0;
 }
@@ -594,7 +622,13 @@ static int enqueue_final(fgnn_handle* h, bool closed, int write_z, cudaStream_t 
     p.write_z_last = write_z;
     p.last_hop_done = (h->last_hop_separate && p.K >= 2) ? 1 : 0;
     p.fuse = fuse_pack ? h->d_fuse : nullptr;
-    if (h->use_tc) {
+    if (h->use_tc2) {
+        final_tc_kernel_t fk = final_tc2_kernel(p.K, h->HP, closed);
+        int grid = closed ? h->tc2_grid_closed : h->tc2_grid_open;
+        if (tile_hi > tile_lo && grid > tile_hi - tile_lo) grid = tile_hi - tile_lo;
+        launch_step(h, fk, grid, 2 * FINAL_THREADS, h->tc_smem + 1024, st, p, (const uint8_t*)h->d_tc_weights);
+        if (launch_check(h, "final")) return 1;
+    } else if (h->use_tc) {
         final_tc_kernel_t fk = final_tc_kernel(p.K, h->HP, closed);
         int grid = closed ? h->tc_grid_closed : h->tc_grid_open;
         if (tile_hi > tile_lo && grid > tile_hi - tile_lo) grid = tile_hi - tile_lo;
@@ -1105,7 +1139,7 @@ extern "C" int fgnn_shard_step_begin(fgnn_handle* h, const double* windows, int6
         h->fuse_host = f;
         CK(cudaMemcpyAsync(h->d_fuse, &h->fuse_host, sizeof f, cudaMemcpyHostToDevice, st));
     }
-    const int final_grid = h->use_tc ? h->tc_grid_closed : h->final_grid_closed;
+    const int final_grid = h->use_tc2 ? h->tc2_grid_closed : h->use_tc ? h->tc_grid_closed : h->final_grid_closed;
     ShardGraph& g = shard_graphs(h)[0];
     int rc = run_cached_graph(h, g, nullptr, send_buf, h->shard_epoch, final_grid, 0, 0, 0.0, st, [&](cudaStream_t cs) {
         if (enqueue_hops(h, cs)) return 1;
@@ -1179,7 +1213,7 @@ extern "C" int fgnn_shard_step(fgnn_handle* h, double* send_buf, double* recv_bu
         CK(cudaStreamSynchronize(st));
         h->nccl_warm = true;
     }
-    const int final_grid = h->use_tc ? h->tc_grid_closed : h->final_grid_closed;
+    const int final_grid = h->use_tc2 ? h->tc2_grid_closed : h->use_tc ? h->tc_grid_closed : h->final_grid_closed;
     ShardGraph& g = shard_graphs(h)[2];
     int rc = run_cached_graph(h, g, recv_buf, send_buf, h->shard_epoch, final_grid, cap, 0, 0.0, st, [&](cudaStream_t cs) {
         if (enqueue_hops(h, cs)) return 1;

@@ -16,11 +16,11 @@ from bench import make_workload, make_weights      # noqa: E402
 from multiagent_gnn_policies_b200.engine import FlockEngine        # noqa: E402
 
 
-def run(n, steps, env, x0, sd, k=3, hidden=32):
+def run(n, steps, env, x0, sd, k=3, hidden=32, readout_mode=0):
     for key in ("FGNN_ADJ_MODE", "FGNN_LAST_HOP_SEPARATE", "FGNN_SCAN_TWO_PASS", "FGNN_PDL"):
         os.environ.pop(key, None)
     os.environ.update(env)
-    eng = FlockEngine(n_agents=n, k=k, hidden=hidden, n_layers=2, comm_radius=1.0, dt=0.01)
+    eng = FlockEngine(n_agents=n, k=k, hidden=hidden, n_layers=2, comm_radius=1.0, dt=0.01, readout_mode=readout_mode)
     eng.load_state_dict(sd)
     eng.reset(x0)
     eng.rollout(40)
@@ -61,6 +61,14 @@ def main():
         kern = " ".join(f"{k_}={v * 1e3:.1f}" for k_, v in per.items())
         print(f"adj_ws={adj} last_sep={sep} scan_two_pass={tp} pdl={pdl}: {ms * 1e3:.1f} us/step  {n / ms / 1e6:.3f}e9 agent-steps/s  "
               f"bit-identical={same}  [{kern}] sum={sum(per.values()) * 1e3:.1f}", flush=True)
+
+
+    if os.environ.get("FGNN_TRY_READOUT3") == "1":
+        # EXPERIMENTAL two-warp readout (readout_mode = 3, csrc/fgnn_final_tc2.cuh): not validated in round 1
+        env = {"FGNN_ADJ_MODE": "1", "FGNN_LAST_HOP_SEPARATE": "1", "FGNN_SCAN_TWO_PASS": "1", "FGNN_PDL": "0"}
+        ms, per, st = run(n, steps, env, x0, sd, readout_mode=3)
+        kern = " ".join(f"{k_}={v * 1e3:.1f}" for k_, v in per.items())
+        print(f"readout_mode=3: {ms * 1e3:.1f} us/step  bit-identical={bool(np.array_equal(st, ref_state))}  [{kern}]", flush=True)
 
 
 if __name__ == "__main__":
