@@ -41,3 +41,23 @@ def test_engine_fails_loudly_without_gpu():
         pytest.skip("GPU present")
     with pytest.raises(engine.FgnnError):
         engine.FlockEngine(n_agents=10)
+
+
+def test_header_compiles_as_plain_c(tmp_path):
+    """The drop-in boundary is a C ABI: include/fgnn.h must be valid C99 (no C++ in the signatures), and every declared
+    entry point must be addressable with the declared prototype."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    names = declared_symbols()
+    body = "\n".join(f"    p[{i}] = (void*)&{n};" for i, n in enumerate(names))
+    src = tmp_path / "abi_check.c"
+    src.write_text('#include "fgnn.h"\n#include <stddef.h>\n'
+                   f"void* fgnn_abi_table[{len(names)}];\n"
+                   "void fgnn_abi_fill(void) {\n    void** p = fgnn_abi_table;\n" + body + "\n}\n"
+                   "size_t fgnn_cfg_size(void) { return sizeof(fgnn_config) + sizeof(fgnn_stats); }\n")
+    out = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-Wno-pedantic", "-I", os.path.join(ROOT, "include"), "-c",
+                          str(src), "-o", str(tmp_path / "abi_check.o")], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
