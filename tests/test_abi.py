@@ -61,3 +61,24 @@ def test_header_compiles_as_plain_c(tmp_path):
     out = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-Wno-pedantic", "-I", os.path.join(ROOT, "include"), "-c",
                           str(src), "-o", str(tmp_path / "abi_check.o")], capture_output=True, text=True)
     assert out.returncode == 0, out.stderr
+
+
+def test_argument_errors_are_reported_without_a_gpu():
+    """Error convention of the boundary: non-zero status + fgnn_last_error() text; argument checks come before any CUDA call."""
+    import ctypes
+    lib = engine.load_library()
+    h = ctypes.c_void_p()
+    assert lib.fgnn_create(None, ctypes.byref(h)) != 0
+    assert b"null" in lib.fgnn_last_error()
+    bad = engine.FgnnConfig(100, 1, 9, 6, 2, 32, 2, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1.0, 0.01, 10.0)       # k = 9
+    assert lib.fgnn_create(ctypes.byref(bad), ctypes.byref(h)) != 0
+    assert b"k must be in 1..4" in lib.fgnn_last_error()
+    bad = engine.FgnnConfig(100, 1, 3, 5, 2, 32, 2, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1.0, 0.01, 10.0)       # n_states = 5
+    assert lib.fgnn_create(ctypes.byref(bad), ctypes.byref(h)) != 0
+    assert b"n_states" in lib.fgnn_last_error()
+    tr = ctypes.c_void_p()
+    assert lib.fgnn_trainer_create(7, 32, 2, 0, ctypes.byref(tr)) != 0
+    assert b"k must be in 1..4" in lib.fgnn_last_error()
+    assert lib.fgnn_trainer_step(None, 1, 1, None, None, None, None, None, 1, 1e-3, 0.9, 0.999, 1e-8, 1, None, None, None) != 0
+    assert lib.fgnn_step(None, None, None, None) != 0 and lib.fgnn_policy(None, None, None) != 0
+    assert lib.fgnn_destroy(None) == 0 and lib.fgnn_trainer_destroy(None) == 0       # destroying nothing is fine
