@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from multiagent_gnn_policies_b200 import parallel                 # noqa: E402
 from multiagent_gnn_policies_b200.engine import FlockEngine       # noqa: E402
-from oracle import flock_env                                      # noqa: E402  (workload generator only)
+from bench import make_workload                                   # noqa: E402
 
 
 def main():
@@ -25,7 +25,7 @@ def main():
     n_total, steps, K, R = 200_000, 60, 3, 1.0
     g = np.load(os.path.join(ROOT, "tests", "golden", "ckpt_n100_k3.npz"))
     sd = {k[3:]: g[k] for k in g.files if k.startswith("sd.")}
-    x0 = flock_env.synthetic_state(n_total, seed=5, density=1.6)
+    x0 = make_workload(n_total, seed=5)
     x0 = x0[np.argsort(x0[:, 0], kind="stable")]
     ranges = parallel.shard_ranges(n_total, world)
     lo, cnt = ranges[rank]

@@ -1,3 +1,4 @@
+"""Debugging aid (a checker, hence under tests/): large-N engine run printed next to the edge-list oracle, step by step."""
 import sys, numpy as np, torch
 sys.path.insert(0, '.')
 from oracle import flock_env, learner, sparse
