@@ -13,7 +13,7 @@ arithmetic / fp64 environment arithmetic, synthetic data, random-init or shipped
 Prints ONE JSON line (rank 0).  `value` = device-resident throughput (CUDA-graph rollout);
 `e2e` = the same metric through the reference-facing calls with HOST buffers every step
 (select_action -> host, env.step(action from host)); `roofline` = dominant kernel vs measured HBM
-peak; `cpu_baseline` = the reference algorithm (dense numpy/oracle port) timed on this box's cores.
+peak; `cpu_baseline` = the reference's own learner code (oracle/_ref, unmodified) timed on this box's cores.
 """
 import argparse
 import json
@@ -149,38 +149,106 @@ def measured_peaks():
 
 
 # ---------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the reference ALGORITHM (dense N x N GSO products + dense all-pairs
-# env) restated in numpy (oracle/), timed on the host cores over a bounded sample of the workload.
+# reference arm / cpu baseline: the reference's OWN CPU implementation of the path --
+# MultiAgentStateWithDelay (learner/state_with_delay.py:6-53) + DAGGER.select_action
+# (learner/gnn_dagger.py:55-72) + Actor.forward (learner/actor.py:45-86), UNMODIFIED, from oracle/_ref/
+# (staged by `python -m oracle.make_ref`; kind = "reference") -- driven by the spec env (oracle/flock_env.py:
+# gym_flock is not installed anywhere here).  Without oracle/_ref the numpy port of the same dense algorithm
+# (oracle/learner.py) is timed instead (kind = "port").  The dense algorithm holds 2 K N^2 floats per state, so
+# it is timed on bounded samples of the workload (same density): N = 100 (the reference's own cfg/dagger.cfg)
+# and N = 1000; `value` is the BEST agent-steps/s over samples and thread counts {1, all host cores}.
 # ---------------------------------------------------------------------------------------------
-def run_cpu_reference(n_sample, steps, warmup, hidden, k, n_layers, seed=11):
-    from oracle import flock_env, learner
-    sd, _ = make_weights(hidden, k, n_layers)
-    layers = learner.weights_from_state_dict(sd)
-    x = make_workload(n_sample, seed=seed)
-    state = None
-    R2 = 1.0
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
 
-    def one_step(x, state):
-        sv, sn, _, _ = flock_env.compute_helpers(x, R2)
-        state = learner.DelayState((sv, sn), prev_state=state, k=k, with_curr_gso=True)   # reference builds curr_gso too
-        a = learner.select_action(layers, state)
-        return flock_env.integrate(x, a, 0.01), state
 
-    for _ in range(warmup):
-        x, state = one_step(x, state)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        x, state = one_step(x, state)
-    dt = time.perf_counter() - t0
+def _reference_learner(n_agents, hidden, k, n_layers, sd):
+    """The unmodified reference DAGGER object (CPU) with the bench weights, or None if oracle/_ref is absent."""
+    if not os.path.exists(os.path.join(REF_DIR, "learner", "gnn_dagger.py")):
+        return None
+    import configparser
+    import importlib
+    import torch
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    gd = importlib.import_module("learner.gnn_dagger")
+    swd = importlib.import_module("learner.state_with_delay")
+    cp = configparser.ConfigParser()
+    cp.read(os.path.join(REF_DIR, "cfg", "dagger.cfg"))
+    args = cp[cp.default_section]
+    args["n_agents"], args["hidden_size"], args["k"], args["n_layers"] = str(n_agents), str(hidden), str(k), str(n_layers)
+    device = torch.device("cpu")
+    learner = gd.DAGGER(device, args)
+    learner.actor.load_state_dict({key: torch.as_tensor(np.asarray(v)) for key, v in sd.items()})
+    return learner, swd.MultiAgentStateWithDelay, args, device
+
+
+def _time_reference(n_sample, steps, warmup, hidden, k, n_layers, threads, seed=11):
+    """(seconds per step, kind) of the host loop of learner/gnn_dagger.py:196-201 at N = n_sample with `threads` threads."""
+    import torch
+    from oracle import flock_env, learner as port
     try:
-        from threadpoolctl import threadpool_info
-        cores = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+        from threadpoolctl import threadpool_limits
     except Exception:
-        cores = os.cpu_count() or 1
-    return {"value": n_sample * steps / dt, "unit": UNIT, "cores": int(cores), "kind": "port",
-            "sample": f"dense oracle port of the reference algorithm (all-pairs float64 env + dense NxN GSO products, "
-                      f"numpy), N={n_sample} of the same density, {steps} steps after {warmup} warm-up; "
-                      f"{dt / steps * 1e3:.1f} ms/step; host has {os.cpu_count()} cpus"}, dt / steps
+        threadpool_limits = None
+    sd, _ = make_weights(hidden, k, n_layers)
+    torch.set_num_threads(int(threads))
+    ref = _reference_learner(n_sample, hidden, k, n_layers, sd)
+    x = make_workload(n_sample, seed=seed)
+    R2, dt_env = 1.0, 0.01
+    if ref is not None:
+        dagger, State, args, device = ref
+        kind = "reference"
+
+        def one_step(x, state):
+            sv, sn, _, _ = flock_env.compute_helpers(x, R2)                         # env side: spec env (gym_flock absent)
+            state = State(device, args, (sv, sn), prev_state=state)                # state_with_delay.py:6-53
+            a = dagger.select_action(state).cpu().numpy()                          # gnn_dagger.py:55-72, :161
+            return flock_env.integrate(x, a, dt_env), state
+    else:
+        layers = port.weights_from_state_dict(sd)
+        kind = "port"
+
+        def one_step(x, state):
+            sv, sn, _, _ = flock_env.compute_helpers(x, R2)
+            state = port.DelayState((sv, sn), prev_state=state, k=k, with_curr_gso=True)
+            return flock_env.integrate(x, port.select_action(layers, state), dt_env), state
+
+    def loop():
+        xx, state = x, None
+        for _ in range(warmup):
+            xx, state = one_step(xx, state)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            xx, state = one_step(xx, state)
+        return (time.perf_counter() - t0) / steps
+
+    if threadpool_limits is not None:
+        with threadpool_limits(limits=int(threads)):
+            return loop(), kind
+    return loop(), kind
+
+
+def run_cpu_reference(samples, steps, warmup, hidden, k, n_layers, seed=11):
+    """Times the reference path on each N of `samples` with 1 thread and with every host core; returns
+    (cpu_baseline dict, seconds per step of the best cell, N of the best cell)."""
+    ncpu = os.cpu_count() or 1
+    cells, best = [], None
+    for n in samples:
+        for th in sorted({1, ncpu}):
+            sec, kind = _time_reference(n, steps, warmup, hidden, k, n_layers, th, seed)
+            cell = {"n_agents": n, "threads": th, "ms_per_step": sec * 1e3, "agent_steps_per_s": n / sec}
+            cells.append(cell)
+            if best is None or cell["agent_steps_per_s"] > best["agent_steps_per_s"]:
+                best = cell
+    what = ("UNMODIFIED reference learner from oracle/_ref (MultiAgentStateWithDelay + DAGGER.select_action, torch CPU)"
+            if kind == "reference" else "numpy port of the reference's dense algorithm (oracle/learner.py; oracle/_ref absent)")
+    sample = (f"{what} + spec env (oracle/flock_env.py, float64 all-pairs); best cell: N={best['n_agents']} agents of the "
+              f"same density, {best['threads']} thread(s), {steps} steps after {warmup} warm-up, "
+              f"{best['ms_per_step']:.2f} ms/step; cells tried (N, threads, agent-steps/s): "
+              + ", ".join(f"({c['n_agents']}, {c['threads']}, {c['agent_steps_per_s']:.3g})" for c in cells)
+              + f"; host has {ncpu} cpus")
+    return ({"value": best["agent_steps_per_s"], "unit": UNIT, "cores": int(best["threads"]), "kind": kind,
+             "sample": sample, "cells": cells}, best["ms_per_step"] * 1e-3, best["n_agents"])
 
 
 def main():
@@ -194,7 +262,7 @@ def main():
     ap.add_argument("--k", type=int, default=3)
     ap.add_argument("--n-layers", type=int, default=2)
     ap.add_argument("--radius", type=float, default=1.0)
-    ap.add_argument("--cpu-sample", type=int, default=1500, help="N of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="N of the bounded CPU-baseline sample (0: N=100 and N=1000)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer e2e loop (default: min(steps, 50))")
     args = ap.parse_args()
@@ -211,16 +279,13 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        # exactly --steps timed steps after --warmup untimed ones; the bounded sample (N agents of the same density) is
-        # sized so that the whole run fits ~2 minutes of host time.  The dense algorithm costs ~c N^3 per step (c from one
-        # calibration step); a smaller sample only flatters the reference (its cost per agent grows with N^2).
+        # exactly --steps timed steps after --warmup untimed ones, per cell (sample size x thread count); a run at the
+        # driver's --steps 20 --warmup 5 takes well under a minute of host time
         steps, warm = max(1, args.steps), max(0, args.warmup)
-        n_sample = args.cpu_sample
-        if "--cpu-sample" not in sys.argv:
-            _, sec_cal = run_cpu_reference(600, 1, 1, args.hidden, args.k, args.n_layers)
-            c = sec_cal / 600.0 ** 3
-            n_sample = int(min(1500, max(200, (120.0 / (steps + warm) / c) ** (1.0 / 3.0))))
-        cb, sec = run_cpu_reference(n_sample, steps, warm, args.hidden, args.k, args.n_layers)
+        samples = [args.cpu_sample] if args.cpu_sample > 0 else [100, 1000]
+        cb, sec, n_best = run_cpu_reference(samples, steps, warm, args.hidden, args.k, args.n_layers)
+        config = dict(config, workload=f"reference sample N={n_best} agents (dense reference path, cells tried N={samples}; the "
+                                       f"dense (K,N,N) operators of N={args.n_agents} do not fit any host) of: " + workload)
         line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
                 "steps": steps, "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32 learner / f64 env", "data": "synthetic", "config": config,
@@ -351,7 +416,8 @@ def main():
 
     cb = None
     if not args.no_cpu_baseline:
-        cb, _ = run_cpu_reference(args.cpu_sample, 3, 1, args.hidden, args.k, args.n_layers)
+        cb, _, _ = run_cpu_reference([args.cpu_sample] if args.cpu_sample > 0 else [100, 1000], 5, 2, args.hidden, args.k,
+                                     args.n_layers)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -44,11 +44,16 @@ typedef struct fgnn_config {
     int32_t shard_lo;        /* multi-GPU: first agent this rank owns ...                     */
     int32_t shard_count;     /* ... and how many (0 = all: single-GPU)                        */
     int32_t ghost_capacity;  /* multi-GPU: max agents received from other ranks per step      */
-    int32_t reserved0;
+    int32_t flags;           /* FGNN_FLAG_* bits, 0 = defaults                                */
     double  comm_radius;     /* R                                (cfg key comm_radius)        */
     double  dt;              /*                                  (cfg key dt)                 */
     double  action_scalar;   /* gym_flock gain, 10.0                                          */
 } fgnn_config;
+
+/* fgnn_config.flags */
+#define FGNN_FLAG_CSR_TAIL_ONLY 1   /* keep CSR rows only for agents with more than 8 neighbours (the first 8 of every
+                                       row always sit in the per-agent ELL head): fgnn_get_csr is then unavailable,
+                                       every other entry point works unchanged.  Saves 4*deg bytes per agent-step. */
 
 typedef struct fgnn_stats {
     int64_t step;            /* index t of the current graph (0 right after reset)            */

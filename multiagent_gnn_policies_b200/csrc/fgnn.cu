@@ -2,6 +2,7 @@
 #define FGNN_MAIN_TU 1
 #include "fgnn_kernels.cuh"
 #include "fgnn_final_tc.cuh"
+#include "fgnn_tile.cuh"
 #include "../../include/fgnn.h"
 
 #include <dlfcn.h>
@@ -100,6 +101,9 @@ struct fgnn_handle {
     bool last_hop_separate = false;  // last hop as its own launch instead of inside the final kernel
     bool scan_two_pass = false;      // tile sums in their own launch: the scan proper never waits on another block
     bool pdl = false;                // programmatic dependent launch between the step kernels
+    bool tile_mode = false;          // k_tile: adjacency + features + first hop fused per cell tile (fgnn_tile.cuh)
+    TileGeom geo;                    // its geometry and fp32 pre-filter thresholds
+    int tile_grid = 0;
     int policy_chunks = 1;           // fgnn_policy to a host buffer: readout chunks overlapped with their D2H copies
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t chunk_event[FGNN_MAX_CHUNKS + 1] = {};
@@ -296,6 +300,42 @@ extern "C" int fgnn_create(const fgnn_config* cfg, fgnn_handle** out) {
     p.dt = cfg->dt;
     p.gain = cfg->action_scalar;
     p.n_tiles = blocks_for(p.C + 1, SCAN_TILE);
+    {   // tile-fused adjacency + first hop (FGNN_STEP_MODE=0 selects the separate kernels of round 1)
+        const char* sm = getenv("FGNN_STEP_MODE");
+        const char* etw = getenv("FGNN_TILE_W");
+        const char* eth = getenv("FGNN_TILE_H");
+        int tw = etw ? atoi(etw) : 16, th = eth ? atoi(eth) : 8;
+        if (tw > TL_TXMAX) tw = TL_TXMAX;
+        if (th > TL_TYMAX) th = TL_TYMAX;
+        if (tw > G - 4) tw = G - 4;               // a window (tile + two-cell halo) never covers a grid cell twice
+        if (th > Gy - 4) th = Gy - 4;
+        h->tile_mode = (sm ? atoi(sm) != 0 : true) && tw >= 1 && th >= 1;
+        memset(&h->geo, 0, sizeof h->geo);
+        if (h->tile_mode) {
+            TileGeom& ge = h->geo;
+            ge.tw = tw; ge.th = th;
+            ge.ntx = blocks_for(G, tw); ge.nty = blocks_for(Gy, th);
+            h->tile_grid = ge.ntx * ge.nty * cfg->n_episodes;
+            // fp32 pre-filter on window-relative coordinates (|coordinate| <= E).  With u = 2^-24: every coordinate carries
+            // u E, a difference u (2 E + |d|), so for r2 <= 4 R^2 the fp32 r2 is within u (16 R E + 24 R^2) of the float64
+            // value; twice that is the margin.  Pairs inside the margin take the float64 test.
+            const double cell = 1.0 / p.inv_cell, R = cfg->comm_radius;
+            const double E = ((tw > th ? tw : th) + 5) * cell;
+            const double margin = std::ldexp(16.0 * R * E + 24.0 * R * R, -23);
+            ge.far32 = (float)E;
+            ge.lo32 = std::nextafterf((float)(p.R2 - margin), -INFINITY);
+            ge.hi32 = std::nextafterf((float)(p.R2 + margin), INFINITY);
+            ge.csr_tail_only = (cfg->flags & FGNN_FLAG_CSR_TAIL_ONLY) ? 1 : 0;
+            CK(cudaFuncSetAttribute((const void*)k_tile<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(1)));
+            CK(cudaFuncSetAttribute((const void*)k_tile<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(2)));
+            CK(cudaFuncSetAttribute((const void*)k_tile<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(3)));
+            CK(cudaFuncSetAttribute((const void*)k_tile<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(4)));
+            h->last_hop_separate = true;          // the final kernel never gathers in this mode
+        } else if (cfg->flags & FGNN_FLAG_CSR_TAIL_ONLY) {
+            delete h;
+            return fail("fgnn_create: FGNN_FLAG_CSR_TAIL_ONLY needs the tile kernel (grid of at least 5 x 5 cells, FGNN_STEP_MODE != 0)");
+        }
+    }
 
     const size_t M = p.M, K = p.K;
     int rc = 0;
@@ -576,6 +616,19 @@ static int enqueue_build(fgnn_handle* h, int advance, cudaStream_t st) {
     if (launch_check(h, "scatter")) return 1;
     launch_step(h, k_canon, gb, 256, 0, st, p);
     if (launch_check(h, "canon")) return 1;
+    if (h->tile_mode) {
+        const size_t smem = tile_smem_bytes(p.K);
+        switch (p.K) {
+            case 1: launch_step(h, k_tile<1>, h->tile_grid, TL_THREADS, smem, st, p, h->geo); break;
+            case 2: launch_step(h, k_tile<2>, h->tile_grid, TL_THREADS, smem, st, p, h->geo); break;
+            case 3: launch_step(h, k_tile<3>, h->tile_grid, TL_THREADS, smem, st, p, h->geo); break;
+            default: launch_step(h, k_tile<4>, h->tile_grid, TL_THREADS, smem, st, p, h->geo); break;
+        }
+        if (launch_check(h, "tile")) return 1;
+        h->binned = false;
+        if (advance) h->t_host += 1;
+        return 0;
+    }
     if (h->adj_warp_staged) {
         const int stage = h->adj_stage < WS_STAGE ? h->adj_stage : WS_STAGE;
         launch_step(h, k_adjacency_t<true>, blocks_for(h->launch_pool, ADJ_THREADS), ADJ_THREADS,
@@ -597,8 +650,8 @@ static void launch_hop(fgnn_handle* h, int j, cudaStream_t st) {
 
 static int enqueue_hops(fgnn_handle* h, cudaStream_t st) {
     Params& p = h->p;
-    for (int j = 0; j + 2 < p.K; ++j) {     // hops 0 .. K-3 ; hop K-2 lives in the final kernel (or below)
-        const int nb = p.K - 1 - j;
+    for (int j = h->tile_mode ? 1 : 0; j + 2 < p.K; ++j) {     // hops 0 .. K-3 ; hop K-2 lives in the final kernel (or below)
+        const int nb = p.K - 1 - j;                          // (tile mode: hop 0 was done by k_tile when the graph was built)
         if (nb == 3) launch_hop<3, true>(h, j, st);                   // K = 4, hop 0
         else if (nb == 2 && j == 0) launch_hop<2, true>(h, j, st);    // K = 3, hop 0
         else if (nb == 2) launch_hop<2, false>(h, j, st);             // K = 4, hop 1
@@ -607,6 +660,7 @@ static int enqueue_hops(fgnn_handle* h, cudaStream_t st) {
     }
     if (h->last_hop_separate && p.K >= 2) {  // tap K-1 through graph t-(K-2), written to zbuf[K-1] for the final kernel
         const int j = p.K - 2;
+        if (j == 0 && h->tile_mode) return 0;                // K = 2: the only hop is the first one
         if (j == 0) launch_hop<1, true>(h, j, st);
         else launch_hop<1, false>(h, j, st);
         if (launch_check(h, "hop_last")) return 1;
@@ -943,6 +997,7 @@ extern "C" int fgnn_export_network_dense(fgnn_handle* h, int32_t age, float* out
 extern "C" int fgnn_get_csr(fgnn_handle* h, int32_t age, const uint32_t** row_start, const int32_t** deg,
                             const int32_t** cols, const float** src_scale) {
     if (!h) return fail("fgnn_get_csr: null handle");
+    if (h->geo.csr_tail_only) return fail("fgnn_get_csr: the handle keeps CSR rows only for long rows (FGNN_FLAG_CSR_TAIL_ONLY)");
     int g;
     if (age_slot(h, age, &g)) return 1;
     const size_t M = h->p.M;

@@ -1057,8 +1057,9 @@ __global__ void k_export_dense(Params p, int g, float* __restrict__ out) {
     const int d = p.deg[(size_t)g * p.M + a];
     const float sc = p.sinv[(size_t)g * p.M + a];
     const int* cols = p.cols + (size_t)g * p.nnz_cap + rs;
+    const int* head = p.ell + ((size_t)g * p.M + a) * ELLW;      // the first ELLW neighbours (CSR rows may hold long rows only)
     float* row = out + ((size_t)ep * p.N + i) * p.N;
-    for (int e = 0; e < d; ++e) row[cols[e] % p.N] = sc;
+    for (int e = 0; e < d; ++e) row[(e < ELLW ? head[e] : cols[e]) % p.N] = sc;
 }
 
 

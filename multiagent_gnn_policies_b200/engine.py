@@ -25,6 +25,9 @@ ABI_SYMBOLS = [
 ]
 
 
+FLAG_CSR_TAIL_ONLY = 1          # include/fgnn.h FGNN_FLAG_CSR_TAIL_ONLY
+
+
 class FgnnConfig(ctypes.Structure):
     _fields_ = [
         ("n_agents", ctypes.c_int32), ("n_episodes", ctypes.c_int32), ("k", ctypes.c_int32),
@@ -32,7 +35,7 @@ class FgnnConfig(ctypes.Structure):
         ("n_layers", ctypes.c_int32), ("mean_pooling", ctypes.c_int32), ("half_accel_term", ctypes.c_int32),
         ("device", ctypes.c_int32), ("grid_dim", ctypes.c_int32), ("edge_capacity", ctypes.c_int32),
         ("readout_mode", ctypes.c_int32), ("grid_dim_y", ctypes.c_int32), ("shard_lo", ctypes.c_int32),
-        ("shard_count", ctypes.c_int32), ("ghost_capacity", ctypes.c_int32), ("reserved0", ctypes.c_int32),
+        ("shard_count", ctypes.c_int32), ("ghost_capacity", ctypes.c_int32), ("flags", ctypes.c_int32),
         ("comm_radius", ctypes.c_double), ("dt", ctypes.c_double), ("action_scalar", ctypes.c_double),
     ]
 
@@ -144,7 +147,7 @@ class FlockEngine:
     def __init__(self, n_agents, k=3, hidden=32, n_layers=2, comm_radius=1.0, dt=0.01, n_episodes=1,
                  device=0, action_scalar=10.0, mean_pooling=True, half_accel_term=True, grid_dim=0,
                  edge_capacity=0, readout_mode=0, n_states=6, n_actions=2, stream=None, grid_dim_y=0,
-                 shard_lo=0, shard_count=0, ghost_capacity=0):
+                 shard_lo=0, shard_count=0, ghost_capacity=0, csr_tail_only=False):
         import torch  # device memory + streams only
         if not torch.cuda.is_available():
             raise FgnnError("no CUDA device: the rollout engine has no CPU fallback")
@@ -161,7 +164,7 @@ class FlockEngine:
         cfg = FgnnConfig(self.n_agents, self.n_episodes, self.k, self.n_states, self.n_actions, self.hidden,
                          self.n_layers, int(bool(mean_pooling)), int(bool(half_accel_term)), self.device_index,
                          int(grid_dim), int(edge_capacity), int(readout_mode), int(grid_dim_y), int(shard_lo),
-                         int(shard_count), int(ghost_capacity), 0,
+                         int(shard_count), int(ghost_capacity), FLAG_CSR_TAIL_ONLY if csr_tail_only else 0,
                          self.comm_radius, self.dt, self.action_scalar)
         self.shard_lo, self.shard_count, self.ghost_capacity = int(shard_lo), int(shard_count), int(ghost_capacity)
         # rows of the action arrays policy()/integrate() exchange: all agents, or (sharded) the list capacity

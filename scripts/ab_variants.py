@@ -1,7 +1,7 @@
 """A/B the kernel variants of the closed-loop step on the bench workload (one GPU):
     python scripts/ab_variants.py [N] [steps]
-Variants are selected per engine by environment variables read in fgnn_create (FGNN_ADJ_MODE,
-FGNN_LAST_HOP_SEPARATE, FGNN_SCAN_TWO_PASS, FGNN_PDL).  Every variant must leave the SAME state bit for bit after the same number of steps
+Variants are selected per engine by environment variables read in fgnn_create (FGNN_STEP_MODE, FGNN_TILE_W/H,
+FGNN_ADJ_MODE, FGNN_LAST_HOP_SEPARATE, FGNN_SCAN_TWO_PASS, FGNN_PDL).  Every variant must leave the SAME state bit for bit after the same number of steps
 (the sums run in the same order); the script checks that, then prints graph-replay ms/step and per-kernel times."""
 import itertools
 import os
@@ -17,10 +17,12 @@ from multiagent_gnn_policies_b200.engine import FlockEngine        # noqa: E402
 
 
 def run(n, steps, env, x0, sd, k=3, hidden=32, readout_mode=0):
-    for key in ("FGNN_ADJ_MODE", "FGNN_LAST_HOP_SEPARATE", "FGNN_SCAN_TWO_PASS", "FGNN_PDL"):
+    for key in ("FGNN_ADJ_MODE", "FGNN_LAST_HOP_SEPARATE", "FGNN_SCAN_TWO_PASS", "FGNN_PDL", "FGNN_STEP_MODE", "FGNN_TILE_W",
+                "FGNN_TILE_H"):
         os.environ.pop(key, None)
     os.environ.update(env)
-    eng = FlockEngine(n_agents=n, k=k, hidden=hidden, n_layers=2, comm_radius=1.0, dt=0.01, readout_mode=readout_mode)
+    eng = FlockEngine(n_agents=n, k=k, hidden=hidden, n_layers=2, comm_radius=1.0, dt=0.01, readout_mode=readout_mode,
+                      csr_tail_only=env.get("FGNN_STEP_MODE", "1") != "0" and os.environ.get("FGNN_AB_FULL_CSR") != "1")
     eng.load_state_dict(sd)
     eng.reset(x0)
     eng.rollout(40)
@@ -50,16 +52,21 @@ def main():
     sd, _ = make_weights(32, 3, 2)
     ref_state = None
     print(f"N={n} steps={steps}")
-    for adj, sep, tp, pdl in itertools.product("01", "01", "01", "01"):
-        if adj != sep or (pdl == "1" and tp == "0"):
-            continue                      # the mixed combinations were measured earlier (profiles/r1_bench_history.md)
-        env = {"FGNN_ADJ_MODE": adj, "FGNN_LAST_HOP_SEPARATE": sep, "FGNN_SCAN_TWO_PASS": tp, "FGNN_PDL": pdl}
+    # round-1 step (separate adjacency / hop kernels) first: it defines the reference bits
+    variants = [{"FGNN_STEP_MODE": "0"}]
+    tiles = os.environ.get("FGNN_AB_TILES", "16x8,12x8,16x6,24x6,8x8,32x4,16x4").split(",")
+    for tl in tiles:
+        w, h_ = tl.split("x")
+        variants.append({"FGNN_STEP_MODE": "1", "FGNN_TILE_W": w, "FGNN_TILE_H": h_})
+    variants.append({"FGNN_STEP_MODE": "1", "FGNN_PDL": "1"})
+    for env in variants:
         ms, per, st = run(n, steps, env, x0, sd)
         if ref_state is None:
             ref_state = st
         same = bool(np.array_equal(st, ref_state))
         kern = " ".join(f"{k_}={v * 1e3:.1f}" for k_, v in per.items())
-        print(f"adj_ws={adj} last_sep={sep} scan_two_pass={tp} pdl={pdl}: {ms * 1e3:.1f} us/step  {n / ms / 1e6:.3f}e9 agent-steps/s  "
+        tag = " ".join(f"{k_[5:].lower()}={v}" for k_, v in env.items())
+        print(f"{tag}: {ms * 1e3:.1f} us/step  {n / ms / 1e6:.3f}e9 agent-steps/s  "
               f"bit-identical={same}  [{kern}] sum={sum(per.values()) * 1e3:.1f}", flush=True)
 
 
