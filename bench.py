@@ -460,7 +460,11 @@ def run_sharded(args, rank, world, local_rank, N, side, sd, weights_note, edge_c
     bounds = np.array([-parallel.INF] + [q * side for q in range(1, world)] + [parallel.INF])
     frame_vx = float(np.random.default_rng(11).uniform(-3.0, 3.0, size=(2,))[0])       # the flock's common velocity bias
     flock.reset(x_global, ranges, bounds=bounds, frame_velocity=frame_vx)
-    if os.environ.get("FGNN_NATIVE_COMM", "0") == "1":
+    halo = os.environ.get("FGNN_HALO", "p2p")
+    if halo == "p2p":
+        # default: halo records stored straight into the peers' inboxes over NVLink (CUDA-IPC), one CUDA graph per step
+        flock.enable_p2p(parallel.torch_all_gather_object(world))
+    elif os.environ.get("FGNN_NATIVE_COMM", "0") == "1" or halo == "native":
         # opt-in: the all-gather inside ONE step graph on the engine's own communicator (fgnn_shard_step).  Measured at 2
         # GPUs: 5.45e9 vs 5.50e9 agent-steps/s for the default (torch.distributed between two graph halves) -- the
         # sharded step's extra ~70 us is not the collective's launch path -- so the simpler default stays.

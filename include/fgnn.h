@@ -38,8 +38,7 @@ typedef struct fgnn_config {
     int32_t device;          /* CUDA device ordinal                                           */
     int32_t grid_dim;        /* cells per side of the wrapped cell grid, 0 = auto             */
     int32_t edge_capacity;   /* directed-edge capacity per agent (mean), 0 = auto (48)        */
-    int32_t readout_mode;    /* 0 = auto, 1 = FFMA (CUDA cores), 2 = tensor cores (3xTF32),
-                                3 = experimental two-warp tensor-core readout (unvalidated)    */
+    int32_t readout_mode;    /* 0 = auto, 1 = FFMA (CUDA cores), 2 = tensor cores (tcgen05, 3xTF32) */
     int32_t grid_dim_y;      /* cells along y, 0 = same as grid_dim                           */
     int32_t shard_lo;        /* multi-GPU: first agent this rank owns ...                     */
     int32_t shard_count;     /* ... and how many (0 = all: single-GPU)                        */
@@ -96,6 +95,11 @@ int fgnn_integrate(fgnn_handle* h, const float* u_bn2, double* reward_b, void* s
 /* env.step(u) = fgnn_integrate + fgnn_build_graph(advance=1). */
 int fgnn_env_step(fgnn_handle* h, const float* u_bn2, double* reward_b, void* stream);
 
+/* The same two calls for a float64 action: when beta-mixing picks the expert, the reference steps the env with the
+ * controller's float64 array itself (learner/gnn_dagger.py:156-163 -- no fp32 cast on that branch). */
+int fgnn_integrate_f64(fgnn_handle* h, const double* u_bn2, double* reward_b, void* stream);
+int fgnn_env_step_f64(fgnn_handle* h, const double* u_bn2, double* reward_b, void* stream);
+
 /* DAGGER.select_action(state) (learner/gnn_dagger.py:55-72) = MultiAgentStateWithDelay history
  * (learner/state_with_delay.py:44-53) + Actor.forward (learner/actor.py:45-86) on the sparse
  * history the engine keeps: K-hop aggregation + readout.  action_bn2 (B*N,2) fp32 [h/d]. */
@@ -106,6 +110,8 @@ int fgnn_policy(fgnn_handle* h, float* action_bn2, void* stream);
  * clipped to +-max_accel and divided by the gain).  centralized != 0: velocity term over all agents
  * of the episode, potential term inside its own cut-off (r^2 <= comm_radius). */
 int fgnn_controller(fgnn_handle* h, int32_t centralized, double max_accel, float* u_bn2, void* stream);
+/* ... and in float64, as gym_flock returns it (no rounding to fp32 between the controller and env.step). */
+int fgnn_controller_f64(fgnn_handle* h, int32_t centralized, double max_accel, double* u_bn2, void* stream);
 
 /* One closed-loop rollout step (learner/gnn_dagger.py:196-201, test_model.py:38-45):
  * select_action -> env.step(action).  action_bn2 / reward_b may be NULL. */
@@ -168,6 +174,25 @@ int fgnn_shard_owned(fgnn_handle* h, int32_t* ids, int32_t* count, void* stream)
 int fgnn_comm_unique_id(void* id_128);
 int fgnn_comm_init(fgnn_handle* h, const void* id_128, int32_t rank, int32_t world);
 int fgnn_shard_step(fgnn_handle* h, double* send_buf, double* recv_buf, int32_t cap, void* stream);
+
+/* Halo over peer-to-peer stores instead of a collective (one node, NVLink / NVSwitch).  Every rank owns an inbox
+ * [2 halves][world senders][cap + 1 records] (+ one flag word per half and sender).  In step t the closed final kernel of
+ * rank s stores the records rank r needs straight into r's inbox slot [t & 1][s] through a CUDA-IPC mapping; a small kernel
+ * then publishes the header [count, x_lo, x_hi] and, fenced, the flag t + 1; r's graph waits for the flags of its peers and
+ * unpacks.  Only ranks whose windows overlap exchange anything (neighbouring strips), the payload does not grow with the
+ * world size, and a step is ONE CUDA graph with no host round trip.
+ *   fgnn_p2p_alloc    after fgnn_shard_configure: allocate the inbox; ipc_handle_64 (64 bytes, may be NULL) receives its
+ *                     cudaIpcMemHandle_t, *local_ptr (may be NULL) the device pointer
+ *   fgnn_p2p_connect  handles = world x 64 bytes in rank order (ranks in other processes), or direct_ptrs = world device
+ *                     pointers (ranks in this process); the own entry is ignored
+ *   fgnn_p2p_seed     after the reset-time exchange (fgnn_shard_pack / all-gather / fgnn_shard_unpack): the gathered buffer
+ *                     becomes both halves of the inbox (its headers are the first step's windows)
+ *   fgnn_shard_step_p2p  one closed-loop step.  A peer that never signals makes the wait give up after ~2 s and raises
+ *                     fgnn_stats.overflow = 2 instead of hanging the device. */
+int fgnn_p2p_alloc(fgnn_handle* h, int32_t world, int32_t rank, int32_t cap, void* ipc_handle_64, void** local_ptr);
+int fgnn_p2p_connect(fgnn_handle* h, const void* handles, void* const* direct_ptrs);
+int fgnn_p2p_seed(fgnn_handle* h, const double* gathered, void* stream);
+int fgnn_shard_step_p2p(fgnn_handle* h, void* stream);
 
 /* ---- environment variants named by the reference's cfgs (gym_flock, un-vendored) ----
  * FlockingLeader-v0 (cfg/dagger_leader.cfg:24): mask_bn (B*N,) bytes [h/d], 0 = leader -- the integrator ignores

@@ -43,8 +43,7 @@ def _units():
         for hp in HPS:
             units.append((os.path.join(OBJ, f"fgnn_final_k{k}_hp{hp}.o"), os.path.join(CSRC, "fgnn_final.cu"),
                           [f"-DFGNN_K={k}", f"-DFGNN_HP={hp}"],
-                          common_deps + [os.path.join(CSRC, "fgnn_final.cuh"), os.path.join(CSRC, "fgnn_final_tc.cuh"),
-                                         os.path.join(CSRC, "fgnn_final_tc2.cuh")]))
+                          common_deps + [os.path.join(CSRC, "fgnn_final.cuh"), os.path.join(CSRC, "fgnn_final_tc.cuh")]))
     return units
 
 

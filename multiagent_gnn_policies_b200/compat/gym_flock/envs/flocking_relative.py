@@ -8,7 +8,7 @@ All per-step arithmetic runs in libfgnn.so; the host only samples the initial co
 """
 import numpy as np
 
-from multiagent_gnn_policies_b200.engine import FlockEngine
+from multiagent_gnn_policies_b200.engine import FlockEngine, FgnnError
 
 DENSE_LIMIT = 4096      # largest N for which the dense (N,N) state_network is materialised on request
 
@@ -116,9 +116,27 @@ class FlockingRelativeEnv:
             self._engine = FlockEngine(n_agents=self.n_agents, k=self.k, hidden=self.hidden_size,
                                        n_layers=self.n_layers, comm_radius=self.comm_radius, dt=self.dt,
                                        action_scalar=self.action_scalar, mean_pooling=self.mean_pooling,
-                                       device=self.device_index, edge_capacity=64)
+                                       device=self.device_index, edge_capacity=self._edge_capacity())
             self._engine_key = key
         return self._engine
+
+    def _edge_capacity(self):
+        """Directed-edge capacity per agent (mean).  The reference's radius sweeps go up to comm_radius 4 at N = 100
+        (cfg/rad.cfg), where nearly every pair is an edge: small flocks get the complete graph, large ones several times
+        the expected degree of the reset distribution (a disc of radius N^(1/4): density sqrt(N)/pi) within a memory
+        bound; exceeding it raises (``_check_capacity``) instead of returning a void graph."""
+        n = self.n_agents
+        if n <= 2048:
+            return max(n - 1, 1)
+        expected = self.comm_radius2 * np.sqrt(n)
+        cap = int(min(n - 1, max(64, 3.0 * expected + 32)))
+        budget = 8 << 30                                           # bytes for the K-deep CSR ring
+        return int(max(16, min(cap, budget // (4 * max(self.k, 1) * n))))
+
+    def _check_capacity(self):
+        if self.engine.stats()["overflow"]:
+            raise FgnnError(f"edge capacity exceeded ({self._edge_capacity()} per agent at comm_radius {self.comm_radius}): "
+                            "the graph of this step is incomplete")
 
     # -- episode ----------------------------------------------------------------------------
     def _draw_configuration(self, x):
@@ -164,6 +182,7 @@ class FlockingRelativeEnv:
         self.x = self._sample_initial_state() if x0 is None else np.array(x0, dtype=np.float64)
         self._configure_engine(self.engine)
         self.engine.reset(self.x)
+        self._check_capacity()
         self._step = 0
         return self._observe()
 
@@ -171,14 +190,17 @@ class FlockingRelativeEnv:
         u = np.asarray(u)
         assert u.shape == (self.n_agents, self.nu)
         self._before_step(self.engine)
-        reward = self.engine.env_step(np.ascontiguousarray(u, dtype=np.float32))
+        # float64 actions (env.step(env.controller()), learner/gnn_dagger.py:156-163) are integrated as float64; the
+        # policy's ``action.cpu().numpy()`` arrives as fp32 and is widened exactly like numpy does
+        reward = self.engine.env_step(u if u.dtype == np.float64 else np.ascontiguousarray(u, dtype=np.float32))
+        self._check_capacity()
         self._step += 1
         return self._observe(), float(reward[0]), False, {}
 
     def controller(self, centralized=None):
         if centralized is None:
             centralized = self.centralized
-        return self.engine.controller(centralized=centralized, max_accel=self.max_accel).astype(np.float64)
+        return self.engine.controller(centralized=centralized, max_accel=self.max_accel, dtype=np.float64)
 
     def get_state(self):
         return self.engine.get_state()

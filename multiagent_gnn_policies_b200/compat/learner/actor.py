@@ -52,7 +52,7 @@ class Actor(nn.Module):
     def _dense_engine(self, device):
         if self._engine is None or self._engine.device != device:
             self._engine = FlockEngine(n_agents=1, k=self.k, hidden=self.layers[1], n_layers=self.n_layers - 1,
-                                       device=device.index or 0)
+                                       device=device.index if device.index is not None else torch.cuda.current_device())
         self.sync_engine(self._engine)
         return self._engine
 

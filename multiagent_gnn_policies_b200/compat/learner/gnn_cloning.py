@@ -9,7 +9,22 @@ from learner.state_with_delay import MultiAgentStateWithDelay
 
 
 class ImitationLearning(DAGGER):
-    pass
+    """learner/gnn_cloning.py:17-51: ``(device, args)`` only, and always TWO hidden layers of ``hidden_size``
+    (``hidden_layers = [hidden_size, hidden_size]``, gnn_cloning.py:40) whatever the cfg's ``n_layers`` says; no
+    ``k=`` override.  Everything else (select_action / gradient_step / save / load) is DAGGER's."""
+
+    def __init__(self, device, args):
+        class _TwoLayers:                       # the cfg section with n_layers pinned to 2
+            def __init__(self, inner):
+                self._inner = inner
+
+            def getint(self, key, *a, **kw):
+                return 2 if key == 'n_layers' else self._inner.getint(key, *a, **kw)
+
+            def __getattr__(self, name):
+                return getattr(self._inner, name)
+
+        super().__init__(device, _TwoLayers(args))
 
 
 def train_cloning(env, args, device):

@@ -59,7 +59,8 @@ class DAGGER(object):
     def _native_gradient_step(self, batch):
         if self._trainer is None:
             self._trainer = ActorTrainer(self.actor.k, self.actor.layers[1], self.actor.n_layers - 1,
-                                         device=torch.device(self.device).index or 0)
+                                         device=(torch.device(self.device).index if torch.device(self.device).index is not None
+                                                 else torch.cuda.current_device()))
         z = torch.stack([s.aggregated for s in batch.state])                    # (B,K,N,6)
         target = torch.cat(batch.action).to(self.device)                          # (B,1,nA,N)
         params, m, v = self._adam_tensors()

@@ -103,14 +103,12 @@ struct fgnn_handle {
     bool pdl = false;                // programmatic dependent launch between the step kernels
     bool tile_mode = false;          // k_tile: adjacency + features + first hop fused per cell tile (fgnn_tile.cuh)
     TileGeom geo;                    // its geometry and fp32 pre-filter thresholds
-    int tile_grid = 0;
+    dim3 tile_grid;
     int policy_chunks = 1;           // fgnn_policy to a host buffer: readout chunks overlapped with their D2H copies
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t chunk_event[FGNN_MAX_CHUNKS + 1] = {};
     // tensor-core readout (tcgen05, 3xTF32)
     bool use_tc = false;
-    bool use_tc2 = false;            // EXPERIMENTAL readout_mode 3: two warps per TMEM lane quadrant (fgnn_final_tc2.cuh)
-    int tc2_grid_closed = 0, tc2_grid_open = 0;
     std::vector<uint8_t> tc_host;    // TcLayout pack, host mirror
     uint8_t* d_tc_weights = nullptr;
     size_t tc_smem = 0;
@@ -132,6 +130,15 @@ struct fgnn_handle {
     int launch_pool = 0;             // grid sizing for kernels over the pool (pool capacity, or M)
     void* nccl_comm = nullptr;       // ncclComm_t of fgnn_comm_init (the halo all-gather inside the step graph)
     bool nccl_warm = false;
+    // p2p halo transport (fgnn_p2p_*): records stored straight into the peers' inboxes over NVLink
+    double* p2p_inbox = nullptr;     // [2][world][cap + 1][SREC] doubles followed by the flag words [2][world] ints
+    size_t p2p_bytes = 0;
+    int p2p_cap = 0, p2p_world = 0;
+    bool p2p_connected = false;
+    double** d_peer_inbox = nullptr; // [world] device array of inbox bases (own entry: p2p_inbox)
+    int** d_peer_flags = nullptr;
+    int* d_dest_count = nullptr;
+    std::vector<void*> p2p_opened;   // cudaIpcOpenMemHandle mappings to close
     void* shard_graph_store = nullptr;
     long long shard_epoch = 0;       // bumped by fgnn_shard_configure: invalidates cached graphs
     // per-kernel profiling of one step (fgnn_profile_step)
@@ -163,6 +170,9 @@ static int dalloc(fgnn_handle* h, T** ptr, size_t count, bool zero = true) {
 #ifndef FGNN_SCAN_TWO_PASS_DEFAULT
 #define FGNN_SCAN_TWO_PASS_DEFAULT true           // measured: 312 -> 294 us/step; blocks spinning on other blocks' status words are slow here
 #endif
+#ifndef FGNN_STEP_MODE_DEFAULT
+#define FGNN_STEP_MODE_DEFAULT 0                 // 1: k_tile (adjacency + features + first hop fused per cell tile).  Measured at N=1M, d~5:
+#endif                                           // 176 us vs 102 + 67 us for k_adjacency_t + k_hop (profiles/r2_tile_kernel.md): opt-in for now
 #ifndef FGNN_LAST_HOP_SEPARATE_DEFAULT
 #define FGNN_LAST_HOP_SEPARATE_DEFAULT true      // measured: 312 -> 307 us/step (high-occupancy gather + streaming readout)
 #endif
@@ -176,7 +186,7 @@ typedef void (*dense_kernel_t)(const float*, const float*, float*, const float*,
 namespace fgnn {
 typedef void (*final_tc_kernel_t)(Params, const uint8_t*);
 #define FGNN_DECL(K, HP) final_kernel_t get_final_k##K##_hp##HP(bool closed); dense_kernel_t get_dense_k##K##_hp##HP(); \
-    final_tc_kernel_t get_final_tc_k##K##_hp##HP(bool closed); final_tc_kernel_t get_final_tc2_k##K##_hp##HP(bool closed);
+    final_tc_kernel_t get_final_tc_k##K##_hp##HP(bool closed);
 #define FGNN_DECL_K(K) FGNN_DECL(K, 16) FGNN_DECL(K, 32) FGNN_DECL(K, 64) FGNN_DECL(K, 128)
 FGNN_DECL_K(1) FGNN_DECL_K(2) FGNN_DECL_K(3) FGNN_DECL_K(4)
 }
@@ -191,11 +201,6 @@ static void* kernel_lookup(int K, int HP, int closed_or_dense) {
 static final_kernel_t final_kernel(int K, int HP, bool closed) { return (final_kernel_t)kernel_lookup(K, HP, closed ? 1 : 0); }
 static dense_kernel_t dense_kernel(int K, int HP) { return (dense_kernel_t)kernel_lookup(K, HP, 2); }
 static final_tc_kernel_t final_tc_kernel(int K, int HP, bool closed) { return (final_tc_kernel_t)kernel_lookup(K, HP, closed ? 4 : 3); }
-#define FGNN_TC2_CASE(K) case K: return HP == 32 ? get_final_tc2_k##K##_hp32(closed) : HP == 64 ? get_final_tc2_k##K##_hp64(closed) : nullptr;
-static final_tc_kernel_t final_tc2_kernel(int K, int HP, bool closed) {
-    switch (K) { FGNN_TC2_CASE(1) FGNN_TC2_CASE(2) FGNN_TC2_CASE(3) default: FGNN_TC2_CASE(4) }
-}
-
 static size_t final_smem_bytes(const fgnn_handle* h) {
     WeightLayout wl{F * h->cfg.k, h->HP, h->cfg.n_layers};
     if (h->HP > 64) return (size_t)2 * h->HP * FINAL_THREADS * sizeof(float);
@@ -207,11 +212,11 @@ static inline int blocks_for(int n, int threads) { return (n + threads - 1) / th
 // Launch one of the closed-loop step kernels, with the programmatic-serialization attribute when the handle asks for
 // it (the kernel may then become resident while its predecessor drains; it starts with pdl_prologue()).
 template <typename... KArgs, typename... Args>
-static void launch_step(const fgnn_handle* h, void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st,
+static void launch_step(const fgnn_handle* h, void (*kernel)(KArgs...), dim3 grid, int block, size_t smem, cudaStream_t st,
                         Args... args) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
-    cfg.gridDim = dim3((unsigned)grid);
+    cfg.gridDim = grid;
     cfg.blockDim = dim3((unsigned)block);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
@@ -221,6 +226,11 @@ static void launch_step(const fgnn_handle* h, void (*kernel)(KArgs...), int grid
     cfg.attrs = attr;
     cfg.numAttrs = h->pdl ? 1 : 0;
     cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+template <typename... KArgs, typename... Args>
+static void launch_step(const fgnn_handle* h, void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st,
+                        Args... args) {
+    launch_step(h, kernel, dim3((unsigned)grid), block, smem, st, args...);
 }
 
 // ---- ABI --------------------------------------------------------------------------------------
@@ -235,6 +245,7 @@ extern "C" int fgnn_create(const fgnn_config* cfg, fgnn_handle** out) {
     if (cfg->n_actions != 2) return fail("fgnn_create: n_actions must be 2");
     if (cfg->hidden < 1 || cfg->hidden > 128) return fail("fgnn_create: hidden must be in 1..128");
     if (cfg->n_layers < 1 || cfg->n_layers > LMAX) return fail("fgnn_create: n_layers must be in 1..4");
+    if (cfg->readout_mode < 0 || cfg->readout_mode > 2) return fail("fgnn_create: readout_mode must be 0 (auto), 1 (FFMA) or 2 (tensor cores)");
     if (!(cfg->comm_radius > 0.0) || !(cfg->dt > 0.0)) return fail("fgnn_create: comm_radius and dt must be > 0");
     const long long M64 = (long long)cfg->n_agents * cfg->n_episodes;
     if (M64 > (1ll << 30) - 1) return fail("fgnn_create: more than 2^30-1 agents on one device");
@@ -309,13 +320,14 @@ extern "C" int fgnn_create(const fgnn_config* cfg, fgnn_handle** out) {
         if (th > TL_TYMAX) th = TL_TYMAX;
         if (tw > G - 4) tw = G - 4;               // a window (tile + two-cell halo) never covers a grid cell twice
         if (th > Gy - 4) th = Gy - 4;
-        h->tile_mode = (sm ? atoi(sm) != 0 : true) && tw >= 1 && th >= 1;
+        h->tile_mode = (sm ? atoi(sm) != 0 : FGNN_STEP_MODE_DEFAULT != 0) && tw >= 1 && th >= 1;
         memset(&h->geo, 0, sizeof h->geo);
         if (h->tile_mode) {
             TileGeom& ge = h->geo;
             ge.tw = tw; ge.th = th;
             ge.ntx = blocks_for(G, tw); ge.nty = blocks_for(Gy, th);
-            h->tile_grid = ge.ntx * ge.nty * cfg->n_episodes;
+            h->tile_grid = dim3((unsigned)ge.ntx, (unsigned)ge.nty, (unsigned)cfg->n_episodes);
+            if (ge.nty > 65535 || cfg->n_episodes > 65535) { delete h; return fail("fgnn_create: tile grid too large"); }
             // fp32 pre-filter on window-relative coordinates (|coordinate| <= E).  With u = 2^-24: every coordinate carries
             // u E, a difference u (2 E + |d|), so for r2 <= 4 R^2 the fp32 r2 is within u (16 R E + 24 R^2) of the float64
             // value; twice that is the margin.  Pairs inside the margin take the float64 test.
@@ -324,7 +336,7 @@ extern "C" int fgnn_create(const fgnn_config* cfg, fgnn_handle** out) {
             const double margin = std::ldexp(16.0 * R * E + 24.0 * R * R, -23);
             ge.far32 = (float)E;
             ge.lo32 = std::nextafterf((float)(p.R2 - margin), -INFINITY);
-            ge.hi32 = std::nextafterf((float)(p.R2 + margin), INFINITY);
+            ge.hi32n = std::nextafterf(std::nextafterf((float)(p.R2 + margin), INFINITY), INFINITY);
             ge.csr_tail_only = (cfg->flags & FGNN_FLAG_CSR_TAIL_ONLY) ? 1 : 0;
             CK(cudaFuncSetAttribute((const void*)k_tile<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(1)));
             CK(cudaFuncSetAttribute((const void*)k_tile<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(2)));
@@ -387,7 +399,7 @@ extern "C" int fgnn_create(const fgnn_config* cfg, fgnn_handle** out) {
         h->ctl.xminmax = h->d_xminmax;
         h->ctl.shift = h->d_shift;
     }
-    rc |= dalloc(h, &h->d_u_in, (M > (size_t)p.pool_cap ? M : (size_t)p.pool_cap) * 2);
+    rc |= dalloc(h, &h->d_u_in, (M > (size_t)p.pool_cap ? M : (size_t)p.pool_cap) * 2 * 2);   // fp32 or float64 actions
     rc |= dalloc(h, &h->d_staging, K * M * F > (size_t)M * 4 * 2 ? K * M * F : (size_t)M * 4 * 2);
     WeightLayout wl{F * p.K, h->HP, p.L};
     h->weights_floats = wl.total();
@@ -448,28 +460,6 @@ extern "C" int fgnn_create(const fgnn_config* cfg, fgnn_handle** out) {
             (closed ? h->tc_grid_closed : h->tc_grid_open) = grid;
         }
     }
-    if (cfg->readout_mode == 3) {
-        if (!h->use_tc || (h->HP != 32 && h->HP != 64)) { fgnn_destroy(h); return fail("fgnn_create: readout_mode 3 needs hidden in 17..64"); }
-        h->use_tc2 = true;
-        if (p.K >= 2) h->last_hop_separate = true;          // its inputs are plain streaming loads
-        const size_t smem2 = h->tc_smem + 1024;              // + the output partials
-        for (int closed = 0; closed < 2; ++closed) {
-            final_tc_kernel_t fk = final_tc2_kernel(p.K, h->HP, closed != 0);
-            CK(cudaFuncSetAttribute((const void*)fk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-            cudaFuncAttributes fa;
-            CK(cudaFuncGetAttributes(&fa, (const void*)fk));
-            int occ = (int)((size_t)prop.sharedMemPerMultiprocessor / (smem2 + 1024));
-            const int occ_reg = 65536 / ((fa.numRegs > 0 ? ((fa.numRegs + 7) & ~7) : 64) * 2 * FINAL_THREADS);
-            if (occ > occ_reg) occ = occ_reg;
-            const int max_by_tmem = 512 / tc_tmem_cols(h->HP);
-            if (occ > max_by_tmem) occ = max_by_tmem;
-            if (occ < 1) occ = 1;
-            int grid = h->sm_count * occ;
-            int tiles = blocks_for(h->sharded ? p.pool_cap : p.n_own, FINAL_THREADS);
-            if (grid > tiles) grid = tiles;
-            (closed ? h->tc2_grid_closed : h->tc2_grid_open) = grid;
-        }
-    }
     *out = h;
     return 0;
 }
@@ -526,6 +516,7 @@ extern "C" int fgnn_destroy(fgnn_handle* h) {
     if (h->graph) cudaGraphDestroy(h->graph);
     // the communicator is deliberately not destroyed here: ncclCommDestroy waits for the peers and was observed to
     // hang at interpreter shutdown when ranks tear down in different orders; process exit reclaims it
+    for (void* q : h->p2p_opened) cudaIpcCloseMemHandle(q);
     for (void* q : h->allocs) cudaFree(q);
     if (h->copy_stream) {
         cudaStreamDestroy(h->copy_stream);
@@ -676,13 +667,7 @@ static int enqueue_final(fgnn_handle* h, bool closed, int write_z, cudaStream_t 
     p.write_z_last = write_z;
     p.last_hop_done = (h->last_hop_separate && p.K >= 2) ? 1 : 0;
     p.fuse = fuse_pack ? h->d_fuse : nullptr;
-    if (h->use_tc2) {
-        final_tc_kernel_t fk = final_tc2_kernel(p.K, h->HP, closed);
-        int grid = closed ? h->tc2_grid_closed : h->tc2_grid_open;
-        if (tile_hi > tile_lo && grid > tile_hi - tile_lo) grid = tile_hi - tile_lo;
-        launch_step(h, fk, grid, 2 * FINAL_THREADS, h->tc_smem + 1024, st, p, (const uint8_t*)h->d_tc_weights);
-        if (launch_check(h, "final")) return 1;
-    } else if (h->use_tc) {
+    if (h->use_tc) {
         final_tc_kernel_t fk = final_tc_kernel(p.K, h->HP, closed);
         int grid = closed ? h->tc_grid_closed : h->tc_grid_open;
         if (tile_hi > tile_lo && grid > tile_hi - tile_lo) grid = tile_hi - tile_lo;
@@ -763,9 +748,8 @@ extern "C" int fgnn_build_graph(fgnn_handle* h, int32_t advance, void* stream) {
     return enqueue_build(h, advance, (cudaStream_t)stream);
 }
 
-extern "C" int fgnn_integrate(fgnn_handle* h, const float* u, double* reward_b, void* stream) {
-    if (!h || !u) return fail("fgnn_integrate: null argument");
-    cudaStream_t st = (cudaStream_t)stream;
+// u: (rows, 2) fp32 or float64 (f64 != 0)
+static int integrate_impl(fgnn_handle* h, const void* u, int f64, double* reward_b, cudaStream_t st) {
     Params& p = h->p;
     CK(cudaSetDevice(h->cfg.device));
     if (h->binned) {      // positions were binned already (closed-loop kernel or a previous integrate): start over
@@ -774,8 +758,9 @@ extern "C" int fgnn_integrate(fgnn_handle* h, const float* u, double* reward_b, 
     }
     // sharded handle: u has pool_cap rows in owned-list order (rows beyond the owned count are ignored)
     const int rows = h->sharded ? p.pool_cap : p.n_own;
-    CK(cudaMemcpyAsync(h->d_u_in, u, (size_t)rows * 2 * sizeof(float), cudaMemcpyDefault, st));
-    k_integrate<<<blocks_for(rows, 256), 256, 0, st>>>(p, h->d_u_in);
+    CK(cudaMemcpyAsync(h->d_u_in, u, (size_t)rows * 2 * (f64 ? sizeof(double) : sizeof(float)), cudaMemcpyDefault, st));
+    if (f64) k_integrate<double2><<<blocks_for(rows, 256), 256, 0, st>>>(p, reinterpret_cast<const double2*>(h->d_u_in));
+    else k_integrate<float2><<<blocks_for(rows, 256), 256, 0, st>>>(p, reinterpret_cast<const float2*>(h->d_u_in));
     if (launch_check(h, "integrate")) return 1;
     h->binned = true;
     if (reward_b) {
@@ -786,11 +771,30 @@ extern "C" int fgnn_integrate(fgnn_handle* h, const float* u, double* reward_b, 
     return 0;
 }
 
-extern "C" int fgnn_env_step(fgnn_handle* h, const float* u, double* reward_b, void* stream) {
+extern "C" int fgnn_integrate(fgnn_handle* h, const float* u, double* reward_b, void* stream) {
+    if (!h || !u) return fail("fgnn_integrate: null argument");
+    return integrate_impl(h, u, 0, reward_b, (cudaStream_t)stream);
+}
+
+extern "C" int fgnn_integrate_f64(fgnn_handle* h, const double* u, double* reward_b, void* stream) {
+    if (!h || !u) return fail("fgnn_integrate_f64: null argument");
+    return integrate_impl(h, u, 1, reward_b, (cudaStream_t)stream);
+}
+
+static int env_step_impl(fgnn_handle* h, const void* u, int f64, double* reward_b, void* stream) {
     if (h && h->sharded) return fail("fgnn_env_step: sharded handle -- integrate, exchange the halo, then build the graph");
-    if (fgnn_integrate(h, u, nullptr, stream)) return 1;
+    if (!h || !u) return fail("fgnn_env_step: null argument");
+    if (integrate_impl(h, u, f64, nullptr, (cudaStream_t)stream)) return 1;
     if (enqueue_build(h, 1, (cudaStream_t)stream)) return 1;
     return copy_out(reward_b, h->p.reward, (size_t)h->p.B * sizeof(double), (cudaStream_t)stream);
+}
+
+extern "C" int fgnn_env_step(fgnn_handle* h, const float* u, double* reward_b, void* stream) {
+    return env_step_impl(h, u, 0, reward_b, stream);
+}
+
+extern "C" int fgnn_env_step_f64(fgnn_handle* h, const double* u, double* reward_b, void* stream) {
+    return env_step_impl(h, u, 1, reward_b, stream);
 }
 
 extern "C" int fgnn_policy(fgnn_handle* h, float* action, void* stream) {
@@ -1027,7 +1031,7 @@ extern "C" int fgnn_get_stats(fgnn_handle* h, fgnn_stats* out, void* stream) {
     return 0;
 }
 
-extern "C" int fgnn_controller(fgnn_handle* h, int32_t centralized, double max_accel, float* u, void* stream) {
+static int controller_impl(fgnn_handle* h, int32_t centralized, double max_accel, void* u, int f64, void* stream) {
     if (!h || !u) return fail("fgnn_controller: null argument");
     cudaStream_t st = (cudaStream_t)stream;
     Params& p = h->p;
@@ -1046,27 +1050,42 @@ extern "C" int fgnn_controller(fgnn_handle* h, int32_t centralized, double max_a
     int window = 1;
     if (centralized) window = (int)std::ceil(std::sqrt(R) / cell - 1e-12);
     if (window < 1) window = 1;
-    k_controller<<<blocks_for(h->launch_pool, 128), 128, 0, st>>>(p, centralized ? 1 : 0, window, R, max_accel * p.gain, vsum,
-                                                        h->d_u_in);
+    if (f64)
+        k_controller<double2><<<blocks_for(h->launch_pool, 128), 128, 0, st>>>(p, centralized ? 1 : 0, window, R, max_accel * p.gain, vsum,
+                                                                              reinterpret_cast<double2*>(h->d_u_in));
+    else
+        k_controller<float2><<<blocks_for(h->launch_pool, 128), 128, 0, st>>>(p, centralized ? 1 : 0, window, R, max_accel * p.gain, vsum,
+                                                                             reinterpret_cast<float2*>(h->d_u_in));
     if (launch_check(h, "controller")) return 1;
-    return copy_out(u, h->d_u_in, (size_t)p.M * 2 * sizeof(float), st);
+    return copy_out(u, h->d_u_in, (size_t)p.M * 2 * (f64 ? sizeof(double) : sizeof(float)), st);
+}
+
+extern "C" int fgnn_controller(fgnn_handle* h, int32_t centralized, double max_accel, float* u, void* stream) {
+    return controller_impl(h, centralized, max_accel, u, 0, stream);
+}
+
+extern "C" int fgnn_controller_f64(fgnn_handle* h, int32_t centralized, double max_accel, double* u, void* stream) {
+    return controller_impl(h, centralized, max_accel, u, 1, stream);
 }
 
 struct ShardGraph;
 static int enqueue_shard_pack(fgnn_handle* h, const double* windows, int64_t window_stride, double* send_buf, int cap,
                               int advance, cudaStream_t st) {
     Params& p = h->p;
-    k_shard_prepare<<<1, 32, 0, st>>>(h->ctl, advance);
+    k_shard_prepare<<<1, 32, 0, st>>>(h->ctl, advance, nullptr);
     if (launch_check(h, "shard_prepare")) return 1;
-    k_shard_pack<<<blocks_for(p.pool_cap, 256), 256, 0, st>>>(p, h->ctl, windows, (long long)window_stride, send_buf, cap);
+    ShardFuse f;
+    memset(&f, 0, sizeof f);
+    f.ctl = h->ctl; f.windows = windows; f.wstride = window_stride; f.buf = send_buf; f.cap = cap;
+    k_shard_pack<<<blocks_for(p.pool_cap, 256), 256, 0, st>>>(p, f);
     if (launch_check(h, "shard_pack")) return 1;
     k_shard_header<<<1, 256, 0, st>>>(h->ctl, send_buf, blocks_for(p.pool_cap, 256));
     return launch_check(h, "shard_header");
 }
 
-static int enqueue_shard_unpack(fgnn_handle* h, const double* recv_buf, int cap, cudaStream_t st) {
+static int enqueue_shard_unpack(fgnn_handle* h, const double* recv_buf, int cap, cudaStream_t st, long long parity_stride = 0) {
     Params& p = h->p;
-    k_shard_unpack<<<blocks_for(h->ctl.world * cap, 256), 256, 0, st>>>(p, h->ctl, recv_buf, cap);
+    k_shard_unpack<<<dim3((unsigned)blocks_for(cap, 256), (unsigned)h->ctl.world), 256, 0, st>>>(p, h->ctl, recv_buf, cap, parity_stride);
     if (launch_check(h, "shard_unpack")) return 1;
     h->binned = true;
     return 0;
@@ -1194,11 +1213,11 @@ extern "C" int fgnn_shard_step_begin(fgnn_handle* h, const double* windows, int6
         h->fuse_host = f;
         CK(cudaMemcpyAsync(h->d_fuse, &h->fuse_host, sizeof f, cudaMemcpyHostToDevice, st));
     }
-    const int final_grid = h->use_tc2 ? h->tc2_grid_closed : h->use_tc ? h->tc_grid_closed : h->final_grid_closed;
+    const int final_grid = h->use_tc ? h->tc_grid_closed : h->final_grid_closed;
     ShardGraph& g = shard_graphs(h)[0];
     int rc = run_cached_graph(h, g, nullptr, send_buf, h->shard_epoch, final_grid, 0, 0, 0.0, st, [&](cudaStream_t cs) {
         if (enqueue_hops(h, cs)) return 1;
-        k_shard_prepare<<<1, 32, 0, cs>>>(h->ctl, 1);
+        k_shard_prepare<<<1, 32, 0, cs>>>(h->ctl, 1, nullptr);
         if (launch_check(h, "shard_prepare")) return 1;
         if (enqueue_final(h, true, 0, cs, true)) return 1;
         k_shard_header<<<1, 256, 0, cs>>>(h->ctl, send_buf, final_grid);
@@ -1268,11 +1287,11 @@ extern "C" int fgnn_shard_step(fgnn_handle* h, double* send_buf, double* recv_bu
         CK(cudaStreamSynchronize(st));
         h->nccl_warm = true;
     }
-    const int final_grid = h->use_tc2 ? h->tc2_grid_closed : h->use_tc ? h->tc_grid_closed : h->final_grid_closed;
+    const int final_grid = h->use_tc ? h->tc_grid_closed : h->final_grid_closed;
     ShardGraph& g = shard_graphs(h)[2];
     int rc = run_cached_graph(h, g, recv_buf, send_buf, h->shard_epoch, final_grid, cap, 0, 0.0, st, [&](cudaStream_t cs) {
         if (enqueue_hops(h, cs)) return 1;
-        k_shard_prepare<<<1, 32, 0, cs>>>(h->ctl, 1);
+        k_shard_prepare<<<1, 32, 0, cs>>>(h->ctl, 1, nullptr);
         if (launch_check(h, "shard_prepare")) return 1;
         if (enqueue_final(h, true, 0, cs, true)) return 1;
         k_shard_header<<<1, 256, 0, cs>>>(h->ctl, send_buf, final_grid);
@@ -1280,6 +1299,129 @@ extern "C" int fgnn_shard_step(fgnn_handle* h, double* send_buf, double* recv_bu
         if (nccl_check(g_nccl.AllGather(send_buf, recv_buf, (size_t)stride, 8 /* ncclFloat64 */, h->nccl_comm, cs), "ncclAllGather"))
             return 1;
         if (enqueue_shard_unpack(h, recv_buf, cap, cs)) return 1;
+        return enqueue_build(h, 1, cs);
+    });
+    if (rc) return 1;
+    h->binned = false;
+    h->t_host += 1;
+    return 0;
+}
+
+// ---- p2p halo transport -------------------------------------------------------------------------------------------
+// Every rank owns an inbox [2][world][cap + 1][SREC] (+ flag words [2][world]); the closed final kernel of a peer stores
+// its records for this rank straight into slot [t & 1][peer] through a CUDA-IPC mapping (NVLink), k_shard_flag
+// publishes header + flag, k_shard_wait spins on the flags, k_shard_unpack reads the inbox.  No collective, no host
+// round trip: the whole step is ONE CUDA graph per rank.
+static size_t p2p_inbox_doubles(int world, int cap) { return (size_t)2 * world * (cap + 1) * SREC; }
+
+extern "C" int fgnn_p2p_alloc(fgnn_handle* h, int32_t world, int32_t rank, int32_t cap, void* ipc_handle_64, void** local_ptr) {
+    if (!h || !h->sharded) return fail("fgnn_p2p_alloc: handle is not sharded");
+    if (!h->shard_configured || world != h->ctl.world || rank != h->ctl.rank) return fail("fgnn_p2p_alloc: call fgnn_shard_configure with the same world / rank first");
+    if (world < 1 || world > 256 || cap < 1) return fail("fgnn_p2p_alloc: bad world / capacity");
+    if (h->p2p_inbox) return fail("fgnn_p2p_alloc: inbox already allocated");
+    CK(cudaSetDevice(h->cfg.device));
+    h->p2p_bytes = p2p_inbox_doubles(world, cap) * sizeof(double) + (size_t)2 * world * sizeof(int);
+    void* q = nullptr;
+    CK(cudaMalloc(&q, h->p2p_bytes));                    // its own allocation: an IPC handle names a whole allocation
+    CK(cudaMemset(q, 0, h->p2p_bytes));
+    h->allocs.push_back(q);
+    h->p2p_inbox = reinterpret_cast<double*>(q);
+    h->p2p_cap = cap; h->p2p_world = world;
+    if (dalloc(h, &h->d_peer_inbox, (size_t)world) || dalloc(h, &h->d_peer_flags, (size_t)world) || dalloc(h, &h->d_dest_count, (size_t)world))
+        return 1;
+    if (ipc_handle_64) {
+        cudaIpcMemHandle_t hd;
+        static_assert(sizeof hd == 64, "cudaIpcMemHandle_t is 64 bytes");
+        CK(cudaIpcGetMemHandle(&hd, q));
+        memcpy(ipc_handle_64, &hd, sizeof hd);
+    }
+    if (local_ptr) *local_ptr = q;
+    return 0;
+}
+
+// handles: world x 64 bytes (cudaIpcMemHandle_t of every rank's inbox, in rank order) -- ranks are separate processes; or
+// direct_ptrs: world device pointers to the inboxes (ranks that live in this process, e.g. the single-process tests).
+extern "C" int fgnn_p2p_connect(fgnn_handle* h, const void* handles, void* const* direct_ptrs) {
+    if (!h || !h->p2p_inbox) return fail("fgnn_p2p_connect: call fgnn_p2p_alloc first");
+    if (!handles && !direct_ptrs) return fail("fgnn_p2p_connect: need IPC handles or direct pointers");
+    CK(cudaSetDevice(h->cfg.device));
+    const int world = h->p2p_world, rank = h->ctl.rank;
+    std::vector<double*> inbox(world);
+    std::vector<int*> flags(world);
+    for (int q = 0; q < world; ++q) {
+        void* base = nullptr;
+        if (q == rank) {
+            base = h->p2p_inbox;
+        } else if (direct_ptrs) {
+            base = direct_ptrs[q];
+            cudaPointerAttributes attr;
+            if (cudaPointerGetAttributes(&attr, base) == cudaSuccess && attr.type == cudaMemoryTypeDevice && attr.device != h->cfg.device) {
+                int can = 0;
+                CK(cudaDeviceCanAccessPeer(&can, h->cfg.device, attr.device));
+                if (!can) return fail("fgnn_p2p_connect: no peer access between the devices");
+                cudaError_t e = cudaDeviceEnablePeerAccess(attr.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(std::string("cudaDeviceEnablePeerAccess -> ") + cudaGetErrorString(e));
+                cudaGetLastError();
+            }
+        } else {
+            cudaIpcMemHandle_t hd;
+            memcpy(&hd, reinterpret_cast<const char*>(handles) + (size_t)q * sizeof hd, sizeof hd);
+            CK(cudaIpcOpenMemHandle(&base, hd, cudaIpcMemLazyEnablePeerAccess));
+            h->p2p_opened.push_back(base);
+        }
+        if (!base) return fail("fgnn_p2p_connect: null inbox pointer");
+        inbox[q] = reinterpret_cast<double*>(base);
+        flags[q] = reinterpret_cast<int*>(inbox[q] + p2p_inbox_doubles(world, h->p2p_cap));
+    }
+    CK(cudaMemcpy(h->d_peer_inbox, inbox.data(), world * sizeof(double*), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->d_peer_flags, flags.data(), world * sizeof(int*), cudaMemcpyHostToDevice));
+    h->p2p_connected = true;
+    h->shard_epoch += 1;
+    return 0;
+}
+
+// After the reset-time exchange: install the gathered buffer (world x (cap + 1) records, what fgnn_shard_unpack consumed) as
+// BOTH halves of the inbox, so that the first p2p step finds every rank's x-interval in the headers.
+extern "C" int fgnn_p2p_seed(fgnn_handle* h, const double* gathered, void* stream) {
+    if (!h || !h->p2p_inbox || !gathered) return fail("fgnn_p2p_seed: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(h->cfg.device));
+    const size_t half = p2p_inbox_doubles(h->p2p_world, h->p2p_cap) / 2;
+    CK(cudaMemcpyAsync(h->p2p_inbox, gathered, half * sizeof(double), cudaMemcpyDefault, st));
+    CK(cudaMemcpyAsync(h->p2p_inbox + half, gathered, half * sizeof(double), cudaMemcpyDefault, st));
+    CK(cudaMemsetAsync(h->p2p_inbox + 2 * half, 0, (size_t)2 * h->p2p_world * sizeof(int), st));
+    return 0;
+}
+
+// One closed-loop step of a rank as ONE CUDA graph, halo over p2p stores:
+//   hops -> final (+ fused pack: records into the peers' inboxes) -> flag -> wait -> unpack -> scan/scatter/canon/adjacency
+extern "C" int fgnn_shard_step_p2p(fgnn_handle* h, void* stream) {
+    if (!h || !h->sharded) return fail("fgnn_shard_step_p2p: handle is not sharded");
+    if (!h->p2p_connected) return fail("fgnn_shard_step_p2p: call fgnn_p2p_alloc / fgnn_p2p_connect / fgnn_p2p_seed first");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(h->cfg.device));
+    if (h->binned) return fail("fgnn_shard_step_p2p: graph not rebuilt since the last step");
+    ShardFuse f;
+    memset(&f, 0, sizeof f);
+    f.ctl = h->ctl; f.cap = h->p2p_cap; f.p2p = 1;
+    f.peer_inbox = h->d_peer_inbox; f.peer_flags = h->d_peer_flags; f.dest_count = h->d_dest_count;
+    if (memcmp(&f, &h->fuse_host, sizeof f) != 0) {
+        h->fuse_host = f;
+        CK(cudaMemcpyAsync(h->d_fuse, &h->fuse_host, sizeof f, cudaMemcpyHostToDevice, st));
+    }
+    const int final_grid = h->use_tc ? h->tc_grid_closed : h->final_grid_closed;
+    const long long parity_stride = (long long)(p2p_inbox_doubles(h->p2p_world, h->p2p_cap) / 2);
+    ShardGraph& g = shard_graphs(h)[2];
+    int rc = run_cached_graph(h, g, h->p2p_inbox, h->d_peer_inbox, h->shard_epoch, final_grid, h->p2p_cap, 1, 0.0, st, [&](cudaStream_t cs) {
+        if (enqueue_hops(h, cs)) return 1;
+        k_shard_prepare<<<1, 256, 0, cs>>>(h->ctl, 1, h->d_dest_count);
+        if (launch_check(h, "shard_prepare")) return 1;
+        if (enqueue_final(h, true, 0, cs, true)) return 1;
+        k_shard_flag<<<1, 256, 0, cs>>>(h->p, f, final_grid);
+        if (launch_check(h, "shard_flag")) return 1;
+        k_shard_wait<<<1, 256, 0, cs>>>(h->p, f);
+        if (launch_check(h, "shard_wait")) return 1;
+        if (enqueue_shard_unpack(h, h->p2p_inbox, h->p2p_cap, cs, parity_stride)) return 1;
         return enqueue_build(h, 1, cs);
     });
     if (rc) return 1;

@@ -1,5 +1,5 @@
 // fgnn_final.cu -- compiled once per (FGNN_K, FGNN_HP) pair: -DFGNN_K=<1..4> -DFGNN_HP=<16|32|64|128>
-#include "fgnn_final_tc2.cuh"
+#include "fgnn_final_tc.cuh"
 
 #define FGNN_CAT2(a, b, c, d) a##b##c##d
 #define FGNN_CAT(a, b, c, d) FGNN_CAT2(a, b, c, d)
@@ -20,15 +20,6 @@ final_tc_kernel_t FGNN_CAT(get_final_tc_k, FGNN_K, _hp, FGNN_HP)(bool closed) {
 #else
     (void)closed;
     return nullptr;      // HP = 128: operands do not fit shared memory; FFMA path only
-#endif
-}
-// experimental two-warps-per-quadrant readout (readout_mode = 3): HP in {32, 64}
-final_tc_kernel_t FGNN_CAT(get_final_tc2_k, FGNN_K, _hp, FGNN_HP)(bool closed) {
-#if FGNN_HP == 32 || FGNN_HP == 64
-    return closed ? k_final_tc2<FGNN_K, FGNN_HP, true> : k_final_tc2<FGNN_K, FGNN_HP, false>;
-#else
-    (void)closed;
-    return nullptr;
 #endif
 }
 }  // namespace fgnn

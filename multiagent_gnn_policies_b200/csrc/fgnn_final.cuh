@@ -179,8 +179,7 @@ __global__ void __launch_bounds__(FINAL_THREADS) k_final(Params p) {
             reinterpret_cast<float2*>(p.action)[a] = make_float2(o0, o1);
             if (CLOSED) {
                 const double4 st_new = integrate_and_bin(p, a, st_own, o0, o1, racc);
-                if (p.fuse) shard_pack_agent(p, p.fuse->ctl, p.fuse->windows, p.fuse->wstride, p.fuse->buf, p.fuse->cap, oi, a,
-                                             st_new, klo, khi);
+                if (p.fuse) shard_pack_agent(p, *p.fuse, oi, a, st_new, klo, khi);
             }
         }
     }

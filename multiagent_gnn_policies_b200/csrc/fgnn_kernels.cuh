@@ -884,15 +884,37 @@ __device__ __forceinline__ int strip_of(const ShardCtl& c, double xs) {
 }
 
 
+// Arguments of the pack step (device-resident when it is fused into the closed final kernel: the CUDA graph of a step
+// stays valid when buffers change).  Two transports:
+//   gather (p2p == 0): every record goes into ONE send buffer that the host all-gathers to every rank;
+//   p2p    (p2p == 1): a record goes straight into the inbox of each rank that needs it -- plain stores into peer memory
+//                      over NVLink (CUDA-IPC mapped) -- slot [parity][sender] of the receiver, parity = t & 1.
+struct ShardFuse {
+    ShardCtl ctl;
+    const double* windows;    // gather: [q * wstride + {0, 1}] = rank q's owned x-interval (one step old)
+    long long wstride;
+    double* buf;              // gather: send buffer, (cap + 1) records
+    int cap;
+    int p2p;
+    double* const* peer_inbox;    // p2p: [world] base of every rank's inbox  [2][world][cap + 1][SREC]  (own entry: local)
+    int* const* peer_flags;       // p2p: [world] base of every rank's flags  [2][world]
+    int* dest_count;              // p2p: [world] records written for each destination this step
+};
+
+__device__ __forceinline__ size_t inbox_offset(const ShardFuse& f, int parity, int sender) {
+    return ((size_t)(parity * f.ctl.world + sender) * (f.cap + 1)) * SREC;
+}
+
 // Hand-over decision and halo record of ONE owned agent whose (new) state is `st` (used by k_shard_pack and,
 // fused, by the epilogue of the closed final kernel).  i = position in the owned list.
-__device__ __forceinline__ void shard_pack_agent(const Params& p, const ShardCtl& c, const double* __restrict__ windows,
-                                                 long long wstride, double* __restrict__ buf, int cap, int i, int a,
-                                                 const double4 st, long long& klo, long long& khi) {
+__device__ __forceinline__ void shard_pack_agent(const Params& p, const ShardFuse& f, int i, int a, const double4 st,
+                                                 long long& klo, long long& khi) {
+    const ShardCtl& c = f.ctl;
     const double shift = *c.shift;
     const double xs = st.x - shift;
+    const int t = *p.t;
     int new_owner = -1;
-    if (*p.t >= c.handover_after) {
+    if (t >= c.handover_after) {
         const int sp = strip_of(c, xs);
         if (sp > c.rank && xs - c.bounds[c.rank + 1] > c.margin) new_owner = sp;
         if (sp < c.rank && c.bounds[c.rank] - xs > c.margin) new_owner = sp;
@@ -907,17 +929,33 @@ __device__ __forceinline__ void shard_pack_agent(const Params& p, const ShardCtl
         const int slot = atomicAdd(c.n_ghost, 1);
         if (slot < p.pool_cap) c.ghost[slot] = a; else *p.overflow = 1;
     }
-    bool wanted = new_owner >= 0;                         // who needs this agent's state?
+    // who needs this agent's state?  windows: the x-intervals the ranks announced one step ago
+    const double* windows = f.p2p ? f.peer_inbox[c.rank] + inbox_offset(f, (t + 1) & 1, 0) + 1 : f.windows;
+    const long long wstride = f.p2p ? (long long)(f.cap + 1) * SREC : f.wstride;
+    bool wanted = new_owner >= 0 && !f.p2p;
+    bool wrote = false;
     for (int q = 0; q < c.world && !wanted; ++q) {
         if (q == c.rank) continue;
         const bool in_strip = xs >= c.bounds[q] - c.depth && xs <= c.bounds[q + 1] + c.depth;
         const bool in_ival = st.x >= windows[q * wstride] - c.depth && st.x <= windows[q * wstride + 1] + c.depth;
-        wanted = in_strip || in_ival;
+        if (!f.p2p) {
+            wanted = in_strip || in_ival;
+        } else if (in_strip || in_ival || q == new_owner) {
+            const int slot = atomicAdd(&f.dest_count[q], 1);
+            if (slot < f.cap) {                           // overflow is reported through the header count
+                double2* rec = reinterpret_cast<double2*>(f.peer_inbox[q] + inbox_offset(f, t & 1, c.rank) + (size_t)(slot + 1) * SREC);
+                rec[0] = make_double2((double)a, st.x);   // three 16-byte stores into peer memory
+                rec[1] = make_double2(st.y, st.z);
+                rec[2] = make_double2(st.w, (double)new_owner);
+                wrote = true;
+            }
+        }
     }
+    if (wrote) __threadfence_system();                    // the flag that follows (k_shard_flag) must not overtake these stores
     if (wanted) {
         const int slot = atomicAdd(c.counter, 1);
-        if (slot < cap) {                                  // overflow is reported through the header count
-            double* rec = buf + (size_t)(slot + 1) * SREC;
+        if (slot < f.cap) {                                // overflow is reported through the header count
+            double* rec = f.buf + (size_t)(slot + 1) * SREC;
             rec[0] = (double)a; rec[1] = st.x; rec[2] = st.y; rec[3] = st.z; rec[4] = st.w; rec[5] = (double)new_owner;
         }
     }
@@ -941,20 +979,12 @@ __device__ __forceinline__ void shard_interval_flush(const ShardCtl& c, long lon
     }
 }
 
-// arguments of the pack step when it is fused into the closed final kernel (device-resident: the CUDA graph
-// of a step stays valid when buffers change)
-struct ShardFuse {
-    ShardCtl ctl;
-    const double* windows;
-    long long wstride;
-    double* buf;
-    int cap;
-};
-
 // double integrator exactly in numpy's evaluation order (no FMA contraction), then bin the new position
-__device__ __forceinline__ double4 integrate_and_bin(const Params& p, int a, const double4 s, float u0, float u1,
+// (u0, u1): the action as float64 -- exactly (double)fp32 for the policy's own actions (learner/gnn_dagger.py:161), the
+// controller's float64 value when the expert drives the env (learner/gnn_dagger.py:156-163)
+__device__ __forceinline__ double4 integrate_and_bin(const Params& p, int a, const double4 s, double u0, double u1,
                                                      double (&racc)[4]) {
-    double ax = __dmul_rn((double)u0, p.gain), ay = __dmul_rn((double)u1, p.gain);
+    double ax = __dmul_rn(u0, p.gain), ay = __dmul_rn(u1, p.gain);
     if (p.amask && p.amask[a] == 0) { ax = 0.0; ay = 0.0; }      // u * mask (leaders keep their velocity)
     double nx = __dadd_rn(s.x, __dmul_rn(s.z, p.dt));
     double ny = __dadd_rn(s.y, __dmul_rn(s.w, p.dt));
@@ -1026,14 +1056,15 @@ __device__ __forceinline__ void reward_block_flush(const Params& p, const double
 
 #ifdef FGNN_MAIN_TU
 // first half of env.step(u) with an externally supplied action
-__global__ void __launch_bounds__(256) k_integrate(Params p, const float* __restrict__ u) {
+template <typename T2>      // float2: select_action's fp32 action; double2: the controller's float64 action
+__global__ void __launch_bounds__(256) k_integrate(Params p, const T2* __restrict__ u) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double racc[4] = {0, 0, 0, 0};
     if (i < owned_count(p)) {
         const int a = owned_agent(p, i);
         if (a >= 0) {
-            const float2 uu = reinterpret_cast<const float2*>(u)[i];      // u is in owned-list order
-            integrate_and_bin(p, a, ldg256(&p.state[a]), uu.x, uu.y, racc);
+            const T2 uu = u[i];                                            // u is in owned-list order
+            integrate_and_bin(p, a, ldg256(&p.state[a]), (double)uu.x, (double)uu.y, racc);
         }
     }
     reward_block_flush<256>(p, racc);
@@ -1081,8 +1112,9 @@ __global__ void __launch_bounds__(256) k_vel_sum(Params p, double* __restrict__ 
     atomicAdd(&vsum[ep * 2 + 1], s.w);
 }
 
+template <typename T2>      // float2 / double2 output
 __global__ void __launch_bounds__(128) k_controller(Params p, int centralized, int window, double grad_cut /* comm_radius */,
-                                                    double max_u, const double* __restrict__ vsum, float* __restrict__ out) {
+                                                    double max_u, const double* __restrict__ vsum, T2* __restrict__ out) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= sorted_count(p)) return;
     const int a = p.sorted_id[s];
@@ -1127,7 +1159,10 @@ __global__ void __launch_bounds__(128) k_controller(Params p, int centralized, i
     double ux = -gx - dvx, uy = -gy - dvy;
     ux = fmin(fmax(ux, -max_u), max_u) / p.gain;
     uy = fmin(fmax(uy, -max_u), max_u) / p.gain;
-    reinterpret_cast<float2*>(out)[a] = make_float2((float)ux, (float)uy);
+    T2 o;
+    o.x = (decltype(o.x))ux;
+    o.y = (decltype(o.y))uy;
+    out[a] = o;
 }
 
 
@@ -1148,20 +1183,20 @@ __global__ void __launch_bounds__(128) k_controller(Params p, int centralized, i
 //   k_shard_unpack  : install received states; new owner -> appended to the owned list, otherwise ghost list; bin
 // A rank's window = its strip +- depth, united with the x-interval of what it still owns +- depth.
 // ------------------------------------------------------------------------------------------
-__global__ void k_shard_prepare(ShardCtl c, int advance) {
+__global__ void k_shard_prepare(ShardCtl c, int advance, int* dest_count) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         *c.n_ghost = 0; *c.counter = 0;
         if (advance) *c.shift += c.dshift;
     }
+    if (dest_count && threadIdx.x < c.world) dest_count[threadIdx.x] = 0;
 }
 
-__global__ void __launch_bounds__(256) k_shard_pack(Params p, ShardCtl c, const double* __restrict__ windows, long long wstride,
-                                                    double* __restrict__ buf, int cap) {
+__global__ void __launch_bounds__(256) k_shard_pack(Params p, ShardFuse f) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     long long klo = 0x7fffffffffffffffll, khi = -0x7fffffffffffffffll - 1;
     const int a = i < owned_count(p) ? owned_agent(p, i) : -1;
-    if (a >= 0) shard_pack_agent(p, c, windows, wstride, buf, cap, i, a, p.state[a], klo, khi);
-    shard_interval_flush<256>(c, klo, khi);
+    if (a >= 0) shard_pack_agent(p, f, i, a, p.state[a], klo, khi);
+    shard_interval_flush<256>(f.ctl, klo, khi);
 }
 
 // header record [count, x_lo, x_hi, 0, 0, 0]: reduce the per-block intervals written by k_shard_pack
@@ -1186,11 +1221,64 @@ __global__ void __launch_bounds__(256) k_shard_header(ShardCtl c, double* __rest
     }
 }
 
+// grid = (record chunks, world): a block of sender q leaves at once when q sent fewer records than its first slot.
+// parity_stride != 0 (p2p inbox): this step's records sit in half t & 1 of `recv`.
+// p2p transport, after the final kernel has stored the records into the peers' inboxes: header [count, x_lo, x_hi] of this
+// rank into every peer's inbox (and its own), then -- fenced -- the flag word t + 1 that tells the peer its half t & 1 is
+// complete.  One block; thread q serves peer q.
+__global__ void __launch_bounds__(256) k_shard_flag(Params p, ShardFuse f, int n_blocks) {
+    __shared__ long long s_lo[8], s_hi[8];
+    const ShardCtl& c = f.ctl;
+    long long klo = 0x7fffffffffffffffll, khi = -0x7fffffffffffffffll - 1;
+    for (int i = threadIdx.x; i < n_blocks; i += blockDim.x) {
+        klo = min(klo, c.xminmax[2 * i]);
+        khi = max(khi, c.xminmax[2 * i + 1]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        klo = min(klo, __shfl_xor_sync(0xffffffffu, klo, o));
+        khi = max(khi, __shfl_xor_sync(0xffffffffu, khi, o));
+    }
+    if ((threadIdx.x & 31) == 0) { s_lo[threadIdx.x >> 5] = klo; s_hi[threadIdx.x >> 5] = khi; }
+    __syncthreads();
+    for (int w = 0; w < 8; ++w) { klo = min(klo, s_lo[w]); khi = max(khi, s_hi[w]); }
+    const int t = *p.t;
+    const int q = threadIdx.x;
+    if (q < c.world) {
+        double* hdr = f.peer_inbox[q] + inbox_offset(f, t & 1, c.rank);
+        hdr[0] = q == c.rank ? 0.0 : (double)f.dest_count[q];
+        hdr[1] = dunkey(klo); hdr[2] = dunkey(khi);
+        hdr[3] = 0.0; hdr[4] = 0.0; hdr[5] = 0.0;
+        __threadfence_system();
+        if (q != c.rank) {
+            volatile int* flag = f.peer_flags[q] + (t & 1) * c.world + c.rank;
+            *flag = t + 1;
+        }
+    }
+}
+
+// ... and the receiving side: wait until every peer's flag of half t & 1 says t + 1.  A peer that never arrives (crashed
+// rank) must not hang the GPU: after ~2 s the wait gives up and raises the sticky overflow flag (value 2).
+__global__ void k_shard_wait(Params p, ShardFuse f) {
+    const ShardCtl& c = f.ctl;
+    const int t = *p.t;
+    const int q = threadIdx.x;
+    if (q < c.world && q != c.rank) {
+        volatile const int* flag = f.peer_flags[c.rank] + (t & 1) * c.world + q;
+        const long long t0 = clock64();
+        while (*flag != t + 1) {
+            __nanosleep(200);
+            if (clock64() - t0 > 4000000000ll) { *p.overflow = 2; break; }
+        }
+        __threadfence_system();
+    }
+}
+
 __global__ void __launch_bounds__(256) k_shard_unpack(Params p, ShardCtl c, const double* __restrict__ recv /* [world][cap+1][SREC] */,
-                                                      int cap) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    const int q = idx / cap, r = idx % cap;
-    if (q >= c.world || q == c.rank) return;
+                                                      int cap, long long parity_stride) {
+    const int q = blockIdx.y, r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q == c.rank) return;
+    recv += (size_t)(*p.t & 1) * parity_stride;
     const double* base = recv + (size_t)q * (cap + 1) * SREC;
     const int count = (int)base[0];
     if (r == 0 && count > cap) *p.overflow = 1;

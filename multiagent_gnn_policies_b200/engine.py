@@ -10,16 +10,18 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfgnn.so")
+LIB_PATH = os.environ.get("FGNN_LIB") or os.path.join(_HERE, "libfgnn.so")      # FGNN_LIB: A/B of differently built libraries
 
 ABI_SYMBOLS = [
     "fgnn_last_error", "fgnn_version", "fgnn_create", "fgnn_destroy", "fgnn_set_weights", "fgnn_reset",
-    "fgnn_set_state", "fgnn_build_graph", "fgnn_integrate", "fgnn_env_step", "fgnn_policy", "fgnn_controller", "fgnn_step",
+    "fgnn_set_state", "fgnn_build_graph", "fgnn_integrate", "fgnn_env_step", "fgnn_integrate_f64", "fgnn_env_step_f64",
+    "fgnn_policy", "fgnn_controller", "fgnn_controller_f64", "fgnn_step",
     "fgnn_rollout", "fgnn_actor_forward_dense", "fgnn_get_state", "fgnn_get_features", "fgnn_get_degrees",
     "fgnn_get_aggregated", "fgnn_get_action", "fgnn_export_network_dense", "fgnn_get_csr", "fgnn_get_stats",
     "fgnn_shard_configure", "fgnn_shard_local_step", "fgnn_shard_pack", "fgnn_shard_unpack", "fgnn_shard_step_begin",
     "fgnn_shard_step_end", "fgnn_shard_owned", "fgnn_profile_step", "fgnn_memcpy_sync", "fgnn_launch_count",
     "fgnn_set_agent_mask", "fgnn_set_dt", "fgnn_comm_unique_id", "fgnn_comm_init", "fgnn_shard_step",
+    "fgnn_p2p_alloc", "fgnn_p2p_connect", "fgnn_p2p_seed", "fgnn_shard_step_p2p",
     "fgnn_trainer_create", "fgnn_trainer_destroy", "fgnn_trainer_param_count", "fgnn_trainer_launch_count",
     "fgnn_trainer_step",
 ]
@@ -76,6 +78,9 @@ def load_library(path=None):
     lib.fgnn_build_graph.argtypes = [vp, i32, vp]
     lib.fgnn_integrate.argtypes = [vp, vp, vp, vp]
     lib.fgnn_env_step.argtypes = [vp, vp, vp, vp]
+    lib.fgnn_integrate_f64.argtypes = [vp, vp, vp, vp]
+    lib.fgnn_env_step_f64.argtypes = [vp, vp, vp, vp]
+    lib.fgnn_controller_f64.argtypes = [vp, i32, ctypes.c_double, vp, vp]
     lib.fgnn_policy.argtypes = [vp, vp, vp]
     lib.fgnn_controller.argtypes = [vp, i32, ctypes.c_double, vp, vp]
     lib.fgnn_step.argtypes = [vp, vp, vp, vp]
@@ -104,6 +109,10 @@ def load_library(path=None):
     lib.fgnn_comm_unique_id.argtypes = [vp]
     lib.fgnn_comm_init.argtypes = [vp, vp, i32, i32]
     lib.fgnn_shard_step.argtypes = [vp, vp, vp, i32, vp]
+    lib.fgnn_p2p_alloc.argtypes = [vp, i32, i32, i32, vp, ctypes.POINTER(vp)]
+    lib.fgnn_p2p_connect.argtypes = [vp, vp, vp]
+    lib.fgnn_p2p_seed.argtypes = [vp, vp, vp]
+    lib.fgnn_shard_step_p2p.argtypes = [vp, vp]
     lib.fgnn_set_agent_mask.argtypes = [vp, vp, vp]
     lib.fgnn_set_dt.argtypes = [vp, dbl]
     lib.fgnn_trainer_create.argtypes = [i32, i32, i32, i32, ctypes.POINTER(vp)]
@@ -185,7 +194,11 @@ class FlockEngine:
         return self._torch.cuda.current_stream(self.device).cuda_stream
 
     def sync(self):
-        self._torch.cuda.current_stream(self.device).synchronize()
+        """Wait for the stream the engine enqueues on (an explicit ``stream=`` handle, else torch's current stream)."""
+        if self._stream is not None:
+            self._torch.cuda.ExternalStream(self._stream, device=self.device).synchronize()
+        else:
+            self._torch.cuda.current_stream(self.device).synchronize()
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
@@ -240,26 +253,32 @@ class FlockEngine:
         self.step_index += int(bool(advance))
 
     def _as_action(self, u):
+        """(array, is_f64): float64 actions (the controller's, learner/gnn_dagger.py:156-163) stay float64; everything
+        else is taken as fp32 (select_action's ``action.cpu().numpy()``, learner/gnn_dagger.py:161)."""
         if hasattr(u, "data_ptr"):
-            assert u.dtype == self._torch.float32 and u.numel() == self.rows_io * 2
-            return u.contiguous()
-        u = np.ascontiguousarray(u, dtype=np.float32)
+            assert u.dtype in (self._torch.float32, self._torch.float64) and u.numel() == self.rows_io * 2
+            return u.contiguous(), u.dtype == self._torch.float64
+        u = np.asarray(u)
+        f64 = u.dtype == np.float64
+        u = np.ascontiguousarray(u, dtype=np.float64 if f64 else np.float32)
         assert u.size == self.rows_io * 2
-        return u
+        return u, f64
 
     def integrate(self, u, want_reward=False):
-        u = self._as_action(u)
+        u, f64 = self._as_action(u)
         r = np.empty(self.n_episodes, dtype=np.float64) if want_reward else None
-        self._check(self.lib.fgnn_integrate(self._h, _ptr(u), _ptr(r), self.stream))
+        fn = self.lib.fgnn_integrate_f64 if f64 else self.lib.fgnn_integrate
+        self._check(fn(self._h, _ptr(u), _ptr(r), self.stream))
         if isinstance(u, np.ndarray) or want_reward:
             self.sync()
         return r
 
     def env_step(self, u):
         """env.step(u): integrate + rebuild graph/features; returns the per-episode reward (B,) f64."""
-        u = self._as_action(u)
+        u, f64 = self._as_action(u)
         r = np.empty(self.n_episodes, dtype=np.float64)
-        self._check(self.lib.fgnn_env_step(self._h, _ptr(u), _ptr(r), self.stream))
+        fn = self.lib.fgnn_env_step_f64 if f64 else self.lib.fgnn_env_step
+        self._check(fn(self._h, _ptr(u), _ptr(r), self.stream))
         self.step_index += 1
         self.sync()
         return r
@@ -275,11 +294,14 @@ class FlockEngine:
             self.sync()
         return out
 
-    def controller(self, centralized=True, max_accel=1.0, out=None):
-        """Expert controller action (B*N,2) fp32 for the current state (env.env.controller)."""
+    def controller(self, centralized=True, max_accel=1.0, out=None, dtype=np.float32):
+        """Expert controller action (B*N,2) for the current state (env.env.controller): fp32, or float64 as gym_flock
+        returns it (``dtype=np.float64`` or a float64 ``out``)."""
         if out is None:
-            out = np.empty((self.M, 2), dtype=np.float32)
-        self._check(self.lib.fgnn_controller(self._h, int(bool(centralized)), float(max_accel), _ptr(out), self.stream))
+            out = np.empty((self.M, 2), dtype=dtype)
+        f64 = (out.dtype == np.float64) if isinstance(out, np.ndarray) else (out.dtype == self._torch.float64)
+        fn = self.lib.fgnn_controller_f64 if f64 else self.lib.fgnn_controller
+        self._check(fn(self._h, int(bool(centralized)), float(max_accel), _ptr(out), self.stream))
         if isinstance(out, np.ndarray):
             self.sync()
         return out
@@ -434,6 +456,31 @@ class FlockEngine:
     def shard_step(self, send_buf, recv_buf, cap):
         """The whole sharded step as one CUDA graph with the NCCL all-gather inside."""
         self._check(self.lib.fgnn_shard_step(self._h, _ptr(send_buf), _ptr(recv_buf), cap, self.stream))
+        self.step_index += 1
+
+    # p2p halo transport: records stored straight into the peers' inboxes (CUDA-IPC over NVLink), one graph per step
+    def p2p_alloc(self, world, rank, cap):
+        """Allocate this rank's inbox; returns (64-byte cudaIpcMemHandle_t as bytes, local device pointer)."""
+        handle = ctypes.create_string_buffer(64)
+        ptr = ctypes.c_void_p()
+        self._check(self.lib.fgnn_p2p_alloc(self._h, int(world), int(rank), int(cap), ctypes.addressof(handle), ctypes.byref(ptr)))
+        return handle.raw, ptr.value
+
+    def p2p_connect(self, handles=None, direct_ptrs=None):
+        """``handles``: the ranks' IPC handles concatenated in rank order (separate processes); or ``direct_ptrs``: the
+        inbox device pointers of ranks living in this process."""
+        if direct_ptrs is not None:
+            arr = (ctypes.c_void_p * len(direct_ptrs))(*direct_ptrs)
+            self._check(self.lib.fgnn_p2p_connect(self._h, None, ctypes.addressof(arr)))
+        else:
+            buf = ctypes.create_string_buffer(bytes(handles), len(handles))
+            self._check(self.lib.fgnn_p2p_connect(self._h, ctypes.addressof(buf), None))
+
+    def p2p_seed(self, gathered):
+        self._check(self.lib.fgnn_p2p_seed(self._h, _ptr(gathered), self.stream))
+
+    def shard_step_p2p(self):
+        self._check(self.lib.fgnn_shard_step_p2p(self._h, self.stream))
         self.step_index += 1
 
     def shard_owned(self):

@@ -118,6 +118,20 @@ class CudaShardBackend:
     def step_fused(self, send, recv, cap):
         self.engine.shard_step(send, recv, cap)
 
+    # p2p transport: records go straight into the peers' inboxes (CUDA-IPC mappings over NVLink); no collective in the step
+    def p2p_alloc(self, world, rank, cap):
+        return self.engine.p2p_alloc(world, rank, cap)
+
+    def p2p_connect(self, handles=None, direct_ptrs=None):
+        self.engine.p2p_connect(handles=handles, direct_ptrs=direct_ptrs)
+        self.p2p = True
+
+    def p2p_seed(self, gathered):
+        self.engine.p2p_seed(gathered)
+
+    def step_p2p(self):
+        self.engine.shard_step_p2p()
+
     def owned(self):
         return self.engine.shard_owned()
 
@@ -185,9 +199,22 @@ class ShardedFlock:
         self.recv = self.all_gather(self.send)
         self.backend.unpack(self.recv, self.cap)
 
+    def enable_p2p(self, all_gather_object):
+        """Switch the halo of the following steps to peer-to-peer stores (call once, right after ``reset``):
+        every rank allocates its inbox, the CUDA-IPC handles are exchanged with ``all_gather_object(obj) -> list`` (e.g.
+        torch.distributed.all_gather_object), the peers' inboxes are mapped, and the buffer gathered by the reset-time
+        exchange seeds the inbox headers.  The ranks must be processes of one node whose GPUs have peer access."""
+        handle, _ = self.backend.p2p_alloc(self.world, self.rank, self.cap)
+        handles = all_gather_object(handle)
+        self.backend.p2p_connect(handles=b"".join(handles))
+        self.backend.p2p_seed(self.recv)
+
     def step(self):
         """One closed-loop step: local policy + integrator for owned agents, halo exchange, rebuild."""
         stride = (self.cap + 1) * RECORD
+        if getattr(self.backend, "p2p", False):          # one CUDA graph, halo records stored straight into the peers' inboxes
+            self.backend.step_p2p()
+            return
         if getattr(self.backend, "native_comm", False):  # CUDA backend with its own communicator: one graph per step
             self.backend.step_fused(self.send, self.recv, self.cap)
             return
@@ -207,6 +234,26 @@ class ShardedFlock:
         self.backend.integrate(action_host)       # H2D
         self._exchange(self.recv, (self.cap + 1) * RECORD, advance=True)
         self.backend.build(True)
+
+
+def connect_p2p_local(flocks):
+    """Ranks that live in ONE process (tests): wire their inboxes with direct device pointers.  Every flock must run on its
+    own CUDA stream -- a rank's step graph waits inside the device for the flags of its peers."""
+    ptrs = [f.backend.p2p_alloc(f.world, f.rank, f.cap)[1] for f in flocks]
+    for f in flocks:
+        f.backend.p2p_connect(direct_ptrs=ptrs)
+        f.backend.p2p_seed(f.recv)
+
+
+def torch_all_gather_object(world):
+    """``all_gather_object`` closure on torch.distributed (default group) for ``ShardedFlock.enable_p2p``."""
+    import torch.distributed as dist
+
+    def gather(obj):
+        out = [None] * world
+        dist.all_gather_object(out, obj)
+        return out
+    return gather
 
 
 def nccl_all_gather(world, cap, device):

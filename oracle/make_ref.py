@@ -22,7 +22,10 @@ REF = os.environ.get("FGNN_REFERENCE", "/root/reference")
 HERE = os.path.dirname(os.path.abspath(__file__))
 DST = os.path.join(HERE, "_ref")
 FILES = ["learner/__init__.py", "learner/actor.py", "learner/state_with_delay.py", "learner/gnn_dagger.py",
-         "learner/replay_buffer.py", "cfg/dagger.cfg"]
+         "learner/replay_buffer.py", "cfg/dagger.cfg",
+         # the reference's own entry scripts and shipped checkpoint: tests/test_gpu_reference_scripts.py runs them UNCHANGED
+         # through multiagent_gnn_policies_b200.run (the learner modules they import are then the compat ones)
+         "test_model.py", "train.py", "models/actor_FlockingRelative-v0_dagger_k3"]
 
 
 def make(ref=REF, dst=DST, quiet=False):

@@ -70,13 +70,5 @@ def main():
               f"bit-identical={same}  [{kern}] sum={sum(per.values()) * 1e3:.1f}", flush=True)
 
 
-    if os.environ.get("FGNN_TRY_READOUT3") == "1":
-        # EXPERIMENTAL two-warp readout (readout_mode = 3, csrc/fgnn_final_tc2.cuh): not validated in round 1
-        env = {"FGNN_ADJ_MODE": "1", "FGNN_LAST_HOP_SEPARATE": "1", "FGNN_SCAN_TWO_PASS": "1", "FGNN_PDL": "0"}
-        ms, per, st = run(n, steps, env, x0, sd, readout_mode=3)
-        kern = " ".join(f"{k_}={v * 1e3:.1f}" for k_, v in per.items())
-        print(f"readout_mode=3: {ms * 1e3:.1f} us/step  bit-identical={bool(np.array_equal(st, ref_state))}  [{kern}]", flush=True)
-
-
 if __name__ == "__main__":
     main()

@@ -1,8 +1,9 @@
-"""torchrun check of the NCCL halo path (run on >= 2 GPUs):
+"""torchrun check of the multi-GPU halo paths on REAL ranks (run on >= 2 GPUs; tests/test_gpu_sharding_ranks.py spawns it):
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
-        scripts/check_sharded_nccl.py
-Every rank shards one flock by index, rolls out T steps with one all-gather per step, and rank 0 compares the
-owned slices of all ranks with a single unsharded engine."""
+        scripts/check_sharded_nccl.py [p2p|gather|native]
+Every rank shards one flock by index, rolls out T steps, and rank 0 compares the owned slices of all ranks with a single
+unsharded engine, bit for bit.  Transports: p2p (default: records stored straight into the peers' inboxes over NVLink, one
+CUDA graph per step), gather (torch.distributed all-gather between two graph halves), native (ncclAllGather inside the graph)."""
 import os
 import sys
 
@@ -22,7 +23,8 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    n_total, steps, K, R = 200_000, 60, 3, 1.0
+    mode = sys.argv[1] if len(sys.argv) > 1 else "p2p"
+    n_total, steps, K, R = int(os.environ.get("FGNN_CHECK_N", "200000")), int(os.environ.get("FGNN_CHECK_STEPS", "60")), 3, 1.0
     g = np.load(os.path.join(ROOT, "tests", "golden", "ckpt_n100_k3.npz"))
     sd = {k[3:]: g[k] for k in g.files if k.startswith("sd.")}
     x0 = make_workload(n_total, seed=5)
@@ -35,8 +37,10 @@ def main():
     be.engine.load_state_dict(sd)
     flock = parallel.ShardedFlock(be, rank, world, K, R, cap, parallel.nccl_all_gather(world, cap, be.device))
     flock.reset(x0, ranges)
-    if os.environ.get("FGNN_NATIVE_COMM", "0") == "1":
+    if mode == "native":
         be.init_comm(rank, world)              # one CUDA graph per step with ncclAllGather inside
+    elif mode == "p2p":
+        flock.enable_p2p(parallel.torch_all_gather_object(world))
     for _ in range(steps):
         flock.step()
     torch.cuda.synchronize()
@@ -58,7 +62,7 @@ def main():
         ref = single.get_state()
         one_owner = bool((cnt_all == 1).all().item())
         ok = one_owner and np.array_equal(x_all.cpu().numpy(), ref)
-        print("sharded NCCL rollout == single engine:", ok, "| one owner per agent:", one_owner, "| world", world,
+        print(f"sharded rollout ({mode}) == single engine:", ok, "| one owner per agent:", one_owner, "| world", world,
               "| owned now", ids.size, "of initial", cnt, "| overflow", be.overflow())
     dist.barrier()
     dist.destroy_process_group()

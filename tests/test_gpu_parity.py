@@ -5,12 +5,28 @@ import os
 import numpy as np
 import pytest
 
-from conftest import rel_inf, load_golden, golden_names
+from conftest import ROOT, rel_inf, load_golden, golden_names
 from oracle import flock_env, learner, sparse
 
 pytestmark = pytest.mark.gpu
 
 TOL_ACTION = 1e-5       # north_star: actions within 1e-5 relative (inf-norm) fp32
+
+
+def log_parity(tag, act, act_oracle, truth):
+    """The tests that compare at large N accept max(1e-5, c x the fp32 oracle's own error against float64): print (and, on
+    the GPU box, append to gpurun_out/parity_ratios.log) the observed numbers so it is visible how often the relaxed branch
+    decides."""
+    e_cuda, e_oracle, e_pair = rel_inf(act, truth), rel_inf(act_oracle, truth), rel_inf(act, act_oracle)
+    line = (f"[parity] {tag}: cuda-vs-f64 {e_cuda:.3e}  oracle(fp32)-vs-f64 {e_oracle:.3e}  cuda-vs-oracle {e_pair:.3e}  "
+            f"strict(1e-5)={'pass' if max(e_cuda, e_pair) <= TOL_ACTION else 'RELAXED'}")
+    print(line)
+    out = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out):
+        with open(os.path.join(out, "parity_ratios.log"), "a") as f:
+            f.write(line + "\n")
+
+
 TOL_FEATURE = 2e-7      # fp32 rounding of a float64-accurate sum
 
 
@@ -24,8 +40,6 @@ def make_engine(g, **kw):
 
 FFMA, TENSOR = 1, 2      # fgnn_config.readout_mode
 READOUTS = [FFMA, TENSOR]
-if os.environ.get("FGNN_TEST_READOUT3") == "1":
-    READOUTS.append(3)   # experimental two-warp tensor-core readout (csrc/fgnn_final_tc2.cuh), not validated in round 1
 
 
 @pytest.mark.parametrize("name", golden_names())
@@ -222,11 +236,15 @@ def test_large_n_against_sparse_oracle(n, R, hidden):
         # Yardstick: the same inputs evaluated in float64.  The CUDA path must be as close to it as the
         # fp32 oracle (the reference arithmetic) is, or within the 1e-5 bar.
         truth = sparse.readout(layers, sstate.aggregate(np.float64), np.float64)
+        log_parity(f"large_n n={n} h={hidden} t={t}", act, act_o, truth)
         assert rel_inf(act, truth) <= max(TOL_ACTION, 4.0 * rel_inf(act_o, truth))
         assert rel_inf(act, act_o) <= max(TOL_ACTION, 8.0 * rel_inf(act_o, truth))
         # drive the env with the expert (DAGGER with beta = 1): keeps agents apart, so |features| stay
         # O(1e3) and the fp32 readout stays well conditioned (a random policy makes agents collide)
-        u = sparse.controller_sparse(x, R).astype(np.float32)
+        # ... with its float64 action, NOT cast to fp32: the reference steps the env with the controller's own array
+        # (learner/gnn_dagger.py:156-163), the engine integrates it through fgnn_env_step_f64
+        u = sparse.controller_sparse(x, R)
+        assert u.dtype == np.float64
         x = flock_env.integrate(x, u, 0.01)
         eng.env_step(u)
         np.testing.assert_array_equal(eng.get_state(), x)
@@ -341,10 +359,11 @@ def test_architecture_sweep_against_dense_oracle(k, hidden, n_layers, mean_pooli
             sv_s, deg_s, ei, ej = sparse.compute_helpers_sparse(x, 1.2)
             sstate = sparse.SparseDelayState(sv_s, sparse.network_csr(n, deg_s, ei, ej, mean_pooling), prev_state=sstate, k=k)
             truth = sparse.readout(layers, sstate.aggregate(np.float64), np.float64)
+            log_parity(f"sweep k={k} h={hidden} l={n_layers} mp={int(mean_pooling)} readout={readout} t={t}", a, a_ref, truth)
             assert rel_inf(a, truth) <= max(TOL_ACTION, 3.0 * rel_inf(a_ref, truth)), (readout, t)
             assert rel_inf(a, a_ref) <= max(3.0 * TOL_ACTION, 6.0 * rel_inf(a_ref, truth)), (readout, t)
             # the expert drives (a random policy lets agents collide, |features| -> 1e6, fp32 ill-conditioned)
-            u = flock_env.controller(x, 1.2, 1.2 ** 2, centralized=False).astype(np.float32)
+            u = flock_env.controller(x, 1.2, 1.2 ** 2, centralized=False)       # float64, as gym_flock returns it
             eng.env_step(u)
             x = flock_env.integrate(x, u, 0.01)
             np.testing.assert_array_equal(eng.get_state(), x)
@@ -402,3 +421,115 @@ def test_full_size_one_million_agents():
     assert not eng.stats()["overflow"] and not other.stats()["overflow"]
     eng.close()
     other.close()
+
+    # aggregated features and actions at full size: three expert-driven steps (float64 controller action, as
+    # learner/gnn_dagger.py:156-163 steps the env) against the edge-list oracle, like the 20k-agent test
+    layers = learner.weights_from_state_dict(g["state_dict"])
+    eng = new_engine()
+    x, sstate = x0, None
+    for t in range(3):
+        sv, deg, oi, oj = sparse.compute_helpers_sparse(x, R)
+        assert np.array_equal(eng.get_degrees(), deg)
+        assert rel_inf(eng.get_features(), sv.astype(np.float32)) <= TOL_FEATURE
+        sstate = sparse.SparseDelayState(sv, sparse.network_csr(n, deg, oi, oj), prev_state=sstate, k=3)
+        act = eng.policy().cpu().numpy()
+        assert rel_inf(eng.get_aggregated(), sstate.aggregate()) <= 2e-6
+        act_o = sparse.readout(layers, sstate.aggregate())
+        truth = sparse.readout(layers, sstate.aggregate(np.float64), np.float64)
+        log_parity(f"one_million t={t}", act, act_o, truth)
+        assert rel_inf(act, truth) <= max(TOL_ACTION, 4.0 * rel_inf(act_o, truth))
+        assert rel_inf(act, act_o) <= max(TOL_ACTION, 8.0 * rel_inf(act_o, truth))
+        u = sparse.controller_sparse(x, R)
+        x = flock_env.integrate(x, u, 0.01)
+        eng.env_step(u)
+        np.testing.assert_array_equal(eng.get_state(), x)
+    assert not eng.stats()["overflow"]
+    eng.close()
+
+
+@pytest.mark.parametrize("centralized", [False, True])
+def test_float64_action_path(centralized):
+    """env.step(env.controller()) (learner/gnn_dagger.py:156-163, learner/gnn_baseline.py:16-17): the controller's action
+    is a float64 array and the reference steps the env with it as it is.  The engine's float64 entry points
+    (fgnn_controller_f64 -> fgnn_env_step_f64) must (a) integrate a float64 action bit for bit like the oracle -- the
+    oracle's action is NOT rounded to fp32 first -- and (b) produce a controller action equal to the oracle's to float64
+    accuracy, so that the closed expert loop stays on the oracle's trajectory far below fp32 resolution."""
+    from multiagent_gnn_policies_b200.engine import FlockEngine
+    n, R = 400, 1.0
+    x = flock_env.synthetic_state(n, seed=21, density=1.6)
+    eng = FlockEngine(n_agents=n, comm_radius=R, edge_capacity=64)
+    eng.reset(x)
+    xe = x.copy()                                           # trajectory driven by the ENGINE's float64 controller
+    for t in range(5):
+        u_ref = flock_env.controller(x, R, R * R, centralized=centralized)
+        assert u_ref.dtype == np.float64 and np.any(u_ref != u_ref.astype(np.float32))     # genuinely float64 values
+        u = eng.controller(centralized=centralized, dtype=np.float64)
+        assert u.dtype == np.float64
+        np.testing.assert_allclose(u, u_ref, rtol=1e-9, atol=1e-11)
+        # (a) teacher-forced: the oracle's own float64 action through the engine's integrator
+        eng.env_step(u_ref)
+        x = flock_env.integrate(x, u_ref, 0.01)
+        np.testing.assert_array_equal(eng.get_state(), x)
+        # the fp32 entry point on the same action differs (that is what the old path did)
+        assert not np.array_equal(flock_env.integrate(xe, u_ref.astype(np.float32), 0.01), flock_env.integrate(xe, u_ref, 0.01))
+        xe = x
+    # torch float64 CUDA tensors take the same path
+    import torch
+    u_ref = flock_env.controller(x, R, R * R, centralized=centralized)
+    eng.env_step(torch.from_numpy(u_ref).cuda())
+    np.testing.assert_array_equal(eng.get_state(), flock_env.integrate(x, u_ref, 0.01))
+    eng.close()
+
+
+@pytest.mark.parametrize("n,episodes,k,radius,tail_only", [
+    (100, 1, 3, 1.0, False),          # 10 x 10 grid: every window wraps around the seam
+    (3000, 1, 3, 1.0, True),
+    (20000, 1, 4, 1.0, False),
+    (5000, 1, 2, 1.0, False),
+    (4000, 1, 1, 1.0, False),
+    (500, 6, 3, 1.0, False),          # batched episodes
+    (3000, 1, 3, 3.0, False),         # ~45 neighbours: cell rows longer than 32 candidates, rows longer than the staged
+                                      # neighbour list, windows that must be subdivided to fit the stage
+    (2500, 1, 3, 2.0, True),
+])
+def test_tile_kernel_equals_separate_kernels(n, episodes, k, radius, tail_only, monkeypatch):
+    """k_tile (FGNN_STEP_MODE=1: adjacency + features + first hop fused per cell tile, TMA-staged, fp32 pre-filter with the
+    float64 test for pairs inside the margin) must leave the same bits as k_adjacency_t + k_hop (FGNN_STEP_MODE=0): degrees,
+    features, aggregated z, actions and the integrated state, over a closed-loop rollout."""
+    from multiagent_gnn_policies_b200.engine import FlockEngine
+    rng = np.random.default_rng(n + k)
+    sd = _random_state_dict(rng, k, 32, 2)
+    x0 = np.concatenate([flock_env.synthetic_state(n, seed=7 + e, density=1.6) for e in range(episodes)])
+    cap = int(max(48, 3.5 * np.pi * radius ** 2 * 1.6 + 16))
+    runs = []
+    for mode in ("0", "1"):
+        monkeypatch.setenv("FGNN_STEP_MODE", mode)
+        eng = FlockEngine(n_agents=n, n_episodes=episodes, k=k, hidden=32, n_layers=2, comm_radius=radius, dt=0.01,
+                          edge_capacity=cap, csr_tail_only=(tail_only and mode == "1"))
+        eng.load_state_dict(sd)
+        eng.reset(x0)
+        out = []
+        for t in range(8):
+            a = np.empty((n * episodes, 2), np.float32)
+            d, f = eng.get_degrees(), eng.get_features()
+            eng.policy(out=a)
+            out.append((d, f, eng.get_aggregated(), a.copy(), eng.get_state()))
+            eng.env_step(a * 0.05)        # a tame closed loop (random weights): agents keep moving across cells
+        eng.rollout(6)                    # ... and the CUDA-graph replay of the same kernels
+        out.append((eng.get_degrees(), eng.get_features(), eng.get_state()))
+        assert not eng.stats()["overflow"]
+        if mode == "1" and not tail_only:
+            rs, dg, cols, _ = eng.csr()   # full CSR rows in tile mode too: same neighbour order as the ELL head
+            runs.append((out, np.concatenate([cols[rs[a_]:rs[a_] + dg[a_]] for a_ in range(min(n * episodes, 500))])))
+        elif mode == "0":
+            rs, dg, cols, _ = eng.csr()
+            runs.append((out, np.concatenate([cols[rs[a_]:rs[a_] + dg[a_]] for a_ in range(min(n * episodes, 500))])))
+        else:
+            runs.append((out, None))
+        eng.close()
+    (a_out, a_cols), (b_out, b_cols) = runs
+    for t, (ra, rb) in enumerate(zip(a_out, b_out)):
+        for u, v in zip(ra, rb):
+            np.testing.assert_array_equal(u, v, err_msg=f"step {t}")
+    if b_cols is not None:
+        np.testing.assert_array_equal(a_cols, b_cols)

@@ -1,0 +1,93 @@
+"""The reference's OWN entry scripts, unchanged, on this engine: `python -m multiagent_gnn_policies_b200.run
+<reference>/test_model.py <cfg>` and `.../train.py <cfg>` (test_model.py:14-47, train.py:15-43).
+
+The scripts come from a reference checkout named by FGNN_REFERENCE, else from the byte-for-byte copies
+`oracle/make_ref.py` stages under oracle/_ref/ (git-ignored; travels to the GPU box).  Skipped when neither is there."""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def _reference_dir():
+    for cand in (os.environ.get("FGNN_REFERENCE"), os.path.join(ROOT, "oracle", "_ref")):
+        if cand and os.path.exists(os.path.join(cand, "test_model.py")) and os.path.exists(os.path.join(cand, "train.py")):
+            return cand
+    return None
+
+
+REF = _reference_dir()
+needs_ref = pytest.mark.skipif(REF is None, reason="no reference checkout (FGNN_REFERENCE) and no oracle/_ref staging")
+
+CFG = """[DEFAULT]
+alg = dagger
+batch_size = 4
+buffer_size = 500
+updates_per_step = 2
+seed = 11
+actor_lr = 5e-5
+n_train_episodes = 2
+beta_coeff = 0.993
+test_interval = 1
+n_test_episodes = 1
+k = 3
+hidden_size = 32
+gamma = 0.99
+tau = 0.5
+env = FlockingRelative-v0
+v_max = 3.0
+comm_radius = 1.0
+n_agents = 100
+n_actions = 2
+n_states = 6
+debug = True
+header = reward
+dt = 0.01
+
+[test]
+fname = fgnn_ref_script_test
+"""
+
+
+def _run(script, cfg_path, cwd_models=None):
+    env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    return subprocess.run([sys.executable, "-m", "multiagent_gnn_policies_b200.run", os.path.join(REF, script), cfg_path],
+                          capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
+
+
+@needs_ref
+def test_reference_test_model_py_runs_unchanged(tmp_path):
+    """test_model.py loads models/actor_FlockingRelative-v0_dagger_k3 (the shipped checkpoint) and rolls the policy out for
+    n_test_episodes episodes of 200 steps, printing the header and every episode's summed reward."""
+    cfg = tmp_path / "model_test.cfg"
+    cfg.write_text(CFG)
+    out = _run("test_model.py", str(cfg))
+    assert out.returncode == 0, out.stderr[-3000:]
+    lines = [ln.strip() for ln in out.stdout.splitlines() if ln.strip()]
+    assert lines[0] == "reward"
+    rewards = [float(ln) for ln in lines[1:] if re.fullmatch(r"-?\d+(\.\d+)?(e-?\d+)?", ln)]
+    assert len(rewards) == 1 and rewards[0] < 0.0            # minus the summed velocity variance of 200 steps
+    # the trained policy flocks: far better than the ~ -2 * v_max^2/3 * 200 = -1200 of agents that never align
+    assert rewards[0] > -600.0, rewards
+
+
+@needs_ref
+def test_reference_train_py_two_dagger_episodes(tmp_path):
+    """train.py with a two-episode DAGGER cfg: expert labels, replay, gradient steps, evaluation -- the reference's loop
+    (learner/gnn_dagger.py:126-243 as mirrored by the compat learner) driving the CUDA engine."""
+    cfg = tmp_path / "train_test.cfg"
+    cfg.write_text(CFG)
+    out = _run("train.py", str(cfg))
+    assert out.returncode == 0, out.stderr[-3000:]
+    assert "reward" in out.stdout
+    nums = re.findall(r"-?\d+\.\d+", out.stdout)
+    assert nums, out.stdout[-2000:]
+    for f in os.listdir(os.path.join(REF, "models")) if os.path.isdir(os.path.join(REF, "models")) else []:
+        if "fgnn_ref_script_test" in f:                       # checkpoints the run saved next to the script
+            os.remove(os.path.join(REF, "models", f))

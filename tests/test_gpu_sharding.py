@@ -9,20 +9,26 @@ from oracle import flock_env
 pytestmark = pytest.mark.gpu
 
 
-def make_world(n_total, world, sd, k=3, hidden=32, comm_radius=1.0, cap=None, **kw):
+def make_world(n_total, world, sd, k=3, hidden=32, comm_radius=1.0, cap=None, own_streams=False, **kw):
+    import torch
     from multiagent_gnn_policies_b200 import parallel
     ranges = parallel.shard_ranges(n_total, world)
     cap = cap or n_total
     flocks = []
     for rank, (lo, cnt) in enumerate(ranges):
+        if own_streams:                          # p2p: a rank's step graph waits on the device for its peers' flags
+            stream = torch.cuda.Stream()
+            kw = dict(kw, stream=stream.cuda_stream)
         be = parallel.CudaShardBackend(n_total, lo, cnt, ghost_capacity=n_total, k=k, hidden=hidden,
                                        n_layers=2, comm_radius=comm_radius, dt=0.01, edge_capacity=64, **kw)
+        if own_streams:
+            be._stream_keepalive = stream
         be.engine.load_state_dict(sd)
         flocks.append(parallel.ShardedFlock(be, rank, world, k, comm_radius, cap, all_gather=None))
     return flocks, ranges
 
 
-def drive(flocks, ranges, x0, steps, know_all=True, graphs=False, frame_velocity=0.0):
+def drive(flocks, ranges, x0, steps, know_all=True, graphs=False, frame_velocity=0.0, p2p=False):
     """Lock-step driver: what ShardedFlock.reset/step do, with the collective replaced by a stack."""
     from multiagent_gnn_policies_b200 import parallel
     import torch
@@ -32,7 +38,9 @@ def drive(flocks, ranges, x0, steps, know_all=True, graphs=False, frame_velocity
     shared = torch.zeros((world, flocks[0].cap + 1, parallel.RECORD), dtype=torch.float64, device="cuda")
 
     def gather():
+        torch.cuda.synchronize()                 # (the ranks may run on their own streams)
         shared.copy_(torch.stack([f.send for f in flocks]))
+        torch.cuda.synchronize()
         for f in flocks:
             f.recv = shared
 
@@ -55,9 +63,17 @@ def drive(flocks, ranges, x0, steps, know_all=True, graphs=False, frame_velocity
     for f in flocks:
         f.backend.unpack(shared, f.cap)
         f.backend.build(False)
+    if p2p:
+        torch.cuda.synchronize()
+        parallel.connect_p2p_local(flocks)
+        torch.cuda.synchronize()
     out = []
     for _ in range(steps):
-        if graphs:                               # CUDA-graph replayed halves
+        if p2p:                                  # one graph per rank, launched on the ranks' own streams; the halo records
+            for f in flocks:                     # travel as plain stores into the peers' inboxes, flags order them
+                f.backend.step_p2p()
+            torch.cuda.synchronize()
+        elif graphs:                             # CUDA-graph replayed halves
             for f in flocks:
                 f.backend.step_begin(shared.reshape(-1)[1:], stride, f.send, f.cap)
             gather()
@@ -84,7 +100,9 @@ def drive(flocks, ranges, x0, steps, know_all=True, graphs=False, frame_velocity
 
 
 @pytest.mark.parametrize("world,n_total,order,graphs", [(2, 3000, "sorted", False), (4, 5000, "sorted", True),
-                                                        (3, 1500, "random", False), (2, 2000, "random", True)])
+                                                        (3, 1500, "random", False), (2, 2000, "random", True),
+                                                        (2, 3000, "sorted", "p2p"), (4, 5000, "sorted", "p2p"),
+                                                        (3, 1500, "random", "p2p")])
 def test_sharded_equals_single_engine(world, n_total, order, graphs):
     from multiagent_gnn_policies_b200.engine import FlockEngine
     g = load_golden("ckpt_n100_k3")
@@ -97,8 +115,9 @@ def test_sharded_equals_single_engine(world, n_total, order, graphs):
     single = FlockEngine(n_agents=n_total, k=3, hidden=32, n_layers=2, comm_radius=1.0, dt=0.01, edge_capacity=64)
     single.load_state_dict(g["state_dict"])
     single.reset(x0)
-    flocks, ranges = make_world(n_total, world, g["state_dict"])
-    got, bounds = drive(flocks, ranges, x0, steps, know_all=(order != "sorted"), graphs=graphs)
+    p2p = graphs == "p2p"
+    flocks, ranges = make_world(n_total, world, g["state_dict"], own_streams=p2p)
+    got, bounds = drive(flocks, ranges, x0, steps, know_all=(order != "sorted"), graphs=bool(graphs) and not p2p, p2p=p2p)
     for t in range(steps):
         single.step(None, None)
         # same kernels, same per-row neighbour order (cell lists are canonical) -> identical bits,

@@ -144,3 +144,64 @@ def test_stochastic_variant_draws_dt_per_step():
         dts.append(env.dt)
         np.testing.assert_array_equal(env.x, flock_env.integrate(x0, u, env.dt))
     assert len(set(dts)) == 5 and min(dts) >= env.dt_min
+
+
+def test_env_oracle_against_real_gym_flock():
+    """Pin of the env oracle against the real package (github.com/katetolstaya/gym-flock, un-vendored and un-pinned by the
+    reference: README.md:7, train.py:6).  gym_flock is not installed in this image, so this test SKIPS here and the env
+    side stays `parity unpinned`; wherever the package is importable it compares, on the package's own reset state:
+    state_values / state_network of compute_helpers, the double-integrator step, the reward and both controllers."""
+    import sys
+    # the REAL package only: the compat shim of the same name (multiagent_gnn_policies_b200/compat, possibly put on
+    # sys.path by an earlier test) is the thing under test elsewhere, not a pin
+    shim = [m for m in list(sys.modules) if m == "gym_flock" or m.startswith("gym_flock.")]
+    saved_modules = {m: sys.modules.pop(m) for m in shim}
+    saved_path = list(sys.path)
+    sys.path[:] = [q for q in sys.path if "multiagent_gnn_policies_b200" not in q]
+    try:
+        gym_flock = pytest.importorskip("gym_flock")
+    finally:
+        sys.path[:] = saved_path
+        if "gym_flock" not in sys.modules:
+            sys.modules.update(saved_modules)
+    import configparser
+    cp = configparser.ConfigParser()
+    cp.read_dict({"DEFAULT": {"comm_radius": "1.0", "n_agents": "60", "v_max": "3.0", "dt": "0.01"}})
+    env = gym_flock.envs.FlockingRelativeEnv()
+    env.params_from_cfg(cp["DEFAULT"])
+    np.random.seed(7)
+    values, network = env.reset()
+    x = np.array(env.x, dtype=np.float64)
+    R2 = float(env.comm_radius2)
+    for t in range(5):
+        sv, sn, _, _ = flock_env.compute_helpers(x, R2, mean_pooling=bool(getattr(env, "mean_pooling", True)))
+        np.testing.assert_allclose(values, sv, rtol=1e-12, atol=1e-12)
+        np.testing.assert_array_equal(np.asarray(network) != 0, sn != 0)
+        np.testing.assert_allclose(network, sn, rtol=1e-15, atol=0)
+        for centralized in (True, False):
+            u_env = np.asarray(env.controller(centralized))
+            u_or = flock_env.controller(x, float(env.comm_radius), R2, centralized=centralized,
+                                        max_accel=float(getattr(env, "max_accel", 1.0)),
+                                        action_scalar=float(getattr(env, "action_scalar", 10.0)))
+            np.testing.assert_allclose(u_env, u_or, rtol=1e-10, atol=1e-12)
+        u = np.asarray(env.controller(False))
+        (values, network), reward, done, _ = env.step(u)
+        x = flock_env.integrate(x, u, float(env.dt), action_scalar=float(getattr(env, "action_scalar", 10.0)))
+        np.testing.assert_array_equal(np.asarray(env.x, dtype=np.float64), x)
+        assert reward == pytest.approx(flock_env.instant_cost(x), rel=1e-12)
+        assert done is False or done == 0
+
+
+def test_reference_staging_is_byte_identical():
+    """oracle/_ref (bench.py's reference leg, tests/test_gpu_reference_scripts.py) holds byte-for-byte copies: the sha256
+    of every staged file equals the manifest written when it was copied from the reference tree; when that tree is here
+    the copies are compared with it directly."""
+    import filecmp
+    import os
+    from oracle import make_ref
+    if not make_ref.available():
+        pytest.skip("oracle/_ref not staged (run `python -m oracle.make_ref` where the reference tree is present)")
+    assert make_ref.verify()
+    if os.path.isdir(os.path.join(make_ref.REF, "learner")):
+        for rel in make_ref.FILES:
+            assert filecmp.cmp(os.path.join(make_ref.REF, rel), os.path.join(make_ref.DST, rel), shallow=False), rel
