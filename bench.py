@@ -128,14 +128,63 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def kernel_source_sha():
+    """sha1 over the CUDA sources: profiles/r2_traffic.json records the build its ncu capture was taken from."""
+    import hashlib
+    h = hashlib.sha1()
+    csrc = os.path.join(ROOT, "multiagent_gnn_policies_b200", "csrc")
+    for name in sorted(os.listdir(csrc)):
+        if name.endswith((".cu", ".cuh")):
+            h.update(open(os.path.join(csrc, name), "rb").read())
+    return h.hexdigest()[:16]
+
+
 def ncu_traffic(kernel):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full`
-    capture of this workload (profiles/r1_traffic.json), or None."""
-    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full` capture of
+    this workload (profiles/r2_traffic.json, written by scripts/ncu_summary.py), or None when the capture is of another
+    build of the kernels (the file records the source hash it was taken from)."""
+    path = os.path.join(ROOT, "profiles", "r2_traffic.json")
     try:
-        return json.load(open(path)).get(kernel)
+        t = json.load(open(path))
+        if t.get("_kernel_source_sha") != kernel_source_sha():
+            return None
+        return t.get(kernel)
     except Exception:
         return None
+
+
+def small_config_c1(sd, local_rank, steps=2000):
+    """BASELINE config C1 (cfg/dagger.cfg: N = 100, K = 3, H = 32) on this engine: the size the reference itself runs, for a
+    like-for-like ratio against the N = 100 cell of `cpu_baseline` (agent-steps/s, device-resident and through host buffers)."""
+    import torch
+    from multiagent_gnn_policies_b200.engine import FlockEngine
+    n = 100
+    eng = FlockEngine(n_agents=n, k=3, hidden=32, n_layers=2, comm_radius=1.0, dt=0.01, device=local_rank)
+    eng.load_state_dict(sd)
+    eng.reset(make_workload(n, seed=11))
+    eng.rollout(50)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    eng.rollout(steps)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    act = torch.empty((n, 2), dtype=torch.float32, pin_memory=True).numpy()
+    rew = np.empty(1, np.float64)
+    for _ in range(5):
+        eng.policy(out=act)
+        eng.lib.fgnn_env_step(eng._h, act.ctypes.data, rew.ctypes.data, eng.stream)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(200):
+        eng.policy(out=act)
+        eng.lib.fgnn_env_step(eng._h, act.ctypes.data, rew.ctypes.data, eng.stream)
+        torch.cuda.current_stream().synchronize()
+    e2e_ms = (time.perf_counter() - t0) / 200 * 1e3
+    eng.close()
+    return {"workload": "C1: FlockingRelative N=100 K=3 H=32 (cfg/dagger.cfg)", "value": n / (ms * 1e-3), "unit": UNIT,
+            "us_per_step": ms * 1e3, "e2e_value": n / (e2e_ms * 1e-3), "e2e_us_per_step": e2e_ms * 1e3}
 
 
 def measured_peaks():
@@ -388,7 +437,8 @@ def main():
     peak, peak_src = measured_peaks()
     # SURVEY.md 8(d) algorithmic bytes per agent per launch (K=3; fp32 values, int32 CSR, 16 B state)
     d = deg_prof
-    alg_bytes = {"adjacency": 44 + 4 * d, "hop0": 104 + 4 * d, "final": 120 + 4 * d}
+    alg_bytes = {"adjacency": 44 + 4 * d, "hop0": 104 + 4 * d, "final": 120 + 4 * d,
+                 "tile": 148 + 8 * d}          # k_tile = adjacency + features + first hop in one kernel: K1 + K2 of SURVEY 8(d)
     if "hop_last" in prof:
         # the last hop runs as its own launch: SURVEY's K3 row splits into the gather (CSR 4d+4, deg 4, source rows 24,
         # z_2 written 24) and the streaming readout + integrator (x_t, z_1, z_2 24 each, state 16 in / 16 out, action 8)
@@ -410,14 +460,21 @@ def main():
                           "achieved": step_bytes * value / world / 1e9, "frac": step_bytes * value / world / 1e9 / peak}
     roof["per_kernel_frac"] = {k_: round(alg_bytes[k_] * N / (v * 1e-3) / 1e9 / peak, 4) for k_, v in prof.items()
                                if k_ in alg_bytes and args.k == 3}
-    if dom == "adjacency":
+    if dom in ("adjacency", "tile"):
         roof["note"] = ("the dominant kernel is the float64 pair test + feature kernel: 64 algorithmic bytes per agent but "
                         "~14 candidate pairs per agent in float64 -- issue/fp64-pipe bound, not HBM bound (profiles/)")
 
-    cb = None
+    cb, equal_n = None, None
     if not args.no_cpu_baseline:
         cb, _, _ = run_cpu_reference([args.cpu_sample] if args.cpu_sample > 0 else [100, 1000], 5, 2, args.hidden, args.k,
                                      args.n_layers)
+        if args.hidden == 32 and args.k == 3 and args.n_layers == 2:
+            # like for like: BASELINE config C1 (the reference's own N = 100) on this engine against the N = 100 cell
+            equal_n = small_config_c1(sd, local_rank)
+            ref100 = max([c["agent_steps_per_s"] for c in cb["cells"] if c["n_agents"] == 100] or [0.0])
+            if ref100 > 0:
+                equal_n.update(reference_value=ref100, ratio_device=equal_n["value"] / ref100,
+                               ratio_e2e=equal_n["e2e_value"] / ref100)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -426,15 +483,18 @@ def main():
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": UNIT, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
                     "h2d_bytes_per_step": int(N * 2 * 4), "d2h_bytes_per_step": int(N * 2 * 4 + 8)},
-            "roofline": roof, "cpu_baseline": cb}
+            "roofline": roof, "cpu_baseline": cb, "equal_n": equal_n}
     print(json.dumps(line))
 
 
-def run_sharded(args, rank, world, local_rank, N, side, sd, weights_note, edge_cap, config, barrier, max_over_ranks):
-    """N > 1: ONE flock of world*N agents, sharded by index (rank r owns the r-th strip of N agents), one
-    NCCL halo all-gather per step (multiagent_gnn_policies_b200.parallel).  Weak scaling: N agents per GPU."""
+def sharded_rollout(args, rank, world, local_rank, n_per_rank, sd, edge_cap, barrier, max_over_ranks, steps, warmup,
+                    want_e2e=False, sample_clocks=False):
+    """ONE flock of world * n_per_rank agents, sharded by index into x-strips (rank r owns the r-th strip), closed-loop
+    rollout with the per-step halo exchange.  Returns a dict (identical on every rank up to the rank-0-only fields)."""
     import torch
     from multiagent_gnn_policies_b200 import parallel
+    N = n_per_rank
+    side = np.sqrt(N / DENSITY)
     n_total = world * N
     ranges = parallel.shard_ranges(n_total, world)
     lo, cnt = ranges[rank]
@@ -464,62 +524,87 @@ def run_sharded(args, rank, world, local_rank, N, side, sd, weights_note, edge_c
     if halo == "p2p":
         # default: halo records stored straight into the peers' inboxes over NVLink (CUDA-IPC), one CUDA graph per step
         flock.enable_p2p(parallel.torch_all_gather_object(world))
-    elif os.environ.get("FGNN_NATIVE_COMM", "0") == "1" or halo == "native":
-        # opt-in: the all-gather inside ONE step graph on the engine's own communicator (fgnn_shard_step).  Measured at 2
-        # GPUs: 5.45e9 vs 5.50e9 agent-steps/s for the default (torch.distributed between two graph halves) -- the
-        # sharded step's extra ~70 us is not the collective's launch path -- so the simpler default stays.
-        be.init_comm(rank, world)
-    for _ in range(args.warmup):
+        transport = "p2p stores into the peers' inboxes over NVLink (CUDA-IPC), one CUDA graph per step, no collective"
+    elif halo == "native":
+        be.init_comm(rank, world)               # ncclAllGather inside ONE step graph on the engine's own communicator
+        transport = "ncclAllGather inside the step graph"
+    else:
+        transport = "NCCL all-gather via torch.distributed between two graph halves"
+    for _ in range(warmup):
         flock.step()
     barrier()
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and sample_clocks:
         sampler.start()
     l0 = be.engine.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         flock.step()
     e1.record()
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
     launches = be.engine.launch_count() - l0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop() if (rank == 0 and sample_clocks) else None
     st = be.engine.stats()
     if st["overflow"]:
-        raise RuntimeError("capacity overflow (edges / halo) during the timed region: results void")
-    value = n_total * args.steps / (ms * 1e-3)
-    ghosts = int(flock.recv[:, 0, 0].sum().item())
-    owned_now = len(be.owned())
+        raise RuntimeError(f"capacity overflow / halo time-out ({st['overflow']}) during the timed region: results void")
+    out = {"n_agents_total": n_total, "n_agents_per_gpu": N, "value": n_total * steps / (ms * 1e-3), "ms_per_step": ms / steps,
+           "launches": int(launches), "clocks": clocks, "ghosts": int(st.get("n_ghosts", 0)), "owned": len(be.owned()),
+           "mean_degree": st["n_edges"] / max(1, cnt + int(st.get("n_ghosts", 0))), "transport": transport,
+           "halo_cap": flock.cap, "depth": flock.depth, "rows_io": be.engine.rows_io}
+    if want_e2e:
+        # e2e: the same step through host buffers (select_action -> pinned host -> env.step), gather transport
+        e2e_steps = args.e2e_steps or min(steps, 50)
+        act_host = torch.empty((be.engine.rows_io, 2), dtype=torch.float32, pin_memory=True).numpy()
+        for _ in range(3):
+            flock.step_host(act_host)
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(e2e_steps):
+            flock.step_host(act_host)
+        t1.record()
+        barrier()
+        e2e_ms = max_over_ranks(t0.elapsed_time(t1))
+        out.update(e2e_steps=e2e_steps, e2e_ms_per_step=e2e_ms / e2e_steps, e2e_value=n_total * e2e_steps / (e2e_ms * 1e-3))
+    be.engine.close()
+    barrier()
+    return out
 
-    # e2e: the same step through host buffers (select_action -> pinned host -> env.step)
-    e2e_steps = args.e2e_steps or min(args.steps, 50)
-    act_host = torch.empty((be.engine.rows_io, 2), dtype=torch.float32, pin_memory=True).numpy()
-    for _ in range(3):
-        flock.step_host(act_host)
-    barrier()
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0.record()
-    for _ in range(e2e_steps):
-        flock.step_host(act_host)
-    t1.record()
-    barrier()
-    e2e_ms = max_over_ranks(t0.elapsed_time(t1))
+
+def run_sharded(args, rank, world, local_rank, N, side, sd, weights_note, edge_cap, config, barrier, max_over_ranks):
+    """N > 1.  Headline (`value`, scaling "weak"): ONE flock of world * N agents, N per GPU.  Next to it the fixed-size runs
+    north_star names (`strong`): N agents IN TOTAL sharded over the GPUs (BASELINE config C5 at N = 1M) and config C4
+    (100 000 agents in total, up to 4 GPUs)."""
+    weak = sharded_rollout(args, rank, world, local_rank, N, sd, edge_cap, barrier, max_over_ranks, args.steps, args.warmup,
+                           want_e2e=True, sample_clocks=True)
+    strong = []
+    for n_total, label in ((N, f"C5: N={N} agents in total"), (100_000, "C4: N=100000 agents in total")):
+        if n_total % world or (n_total == 100_000 and world > 4) or n_total // world < 10_000:
+            continue
+        r = sharded_rollout(args, rank, world, local_rank, n_total // world, sd, edge_cap, barrier, max_over_ranks,
+                            max(args.steps, 200), max(args.warmup, 20))
+        strong.append({"workload": label, "n_agents_total": n_total, "n_agents_per_gpu": n_total // world, "value": r["value"],
+                       "unit": UNIT, "ms_per_step": r["ms_per_step"], "halo_records_per_step": r["ghosts"]})
     if rank != 0:
         return
     peak, peak_src = measured_peaks()
-    d = st["n_edges"] / max(1, (cnt + ghosts / world))
+    d = weak["mean_degree"]
     step_bytes = 268 + 12 * d
-    config = dict(config, parallelism=f"index-sharded x{world}, halo all-gather ({'NCCL inside the step graph' if getattr(be, 'native_comm', False) else 'NCCL via torch.distributed between two graph halves'}) of {flock.cap}-record buffers, "
-                                      f"halo depth {flock.depth:.2f}, ownership hand-over", n_agents_total=n_total)
+    value = weak["value"]
+    config = dict(config, parallelism=f"index-sharded x{world} (x-strips), halo: {weak['transport']}; {weak['halo_cap']}-record inboxes, "
+                                      f"halo depth {weak['depth']:.2f}, ownership hand-over", n_agents_total=weak["n_agents_total"])
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": weak["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 learner / f64 env", "data": f"synthetic ({weights_note})", "config": config,
-            "halo_records_per_step": ghosts, "owned_by_rank0_after_run": owned_now, "clocks": clocks, "gpu_launches": int(launches),
-            "e2e": {"value": n_total * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "steps": e2e_steps,
-                    "ms_per_step": e2e_ms / e2e_steps, "h2d_bytes_per_step": int(be.engine.rows_io * 2 * 4) * world,
-                    "d2h_bytes_per_step": int(be.engine.rows_io * 2 * 4) * world},
+            "halo_records_per_step": weak["ghosts"], "owned_by_rank0_after_run": weak["owned"], "clocks": weak["clocks"],
+            "gpu_launches": weak["launches"],
+            "e2e": {"value": weak["e2e_value"], "unit": UNIT, "steps": weak["e2e_steps"],
+                    "ms_per_step": weak["e2e_ms_per_step"], "h2d_bytes_per_step": int(weak["rows_io"] * 2 * 4) * world,
+                    "d2h_bytes_per_step": int(weak["rows_io"] * 2 * 4) * world},
+            "strong": strong,
             "roofline": {"bound": "hbm", "kernel": None, "unit": "GB/s", "peak": peak, "peak_source": peak_src,
                          "achieved": step_bytes * value / world / 1e9, "frac": step_bytes * value / world / 1e9 / peak,
                          "traffic": None, "note": "whole step per GPU (268 + 12 d) B per agent-step; per-kernel breakdown "

@@ -57,10 +57,11 @@ typedef struct fgnn_config {
 typedef struct fgnn_stats {
     int64_t step;            /* index t of the current graph (0 right after reset)            */
     int64_t n_edges;         /* directed edges of the current graph                           */
-    int32_t overflow;        /* 1 if the edge capacity was exceeded at any time (results void) */
+    int32_t overflow;        /* 1: an edge / halo capacity was exceeded at some point (results void); 2: a p2p halo wait timed out */
     int32_t grid_dim;
     int64_t n_cells;
     int64_t edge_capacity;   /* total directed-edge capacity                                   */
+    int64_t n_ghosts;        /* sharded handle: agents received from other ranks in the last exchange */
 } fgnn_stats;
 
 const char* fgnn_last_error(void);

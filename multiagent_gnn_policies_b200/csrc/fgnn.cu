@@ -338,6 +338,7 @@ extern "C" int fgnn_create(const fgnn_config* cfg, fgnn_handle** out) {
             ge.lo32 = std::nextafterf((float)(p.R2 - margin), -INFINITY);
             ge.hi32n = std::nextafterf(std::nextafterf((float)(p.R2 + margin), INFINITY), INFINITY);
             ge.csr_tail_only = (cfg->flags & FGNN_FLAG_CSR_TAIL_ONLY) ? 1 : 0;
+            for (int d = 0; d < 64; ++d) ge.sinvtab[d] = cfg->mean_pooling ? (float)(1.0 / (double)(d > 0 ? d : 1)) : 1.0f;
             CK(cudaFuncSetAttribute((const void*)k_tile<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(1)));
             CK(cudaFuncSetAttribute((const void*)k_tile<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(2)));
             CK(cudaFuncSetAttribute((const void*)k_tile<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(3)));
@@ -1028,6 +1029,13 @@ extern "C" int fgnn_get_stats(fgnn_handle* h, fgnn_stats* out, void* stream) {
     out->grid_dim = h->p.G;
     out->n_cells = h->p.C;
     out->edge_capacity = h->p.nnz_cap;
+    out->n_ghosts = 0;
+    if (h->sharded) {
+        int ng = 0;
+        CK(cudaMemcpyAsync(&ng, h->d_counts + 2, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        out->n_ghosts = ng;
+    }
     return 0;
 }
 

@@ -90,6 +90,7 @@ struct TileGeom {
     float lo32, hi32n;        // r2_32 < lo32: inside for sure;  r2_32 >= hi32n: outside for sure
     float far32;              // |window-relative coordinate| beyond this: aliased agent, always the float64 test
     int csr_tail_only;        // 1: CSR rows only for agents with more than ELLW neighbours
+    float sinvtab[64];        // source scale by degree: (float)(1.0 / max(d, 1)) under mean pooling, else 1
 };
 
 #ifdef FGNN_MAIN_TU
@@ -186,7 +187,7 @@ __global__ void __launch_bounds__(TL_THREADS, FGNN_TL_MINBLOCKS) k_tile(Params p
         s_sp = 1;
         tl::mbar_init(tl::smem_u32(&s_mbar), 1);
     }
-    if (tid < 64) s_sinvtab[tid] = p.mean_pooling ? (float)(1.0 / (double)(tid > 0 ? tid : 1)) : 1.0f;
+    if (tid < 64) s_sinvtab[tid] = geo.sinvtab[tid];
     const int t = *p.t;
     const int g = slot_of(t, K);
     const size_t M = p.M;
@@ -394,21 +395,82 @@ __global__ void __launch_bounds__(TL_THREADS, FGNN_TL_MINBLOCKS) k_tile(Params p
             const bool own = ly >= 2 && ly <= H - 3 && lx >= 2 && lx <= W - 3;
             unsigned short* nb = s_nbr + (own ? s_baseB[ly] + i - s_cs[ly][2] : 0);
             const float2 me = s_xy[i];
+            const int c00 = s_cs[ly - 1][lx - 1], c10 = s_cs[ly][lx - 1], c20 = s_cs[ly + 1][lx - 1];
+            const int n0 = s_cs[ly - 1][lx + 2] - c00, n1 = s_cs[ly][lx + 2] - c10, n2 = s_cs[ly + 1][lx + 2] - c20;
+            const int n = n0 + n1 + n2;
             int cnt = 0;
+            if (n <= 32 && !far) {
+                // common case: ONE pair of sign masks over the three cell rows (candidate b of the concatenation = bit b):
+                // per candidate 4 fp32 instructions + 2 subtractions + 2 funnel shifts, nothing per row but the loop itself
+                unsigned in = 0, le = 0;
+                const float lo = geo.lo32, hi = geo.hi32n;
+                auto push = [&](int c0, int nr) {
+                    const float2* c = s_xy + c0;
+                    int k = 0;
 #pragma unroll 1
-            for (int dyi = 0; dyi < 3; ++dyi) {
-                const int r = ly + dyi - 1;
-                const int c0 = s_cs[r][lx - 1], c1 = s_cs[r][lx + 2];
-                for (int base = c0; base < c1; base += 32) {
-                    unsigned acc = tile_filter(s_xy, s_st, geo, p.R2, i, me, far, base, min(32, c1 - base));
-                    if (!own) {
-                        cnt += __popc(acc);
-                    } else {
-                        while (acc) {
-                            const int j = base + __ffs(acc) - 1;
-                            acc &= acc - 1;
-                            if (cnt < TL_NBR) nb[cnt * TL_CAP] = (unsigned short)j;
-                            ++cnt;
+                    for (; k + 2 <= nr; k += 2) {
+                        const float2 o0 = c[k], o1 = c[k + 1];
+                        const float dx0 = me.x - o0.x, dy0 = me.y - o0.y, dx1 = me.x - o1.x, dy1 = me.y - o1.y;
+                        const float r20 = fmaf(dx0, dx0, dy0 * dy0), r21 = fmaf(dx1, dx1, dy1 * dy1);
+                        in = __funnelshift_l(__float_as_uint(r20 - lo), in, 1);
+                        le = __funnelshift_l(__float_as_uint(r20 - hi), le, 1);
+                        in = __funnelshift_l(__float_as_uint(r21 - lo), in, 1);
+                        le = __funnelshift_l(__float_as_uint(r21 - hi), le, 1);
+                    }
+                    if (k < nr) {
+                        const float2 o0 = c[k];
+                        const float dx0 = me.x - o0.x, dy0 = me.y - o0.y;
+                        const float r20 = fmaf(dx0, dx0, dy0 * dy0);
+                        in = __funnelshift_l(__float_as_uint(r20 - lo), in, 1);
+                        le = __funnelshift_l(__float_as_uint(r20 - hi), le, 1);
+                    }
+                };
+                push(c00, n0);
+                push(c10, n1);
+                push(c20, n2);
+                if (n > 0) {
+                    in = __brev(in) >> (32 - n);             // the first candidate was shifted in first
+                    le = __brev(le) >> (32 - n);
+                    const unsigned self = 1u << (n0 + i - c10);
+                    in &= ~self;
+                    unsigned amb = le & ~in & ~self;
+                    auto staged = [&](int b) { return b < n0 ? c00 + b : (b < n0 + n1 ? c10 + b - n0 : c20 + b - n0 - n1); };
+                    if (amb) {                               // rare: the float64 test numpy evaluates
+                        const double2 a2 = *reinterpret_cast<const double2*>(&s_st[i]);
+                        do {
+                            const int b = __ffs(amb) - 1;
+                            amb &= amb - 1;
+                            const double2 o2 = *reinterpret_cast<const double2*>(&s_st[staged(b)]);
+                            if (r2_exact(a2.x - o2.x, a2.y - o2.y) < p.R2) in |= 1u << b;
+                        } while (amb);
+                    }
+                    cnt = __popc(in);
+                    if (own) {
+                        int e = 0;
+                        while (in && e < TL_NBR) {
+                            const int b = __ffs(in) - 1;
+                            in &= in - 1;
+                            nb[e * TL_CAP] = (unsigned short)staged(b);
+                            ++e;
+                        }
+                    }
+                }
+            } else {
+#pragma unroll 1
+                for (int dyi = 0; dyi < 3; ++dyi) {
+                    const int r = ly + dyi - 1;
+                    const int c0 = s_cs[r][lx - 1], c1 = s_cs[r][lx + 2];
+                    for (int base = c0; base < c1; base += 32) {
+                        unsigned acc = tile_filter(s_xy, s_st, geo, p.R2, i, me, far, base, min(32, c1 - base));
+                        if (!own) {
+                            cnt += __popc(acc);
+                        } else {
+                            while (acc) {
+                                const int j = base + __ffs(acc) - 1;
+                                acc &= acc - 1;
+                                if (cnt < TL_NBR) nb[cnt * TL_CAP] = (unsigned short)j;
+                                ++cnt;
+                            }
                         }
                     }
                 }

@@ -46,6 +46,7 @@ class FgnnStats(ctypes.Structure):
     _fields_ = [
         ("step", ctypes.c_int64), ("n_edges", ctypes.c_int64), ("overflow", ctypes.c_int32),
         ("grid_dim", ctypes.c_int32), ("n_cells", ctypes.c_int64), ("edge_capacity", ctypes.c_int64),
+        ("n_ghosts", ctypes.c_int64),
     ]
 
 
@@ -420,8 +421,8 @@ class FlockEngine:
     def stats(self):
         s = FgnnStats()
         self._check(self.lib.fgnn_get_stats(self._h, ctypes.byref(s), self.stream))
-        return {"step": s.step, "n_edges": s.n_edges, "overflow": bool(s.overflow), "grid_dim": s.grid_dim,
-                "n_cells": s.n_cells, "edge_capacity": s.edge_capacity}
+        return {"step": s.step, "n_edges": s.n_edges, "overflow": int(s.overflow), "grid_dim": s.grid_dim,
+                "n_cells": s.n_cells, "edge_capacity": s.edge_capacity, "n_ghosts": s.n_ghosts}
 
     # -- multi-GPU pieces (orchestrated by parallel.ShardedFlock) ---------------------------
     def shard_configure(self, bounds, world, rank, depth, margin, dshift, handover_after):

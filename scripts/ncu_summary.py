@@ -15,8 +15,9 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
         "l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
         "l1tex__t_sector_hit_rate.pct", "smsp__thread_inst_executed_per_inst_executed.ratio"]
-SHORT = {"k_final_tc": "final", "k_final": "final", "k_scan": "scan", "k_scatter": "scatter", "k_canon": "canon",
-         "k_adjacency_t": "adjacency", "k_hop<2": "hop0", "k_hop<3": "hop0", "k_hop<1": "hop_last"}
+SHORT = {"k_final_tc": "final", "k_final": "final", "k_scan_sums": "scan_sums", "k_scan": "scan", "k_scatter": "scatter",
+         "k_canon": "canon", "k_adjacency_t": "adjacency", "k_tile": "tile", "k_hop<2": "hop0", "k_hop<3": "hop0",
+         "k_hop<(int)2": "hop0", "k_hop<(int)3": "hop0", "k_hop<1": "hop_last", "k_hop<(int)1": "hop_last"}
 
 
 def main():
@@ -50,6 +51,10 @@ def main():
                 traffic[short] = rd * scale[units[ix["dram__bytes_read.sum"]]] + wr * scale[units[ix["dram__bytes_write.sum"]]]
                 break
     open(out_md, "w").write("\n".join(md) + "\n")
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from bench import kernel_source_sha
+    traffic["_kernel_source_sha"] = kernel_source_sha()     # bench.py drops `roofline.traffic` when the kernels have changed since
     json.dump(traffic, open(out_json, "w"), indent=1)
     print(json.dumps(traffic))
 

@@ -113,8 +113,9 @@ def test_two_flocks_env_steps_like_the_oracle(gym_mod):
         u = env.env.controller(False)
         u_ref = oracle.controller(False)
         assert np.abs(u - u_ref).max() <= 1e-6
+        assert u.dtype == np.float64                  # the expert's action stays float64 through env.step (gnn_dagger.py:156-163)
         obs, r, _, _ = env.step(u)
-        oracle.step(u.astype(np.float32))
+        oracle.step(u)
         np.testing.assert_array_equal(env.env.get_state(), oracle.x)
         _check_obs(obs, oracle.x, 1.0)
     env.close()
