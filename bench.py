@@ -550,6 +550,13 @@ def sharded_rollout(args, rank, world, local_rank, n_per_rank, sd, edge_cap, bar
     st = be.engine.stats()
     if st["overflow"]:
         raise RuntimeError(f"capacity overflow / halo time-out ({st['overflow']}) during the timed region: results void")
+    if os.environ.get("FGNN_BENCH_PROFILE") == "1" and halo == "p2p":
+        per = {}
+        for _ in range(10):                      # the p2p step kernel by kernel (CUDA events, un-graphed), every rank in step
+            for name, kms in be.engine.profile_step():
+                per[name] = per.get(name, 0.0) + kms / 10
+        print(f"[profile] rank {rank} N/gpu={N}: graph step {ms / steps * 1e3:.1f} us | "
+              + " ".join(f"{k}={v * 1e3:.1f}" for k, v in per.items()), file=sys.stderr, flush=True)
     out = {"n_agents_total": n_total, "n_agents_per_gpu": N, "value": n_total * steps / (ms * 1e-3), "ms_per_step": ms / steps,
            "launches": int(launches), "clocks": clocks, "ghosts": int(st.get("n_ghosts", 0)), "owned": len(be.owned()),
            "mean_degree": st["n_edges"] / max(1, cnt + int(st.get("n_ghosts", 0))), "transport": transport,

@@ -126,6 +126,7 @@ struct fgnn_handle {
     ShardFuse fuse_host;             // what d_fuse currently holds
     long long* d_xminmax = nullptr;
     double* d_shift = nullptr;
+    double* d_safe = nullptr;         // [2] interior x-interval of the step (k_shard_prepare)
     double* d_bounds = nullptr;      // [world + 1], allocated by fgnn_shard_configure
     int launch_pool = 0;             // grid sizing for kernels over the pool (pool capacity, or M)
     void* nccl_comm = nullptr;       // ncclComm_t of fgnn_comm_init (the halo all-gather inside the step graph)
@@ -299,6 +300,9 @@ extern "C" int fgnn_create(const fgnn_config* cfg, fgnn_handle** out) {
         h->pdl = pd ? atoi(pd) != 0 : FGNN_PDL_DEFAULT;
         const char* tp = getenv("FGNN_SCAN_TWO_PASS");
         h->scan_two_pass = tp ? atoi(tp) != 0 : FGNN_SCAN_TWO_PASS_DEFAULT;
+        const char* sb = getenv("FGNN_SUMS_IN_BIN");
+        p.sums_in_bin = (h->scan_two_pass && sb && atoi(sb) != 0) ? 1 : 0;   // opt-in; measured SLOWER at N=1M (299 vs 288 us/step): the warp-match +
+                                                                          // second atomic cost the final kernel more than the k_scan_sums launch, and k_scan then pays the cold read
         const char* lh = getenv("FGNN_LAST_HOP_SEPARATE");
         h->last_hop_separate = lh ? atoi(lh) != 0 : FGNN_LAST_HOP_SEPARATE_DEFAULT;
         CK(cudaFuncSetAttribute((const void*)k_adjacency_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -374,7 +378,8 @@ extern "C" int fgnn_create(const fgnn_config* cfg, fgnn_handle** out) {
     rc |= dalloc(h, &p.ybuf, 2 * K * M * ROW);
     rc |= dalloc(h, &p.action, M * 2);
     rc |= dalloc(h, &p.racc, (size_t)RSLOTS * p.B * 4);
-    rc |= dalloc(h, &p.racc_part, (size_t)(blocks_for(p.M, FINAL_THREADS) + 1) * 4);
+    // one row per block of the largest grid that integrates: the final kernel of a sharded handle walks pool_cap slots
+    rc |= dalloc(h, &p.racc_part, (size_t)(blocks_for(p.M > p.pool_cap ? p.M : p.pool_cap, FINAL_THREADS) + 1) * 4);
     rc |= dalloc(h, &p.n_partials, 1);
     rc |= dalloc(h, &p.reward, (size_t)p.B);
     rc |= dalloc(h, &p.reward_pending, 1);
@@ -388,6 +393,7 @@ extern "C" int fgnn_create(const fgnn_config* cfg, fgnn_handle** out) {
         rc |= dalloc(h, &h->d_counts, 4);
         rc |= dalloc(h, &h->d_xminmax, (size_t)2 * (blocks_for(p.pool_cap, FINAL_THREADS) + 1));
         rc |= dalloc(h, &h->d_shift, 1);
+        rc |= dalloc(h, &h->d_safe, 2);
         p.own = h->d_own;
         p.n_own_d = h->d_counts + 0;
         p.ghost = h->d_ghost;
@@ -399,6 +405,7 @@ extern "C" int fgnn_create(const fgnn_config* cfg, fgnn_handle** out) {
         h->ctl.counter = h->d_counts + 3;
         h->ctl.xminmax = h->d_xminmax;
         h->ctl.shift = h->d_shift;
+        h->ctl.safe = h->d_safe;
     }
     rc |= dalloc(h, &h->d_u_in, (M > (size_t)p.pool_cap ? M : (size_t)p.pool_cap) * 2 * 2);   // fp32 or float64 actions
     rc |= dalloc(h, &h->d_staging, K * M * F > (size_t)M * 4 * 2 ? K * M * F : (size_t)M * 4 * 2);
@@ -597,7 +604,7 @@ static int enqueue_build(fgnn_handle* h, int advance, cudaStream_t st) {
         k_bin<<<gb, 256, 0, st>>>(p);
         if (launch_check(h, "bin")) return 1;
     }
-    if (h->scan_two_pass) {
+    if (h->scan_two_pass && !p.sums_in_bin) {      // (sums_in_bin: the binning sites accumulated the tile sums already)
         launch_step(h, k_scan_sums, p.n_tiles, SCAN_THREADS, 0, st, p);
         if (launch_check(h, "scan_sums")) return 1;
     }
@@ -698,6 +705,7 @@ extern "C" int fgnn_set_state(fgnn_handle* h, const double* x, void* stream) {
     CK(cudaMemcpyAsync(h->p.state, x, (size_t)h->p.M * sizeof(double4), cudaMemcpyDefault, st));
     if (h->binned) {
         CK(cudaMemsetAsync(h->p.cell_count, 0, ((size_t)h->p.C + 1) * sizeof(int), st));
+        CK(cudaMemsetAsync(h->p.tile_status, 0, (size_t)h->p.n_tiles * sizeof(unsigned), st));
         CK(cudaMemsetAsync(h->p.racc, 0, (size_t)RSLOTS * h->p.B * 4 * sizeof(double), st));
         CK(cudaMemsetAsync(h->p.reward_pending, 0, sizeof(int), st));
         h->binned = false;
@@ -755,6 +763,7 @@ static int integrate_impl(fgnn_handle* h, const void* u, int f64, double* reward
     CK(cudaSetDevice(h->cfg.device));
     if (h->binned) {      // positions were binned already (closed-loop kernel or a previous integrate): start over
         CK(cudaMemsetAsync(p.cell_count, 0, ((size_t)p.C + 1) * sizeof(int), st));
+        CK(cudaMemsetAsync(p.tile_status, 0, (size_t)p.n_tiles * sizeof(unsigned), st));
         CK(cudaMemsetAsync(p.racc, 0, (size_t)RSLOTS * p.B * 4 * sizeof(double), st));
     }
     // sharded handle: u has pool_cap rows in owned-list order (rows beyond the owned count are ignored)
@@ -1080,11 +1089,11 @@ struct ShardGraph;
 static int enqueue_shard_pack(fgnn_handle* h, const double* windows, int64_t window_stride, double* send_buf, int cap,
                               int advance, cudaStream_t st) {
     Params& p = h->p;
-    k_shard_prepare<<<1, 32, 0, st>>>(h->ctl, advance, nullptr);
-    if (launch_check(h, "shard_prepare")) return 1;
     ShardFuse f;
     memset(&f, 0, sizeof f);
     f.ctl = h->ctl; f.windows = windows; f.wstride = window_stride; f.buf = send_buf; f.cap = cap;
+    k_shard_prepare<<<1, 256, 0, st>>>(p, f, advance);
+    if (launch_check(h, "shard_prepare")) return 1;
     k_shard_pack<<<blocks_for(p.pool_cap, 256), 256, 0, st>>>(p, f);
     if (launch_check(h, "shard_pack")) return 1;
     k_shard_header<<<1, 256, 0, st>>>(h->ctl, send_buf, blocks_for(p.pool_cap, 256));
@@ -1225,7 +1234,7 @@ extern "C" int fgnn_shard_step_begin(fgnn_handle* h, const double* windows, int6
     ShardGraph& g = shard_graphs(h)[0];
     int rc = run_cached_graph(h, g, nullptr, send_buf, h->shard_epoch, final_grid, 0, 0, 0.0, st, [&](cudaStream_t cs) {
         if (enqueue_hops(h, cs)) return 1;
-        k_shard_prepare<<<1, 32, 0, cs>>>(h->ctl, 1, nullptr);
+        k_shard_prepare<<<1, 256, 0, cs>>>(h->p, f, 1);
         if (launch_check(h, "shard_prepare")) return 1;
         if (enqueue_final(h, true, 0, cs, true)) return 1;
         k_shard_header<<<1, 256, 0, cs>>>(h->ctl, send_buf, final_grid);
@@ -1299,7 +1308,7 @@ extern "C" int fgnn_shard_step(fgnn_handle* h, double* send_buf, double* recv_bu
     ShardGraph& g = shard_graphs(h)[2];
     int rc = run_cached_graph(h, g, recv_buf, send_buf, h->shard_epoch, final_grid, cap, 0, 0.0, st, [&](cudaStream_t cs) {
         if (enqueue_hops(h, cs)) return 1;
-        k_shard_prepare<<<1, 32, 0, cs>>>(h->ctl, 1, nullptr);
+        k_shard_prepare<<<1, 256, 0, cs>>>(h->p, f, 1);
         if (launch_check(h, "shard_prepare")) return 1;
         if (enqueue_final(h, true, 0, cs, true)) return 1;
         k_shard_header<<<1, 256, 0, cs>>>(h->ctl, send_buf, final_grid);
@@ -1401,6 +1410,19 @@ extern "C" int fgnn_p2p_seed(fgnn_handle* h, const double* gathered, void* strea
     return 0;
 }
 
+static int enqueue_p2p_step(fgnn_handle* h, const ShardFuse& f, int final_grid, long long parity_stride, cudaStream_t cs) {
+    if (enqueue_hops(h, cs)) return 1;
+    k_shard_prepare<<<1, 256, 0, cs>>>(h->p, f, 1);
+    if (launch_check(h, "shard_prepare")) return 1;
+    if (enqueue_final(h, true, 0, cs, true)) return 1;
+    k_shard_flag<<<1, 256, 0, cs>>>(h->p, f, final_grid);
+    if (launch_check(h, "shard_flag")) return 1;
+    k_shard_wait<<<1, 256, 0, cs>>>(h->p, f);
+    if (launch_check(h, "shard_wait")) return 1;
+    if (enqueue_shard_unpack(h, h->p2p_inbox, h->p2p_cap, cs, parity_stride)) return 1;
+    return enqueue_build(h, 1, cs);
+}
+
 // One closed-loop step of a rank as ONE CUDA graph, halo over p2p stores:
 //   hops -> final (+ fused pack: records into the peers' inboxes) -> flag -> wait -> unpack -> scan/scatter/canon/adjacency
 extern "C" int fgnn_shard_step_p2p(fgnn_handle* h, void* stream) {
@@ -1420,18 +1442,8 @@ extern "C" int fgnn_shard_step_p2p(fgnn_handle* h, void* stream) {
     const int final_grid = h->use_tc ? h->tc_grid_closed : h->final_grid_closed;
     const long long parity_stride = (long long)(p2p_inbox_doubles(h->p2p_world, h->p2p_cap) / 2);
     ShardGraph& g = shard_graphs(h)[2];
-    int rc = run_cached_graph(h, g, h->p2p_inbox, h->d_peer_inbox, h->shard_epoch, final_grid, h->p2p_cap, 1, 0.0, st, [&](cudaStream_t cs) {
-        if (enqueue_hops(h, cs)) return 1;
-        k_shard_prepare<<<1, 256, 0, cs>>>(h->ctl, 1, h->d_dest_count);
-        if (launch_check(h, "shard_prepare")) return 1;
-        if (enqueue_final(h, true, 0, cs, true)) return 1;
-        k_shard_flag<<<1, 256, 0, cs>>>(h->p, f, final_grid);
-        if (launch_check(h, "shard_flag")) return 1;
-        k_shard_wait<<<1, 256, 0, cs>>>(h->p, f);
-        if (launch_check(h, "shard_wait")) return 1;
-        if (enqueue_shard_unpack(h, h->p2p_inbox, h->p2p_cap, cs, parity_stride)) return 1;
-        return enqueue_build(h, 1, cs);
-    });
+    int rc = run_cached_graph(h, g, h->p2p_inbox, h->d_peer_inbox, h->shard_epoch, final_grid, h->p2p_cap, 1, 0.0, st,
+                              [&](cudaStream_t cs) { return enqueue_p2p_step(h, f, final_grid, parity_stride, cs); });
     if (rc) return 1;
     h->binned = false;
     h->t_host += 1;
@@ -1444,6 +1456,7 @@ extern "C" int fgnn_profile_step(fgnn_handle* h, int32_t max_kernels, float* ms_
     cudaStream_t st = (cudaStream_t)stream;
     CK(cudaSetDevice(h->cfg.device));
     if (h->binned) return fail("fgnn_profile_step: state was integrated but the graph not rebuilt");
+    if (h->sharded && !h->p2p_connected) return fail("fgnn_profile_step: a sharded handle is profiled through its p2p step (fgnn_p2p_connect first)");
     h->prof_events.clear();
     h->prof_names.clear();
     cudaEvent_t e0;
@@ -1451,7 +1464,22 @@ extern "C" int fgnn_profile_step(fgnn_handle* h, int32_t max_kernels, float* ms_
     CK(cudaEventRecord(e0, st));
     h->profiling = true;
     h->prof_stream = st;
-    int rc = enqueue_closed_step(h, st);
+    int rc;
+    if (h->sharded) {                                   // the p2p step of this rank, kernel by kernel (the peers must step too)
+        ShardFuse f;
+        memset(&f, 0, sizeof f);
+        f.ctl = h->ctl; f.cap = h->p2p_cap; f.p2p = 1;
+        f.peer_inbox = h->d_peer_inbox; f.peer_flags = h->d_peer_flags; f.dest_count = h->d_dest_count;
+        if (memcmp(&f, &h->fuse_host, sizeof f) != 0) {
+            h->fuse_host = f;
+            CK(cudaMemcpyAsync(h->d_fuse, &h->fuse_host, sizeof f, cudaMemcpyHostToDevice, st));
+        }
+        rc = enqueue_p2p_step(h, f, h->use_tc ? h->tc_grid_closed : h->final_grid_closed,
+                              (long long)(p2p_inbox_doubles(h->p2p_world, h->p2p_cap) / 2), st);
+        if (!rc) { h->binned = false; }
+    } else {
+        rc = enqueue_closed_step(h, st);
+    }
     h->profiling = false;
     if (rc) return 1;
     CK(cudaStreamSynchronize(st));

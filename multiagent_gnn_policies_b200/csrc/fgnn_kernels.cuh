@@ -47,6 +47,7 @@ struct Params {
     const struct ShardFuse* fuse;   // non-null: the closed final kernel also packs the halo records (fgnn_shard_step_begin)
     int mean_pooling;
     int half_accel;
+    int sums_in_bin;          // every binning site also accumulates the per-scan-tile sums (no k_scan_sums launch)
     int write_z_last;         // final kernel also stores z_{K-1} (debug / fgnn_get_aggregated)
     int last_hop_done;        // z_{K-1} was already written by a separate hop launch: the final kernel reads it
     int tile_lo, tile_hi;     // final kernel: range of 128-agent tiles of this launch (tile_hi <= 0: all of them)
@@ -140,6 +141,19 @@ __device__ __forceinline__ int cell_index(const Params& p, int ep, long long ix,
     return (ep * p.Gy + wrap(iy, p.Gy)) * p.G + wrap(ix, p.G);
 }
 
+// One more agent in cell c: per-cell counter, and (sums_in_bin) the population of the cell's scan tile, which k_scan reads
+// instead of a k_scan_sums pass.  The lanes of a warp mostly fall into the same tile: one atomic per distinct tile.
+constexpr int SCAN_TILE_LOG2 = 11;
+__device__ __forceinline__ int bin_agent(const Params& p, int c) {
+    const int rank = atomicAdd(&p.cell_count[c], 1);
+    if (p.sums_in_bin) {
+        const unsigned ts = (unsigned)c >> SCAN_TILE_LOG2;
+        const unsigned peers = __match_any_sync(__activemask(), ts);
+        if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&p.tile_status[ts], (unsigned)__popc(peers));
+    }
+    return rank;
+}
+
 // number of agents present on this rank and the i-th of them
 // Sharded: the owned list keeps its order; an agent that is handed over leaves a tombstone (-1) and new agents
 // are appended, so the kernels keep walking spatially coherent runs.  owned_count = high-water mark,
@@ -222,7 +236,7 @@ __global__ void __launch_bounds__(256) k_bin(Params p) {      // owned agents (g
     cell_coords(p, s.x, s.y, ix, iy);
     int c = cell_index(p, episode_of(p, a), ix, iy);
     p.cell_of[a] = c;
-    atomicAdd(&p.cell_count[c], 1);
+    bin_agent(p, c);
 }
 
 // reward_b = -(var(vx) + var(vy)) per episode from the accumulated sums; clears the sums.
@@ -286,6 +300,7 @@ constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ROUNDS = 2;                                   // int4 vectors per thread
 constexpr int SCAN_ITEMS = 4 * SCAN_ROUNDS;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+static_assert(SCAN_TILE == 1 << SCAN_TILE_LOG2, "bin_agent() maps a cell to its scan tile with a shift");
 constexpr unsigned FLAG_AGG = 1u << 30, VAL_MASK = (1u << 30) - 1;
 
 // Accesses are COALESCED int4 vectors (vector r of thread t sits at r*256 + t inside the tile): the first version
@@ -866,6 +881,8 @@ struct ShardCtl {
     int* n_ghost;
     int* counter;             // records written
     long long* xminmax;       // [pack blocks][2] order-preserving keys of min / max px over the agents kept, per block
+    double* safe;             // [2] this step's interior x-interval: an owned agent strictly inside it is wanted by no other rank
+                              //     and stays owned (k_shard_prepare): the pack step costs it two comparisons
 };
 
 // order-preserving map double <-> signed 64-bit integer (for atomicMin / atomicMax on coordinates)
@@ -910,6 +927,12 @@ __device__ __forceinline__ size_t inbox_offset(const ShardFuse& f, int parity, i
 __device__ __forceinline__ void shard_pack_agent(const Params& p, const ShardFuse& f, int i, int a, const double4 st,
                                                  long long& klo, long long& khi) {
     const ShardCtl& c = f.ctl;
+    if (st.x > c.safe[0] && st.x < c.safe[1]) {           // interior of the strip (~99 % of a large shard): nothing to decide
+        const long long k = dkey(st.x);
+        klo = min(klo, k);
+        khi = max(khi, k);
+        return;
+    }
     const double shift = *c.shift;
     const double xs = st.x - shift;
     const int t = *p.t;
@@ -1000,7 +1023,7 @@ __device__ __forceinline__ double4 integrate_and_bin(const Params& p, int a, con
     const int ep = episode_of(p, a);
     const int c = cell_index(p, ep, ix, iy);
     p.cell_of[a] = c;
-    atomicAdd(&p.cell_count[c], 1);
+    bin_agent(p, c);
     // velocity-variance reward sums
     if (p.B == 1) {                 // thread-local; reduced per block by reward_block_flush()
         racc[0] += nvx; racc[1] += nvy; racc[2] += nvx * nvx; racc[3] += nvy * nvy;
@@ -1183,12 +1206,35 @@ __global__ void __launch_bounds__(128) k_controller(Params p, int centralized, i
 //   k_shard_unpack  : install received states; new owner -> appended to the owned list, otherwise ghost list; bin
 // A rank's window = its strip +- depth, united with the x-interval of what it still owns +- depth.
 // ------------------------------------------------------------------------------------------
-__global__ void k_shard_prepare(ShardCtl c, int advance, int* dest_count) {
+// Per step, before the pack: zero the counters, advance the frame, and work out the interior interval (safe[0], safe[1]) of
+// absolute x inside which an owned agent (a) lies strictly inside this rank's strip, so it is not handed over, and (b) is
+// outside every other rank's window (strip +- depth united with its announced owned interval +- depth), so nobody wants
+// its record.  Conservative: empty when some other rank's window covers the middle of what this rank owns.
+__global__ void k_shard_prepare(Params p, ShardFuse f, int advance) {
+    const ShardCtl& c = f.ctl;
+    if (f.dest_count && threadIdx.x < c.world) f.dest_count[threadIdx.x] = 0;
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         *c.n_ghost = 0; *c.counter = 0;
-        if (advance) *c.shift += c.dshift;
+        double shift = *c.shift;
+        if (advance) { shift += c.dshift; *c.shift = shift; }
+        const int t = *p.t;
+        const double* windows = f.p2p ? f.peer_inbox[c.rank] + inbox_offset(f, (t + 1) & 1, 0) + 1 : f.windows;
+        const long long wstride = f.p2p ? (long long)(f.cap + 1) * SREC : f.wstride;
+        double lo = c.bounds[c.rank] + shift, hi = c.bounds[c.rank + 1] + shift;       // strictly inside the own strip
+        // seed: the middle of what this rank owned one step ago; the interval grows from it until it meets a window
+        const double centre = 0.5 * (windows[c.rank * wstride] + windows[c.rank * wstride + 1]);
+        if (!(centre > lo && centre < hi)) { lo = 1.0; hi = -1.0; }
+        for (int q = 0; q < c.world; ++q) {
+            if (q == c.rank) continue;
+            const double wl = fmin(c.bounds[q] + shift, windows[q * wstride]) - c.depth;
+            const double wh = fmax(c.bounds[q + 1] + shift, windows[q * wstride + 1]) + c.depth;
+            if (wh < centre) lo = fmax(lo, wh);
+            else if (wl > centre) hi = fmin(hi, wl);
+            else { lo = 1.0; hi = -1.0; }                  // a window straddles the centre: no interior
+        }
+        c.safe[0] = lo;
+        c.safe[1] = hi;
     }
-    if (dest_count && threadIdx.x < c.world) dest_count[threadIdx.x] = 0;
 }
 
 __global__ void __launch_bounds__(256) k_shard_pack(Params p, ShardFuse f) {
@@ -1311,7 +1357,7 @@ __global__ void __launch_bounds__(256) k_shard_unpack(Params p, ShardCtl c, cons
     cell_coords(p, rec[1], rec[2], ix, iy);
     const int cc = cell_index(p, a / p.N, ix, iy);
     p.cell_of[a] = cc;
-    atomicAdd(&p.cell_count[cc], 1);
+    bin_agent(p, cc);
 }
 
 // owned list = contiguous range [lo, lo + count)  (reset)

@@ -44,6 +44,23 @@ def main():
     for _ in range(steps):
         flock.step()
     torch.cuda.synchronize()
+    if os.environ.get("FGNN_CHECK_PROFILE") == "1" and mode == "p2p":
+        # the p2p step kernel by kernel (CUDA events, un-graphed) on every rank, then the graph-replayed step time
+        per = {}
+        for _ in range(10):
+            for name, ms in be.engine.profile_step():
+                per[name] = per.get(name, 0.0) + ms / 10
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(200):
+            flock.step()
+        e1.record()
+        torch.cuda.synchronize()
+        print(f"rank {rank}: graph step {e0.elapsed_time(e1) / 200 * 1e3:.1f} us | per kernel (events): "
+              + " ".join(f"{k}={v * 1e3:.1f}" for k, v in per.items()) + f" | ghosts {be.engine.stats()['n_ghosts']}", flush=True)
+        steps += 210
     ids, st = be.owned_state()
     # assemble the global state on every rank: sum of each rank's owned rows (exactly one owner per agent)
     x_all = torch.zeros((n_total, 4), dtype=torch.float64, device="cuda")

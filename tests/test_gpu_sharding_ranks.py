@@ -30,4 +30,4 @@ def test_real_ranks_reproduce_single_engine(world, mode):
                          capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
     assert out.returncode == 0, (out.stdout[-2000:], out.stderr[-3000:])
     assert f"sharded rollout ({mode}) == single engine: True" in out.stdout, out.stdout[-2000:]
-    assert "one owner per agent: True" in out.stdout and "overflow False" in out.stdout
+    assert "one owner per agent: True" in out.stdout and "overflow 0" in out.stdout
