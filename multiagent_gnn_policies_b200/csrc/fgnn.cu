@@ -1100,9 +1100,11 @@ static int enqueue_shard_pack(fgnn_handle* h, const double* windows, int64_t win
     return launch_check(h, "shard_header");
 }
 
-static int enqueue_shard_unpack(fgnn_handle* h, const double* recv_buf, int cap, cudaStream_t st, long long parity_stride = 0) {
+static int enqueue_shard_unpack(fgnn_handle* h, const double* recv_buf, int cap, cudaStream_t st, long long parity_stride = 0,
+                                const int* wait_flags = nullptr) {
     Params& p = h->p;
-    k_shard_unpack<<<dim3((unsigned)blocks_for(cap, 256), (unsigned)h->ctl.world), 256, 0, st>>>(p, h->ctl, recv_buf, cap, parity_stride);
+    k_shard_unpack<<<dim3((unsigned)blocks_for(cap, 256), (unsigned)h->ctl.world), 256, 0, st>>>(p, h->ctl, recv_buf, cap, parity_stride,
+                                                                                                  wait_flags);
     if (launch_check(h, "shard_unpack")) return 1;
     h->binned = true;
     return 0;
@@ -1417,9 +1419,9 @@ static int enqueue_p2p_step(fgnn_handle* h, const ShardFuse& f, int final_grid, 
     if (enqueue_final(h, true, 0, cs, true)) return 1;
     k_shard_flag<<<1, 256, 0, cs>>>(h->p, f, final_grid);
     if (launch_check(h, "shard_flag")) return 1;
-    k_shard_wait<<<1, 256, 0, cs>>>(h->p, f);
-    if (launch_check(h, "shard_wait")) return 1;
-    if (enqueue_shard_unpack(h, h->p2p_inbox, h->p2p_cap, cs, parity_stride)) return 1;
+    // (the unpack blocks of sender q wait for q's flag themselves)
+    const int* my_flags = reinterpret_cast<const int*>(h->p2p_inbox + p2p_inbox_doubles(h->p2p_world, h->p2p_cap));
+    if (enqueue_shard_unpack(h, h->p2p_inbox, h->p2p_cap, cs, parity_stride, my_flags)) return 1;
     return enqueue_build(h, 1, cs);
 }
 

@@ -128,6 +128,8 @@ __global__ void __launch_bounds__(FINAL_THREADS) k_final(Params p) {
     const int n_tiles = (n_owned + FINAL_THREADS - 1) / FINAL_THREADS;
     double racc[4] = {0, 0, 0, 0};
     long long klo = 0x7fffffffffffffffll, khi = -0x7fffffffffffffffll - 1;     // kept x-interval (sharded, fused pack)
+    double safe_lo = 1.0, safe_hi = -1.0;                                     // interior interval of the step (k_shard_prepare), read once
+    if (CLOSED && p.fuse) { safe_lo = p.fuse->ctl.safe[0]; safe_hi = p.fuse->ctl.safe[1]; }
     const int tile_end = (p.tile_hi > 0 && p.tile_hi < n_tiles) ? p.tile_hi : n_tiles;     // chunked launches (fgnn_policy)
     for (int tile = p.tile_lo + blockIdx.x; tile < tile_end; tile += gridDim.x) {
         const int oi = tile * FINAL_THREADS + threadIdx.x;
@@ -179,7 +181,7 @@ __global__ void __launch_bounds__(FINAL_THREADS) k_final(Params p) {
             reinterpret_cast<float2*>(p.action)[a] = make_float2(o0, o1);
             if (CLOSED) {
                 const double4 st_new = integrate_and_bin(p, a, st_own, o0, o1, racc);
-                if (p.fuse) shard_pack_agent(p, *p.fuse, oi, a, st_new, klo, khi);
+                if (p.fuse) shard_pack_agent(p, *p.fuse, oi, a, st_new, klo, khi, safe_lo, safe_hi);
             }
         }
     }

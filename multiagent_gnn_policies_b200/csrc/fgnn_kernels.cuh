@@ -925,9 +925,9 @@ __device__ __forceinline__ size_t inbox_offset(const ShardFuse& f, int parity, i
 // Hand-over decision and halo record of ONE owned agent whose (new) state is `st` (used by k_shard_pack and,
 // fused, by the epilogue of the closed final kernel).  i = position in the owned list.
 __device__ __forceinline__ void shard_pack_agent(const Params& p, const ShardFuse& f, int i, int a, const double4 st,
-                                                 long long& klo, long long& khi) {
+                                                 long long& klo, long long& khi, double safe_lo, double safe_hi) {
     const ShardCtl& c = f.ctl;
-    if (st.x > c.safe[0] && st.x < c.safe[1]) {           // interior of the strip (~99 % of a large shard): nothing to decide
+    if (st.x > safe_lo && st.x < safe_hi) {               // interior of the strip (~99 % of a large shard): nothing to decide
         const long long k = dkey(st.x);
         klo = min(klo, k);
         khi = max(khi, k);
@@ -956,30 +956,47 @@ __device__ __forceinline__ void shard_pack_agent(const Params& p, const ShardFus
     const double* windows = f.p2p ? f.peer_inbox[c.rank] + inbox_offset(f, (t + 1) & 1, 0) + 1 : f.windows;
     const long long wstride = f.p2p ? (long long)(f.cap + 1) * SREC : f.wstride;
     bool wanted = new_owner >= 0 && !f.p2p;
-    bool wrote = false;
+    const int lane = threadIdx.x & 31;
     for (int q = 0; q < c.world && !wanted; ++q) {
         if (q == c.rank) continue;
         const bool in_strip = xs >= c.bounds[q] - c.depth && xs <= c.bounds[q + 1] + c.depth;
         const bool in_ival = st.x >= windows[q * wstride] - c.depth && st.x <= windows[q * wstride + 1] + c.depth;
         if (!f.p2p) {
             wanted = in_strip || in_ival;
-        } else if (in_strip || in_ival || q == new_owner) {
-            const int slot = atomicAdd(&f.dest_count[q], 1);
-            if (slot < f.cap) {                           // overflow is reported through the header count
-                double2* rec = reinterpret_cast<double2*>(f.peer_inbox[q] + inbox_offset(f, t & 1, c.rank) + (size_t)(slot + 1) * SREC);
-                rec[0] = make_double2((double)a, st.x);   // three 16-byte stores into peer memory
-                rec[1] = make_double2(st.y, st.z);
-                rec[2] = make_double2(st.w, (double)new_owner);
-                wrote = true;
+        } else {
+            // boundary agents come in runs (the last cells of a grid row): the lanes of a warp that send to q take their
+            // slots with ONE atomic (thousands of single-address atomics were the cost of the sharded final kernel)
+            const bool sends = in_strip || in_ival || q == new_owner;
+            const unsigned act = __activemask();
+            const unsigned m = __ballot_sync(act, sends);
+            if (sends) {
+                const int leader = __ffs(m) - 1;
+                int base = 0;
+                if (lane == leader) base = atomicAdd(&f.dest_count[q], __popc(m));
+                base = __shfl_sync(m, base, leader);
+                const int slot = base + __popc(m & ((1u << lane) - 1u));
+                if (slot < f.cap) {                       // overflow is reported through the header count
+                    double2* rec = reinterpret_cast<double2*>(f.peer_inbox[q] + inbox_offset(f, t & 1, c.rank) + (size_t)(slot + 1) * SREC);
+                    rec[0] = make_double2((double)a, st.x);   // three 16-byte stores into peer memory; they are complete when
+                    rec[1] = make_double2(st.y, st.z);        // this grid is -- k_shard_flag (a later launch) fences and raises
+                    rec[2] = make_double2(st.w, (double)new_owner);   // the flag
+                }
             }
         }
     }
-    if (wrote) __threadfence_system();                    // the flag that follows (k_shard_flag) must not overtake these stores
-    if (wanted) {
-        const int slot = atomicAdd(c.counter, 1);
-        if (slot < f.cap) {                                // overflow is reported through the header count
-            double* rec = f.buf + (size_t)(slot + 1) * SREC;
-            rec[0] = (double)a; rec[1] = st.x; rec[2] = st.y; rec[3] = st.z; rec[4] = st.w; rec[5] = (double)new_owner;
+    if (!f.p2p) {                                          // gather transport: same aggregation on the single send buffer
+        const unsigned act = __activemask();
+        const unsigned m = __ballot_sync(act, wanted);
+        if (wanted) {
+            const int leader = __ffs(m) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(c.counter, __popc(m));
+            base = __shfl_sync(m, base, leader);
+            const int slot = base + __popc(m & ((1u << lane) - 1u));
+            if (slot < f.cap) {                            // overflow is reported through the header count
+                double* rec = f.buf + (size_t)(slot + 1) * SREC;
+                rec[0] = (double)a; rec[1] = st.x; rec[2] = st.y; rec[3] = st.z; rec[4] = st.w; rec[5] = (double)new_owner;
+            }
         }
     }
 }
@@ -1241,7 +1258,7 @@ __global__ void __launch_bounds__(256) k_shard_pack(Params p, ShardFuse f) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     long long klo = 0x7fffffffffffffffll, khi = -0x7fffffffffffffffll - 1;
     const int a = i < owned_count(p) ? owned_agent(p, i) : -1;
-    if (a >= 0) shard_pack_agent(p, f, i, a, p.state[a], klo, khi);
+    if (a >= 0) shard_pack_agent(p, f, i, a, p.state[a], klo, khi, f.ctl.safe[0], f.ctl.safe[1]);
     shard_interval_flush<256>(f.ctl, klo, khi);
 }
 
@@ -1267,8 +1284,6 @@ __global__ void __launch_bounds__(256) k_shard_header(ShardCtl c, double* __rest
     }
 }
 
-// grid = (record chunks, world): a block of sender q leaves at once when q sent fewer records than its first slot.
-// parity_stride != 0 (p2p inbox): this step's records sit in half t & 1 of `recv`.
 // p2p transport, after the final kernel has stored the records into the peers' inboxes: header [count, x_lo, x_hi] of this
 // rank into every peer's inbox (and its own), then -- fenced -- the flag word t + 1 that tells the peer its half t & 1 is
 // complete.  One block; thread q serves peer q.
@@ -1303,27 +1318,25 @@ __global__ void __launch_bounds__(256) k_shard_flag(Params p, ShardFuse f, int n
     }
 }
 
-// ... and the receiving side: wait until every peer's flag of half t & 1 says t + 1.  A peer that never arrives (crashed
-// rank) must not hang the GPU: after ~2 s the wait gives up and raises the sticky overflow flag (value 2).
-__global__ void k_shard_wait(Params p, ShardFuse f) {
-    const ShardCtl& c = f.ctl;
-    const int t = *p.t;
-    const int q = threadIdx.x;
-    if (q < c.world && q != c.rank) {
-        volatile const int* flag = f.peer_flags[c.rank] + (t & 1) * c.world + q;
-        const long long t0 = clock64();
-        while (*flag != t + 1) {
-            __nanosleep(200);
-            if (clock64() - t0 > 4000000000ll) { *p.overflow = 2; break; }
-        }
-        __threadfence_system();
-    }
-}
-
+// grid = (record chunks, world): a block of sender q leaves at once when q sent fewer records than its first slot.
+// parity_stride != 0 (p2p inbox): this step's records sit in half t & 1 of `recv`.
 __global__ void __launch_bounds__(256) k_shard_unpack(Params p, ShardCtl c, const double* __restrict__ recv /* [world][cap+1][SREC] */,
-                                                      int cap, long long parity_stride) {
+                                                      int cap, long long parity_stride, const int* wait_flags) {
     const int q = blockIdx.y, r = blockIdx.x * blockDim.x + threadIdx.x;
     if (q == c.rank) return;
+    if (wait_flags) {                  // p2p: the blocks of sender q wait for q's flag of this step themselves (no separate launch).
+        if (threadIdx.x == 0) {        // A peer that never arrives must not hang the GPU: after ~2 s give up, overflow = 2.
+            const int t = *p.t;
+            volatile const int* flag = wait_flags + (t & 1) * c.world + q;
+            const long long t0 = clock64();
+            while (*flag != t + 1) {
+                __nanosleep(100);
+                if (clock64() - t0 > 4000000000ll) { *p.overflow = 2; break; }
+            }
+            __threadfence_system();
+        }
+        __syncthreads();
+    }
     recv += (size_t)(*p.t & 1) * parity_stride;
     const double* base = recv + (size_t)q * (cap + 1) * SREC;
     const int count = (int)base[0];

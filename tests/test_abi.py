@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
 def test_config_struct_layout_matches_header():
     import ctypes
     assert ctypes.sizeof(engine.FgnnConfig) == 18 * 4 + 3 * 8
-    assert ctypes.sizeof(engine.FgnnStats) == 8 + 8 + 4 + 4 + 8 + 8
+    assert ctypes.sizeof(engine.FgnnStats) == 8 + 8 + 4 + 4 + 8 + 8 + 8       # ... + n_ghosts
 
 
 def test_engine_fails_loudly_without_gpu():
