@@ -36,7 +36,7 @@ def _units():
     common_deps = [os.path.join(CSRC, "fgnn_kernels.cuh")]
     units = [(os.path.join(OBJ, "fgnn.o"), os.path.join(CSRC, "fgnn.cu"), [],
               common_deps + [os.path.join(INCLUDE, "fgnn.h"), os.path.join(CSRC, "fgnn_final.cuh"),
-                             os.path.join(CSRC, "fgnn_final_tc.cuh"), os.path.join(CSRC, "fgnn_tile.cuh")])]
+                             os.path.join(CSRC, "fgnn_final_tc.cuh"), os.path.join(CSRC, "fgnn_pair.cuh")])]
     units.append((os.path.join(OBJ, "fgnn_train.o"), os.path.join(CSRC, "fgnn_train.cu"), [],
                   [os.path.join(INCLUDE, "fgnn.h")]))
     for k in KS:

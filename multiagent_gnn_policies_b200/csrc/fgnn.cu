@@ -2,7 +2,7 @@
 #define FGNN_MAIN_TU 1
 #include "fgnn_kernels.cuh"
 #include "fgnn_final_tc.cuh"
-#include "fgnn_tile.cuh"
+#include "fgnn_pair.cuh"
 #include "../../include/fgnn.h"
 
 #include <dlfcn.h>
@@ -101,9 +101,12 @@ struct fgnn_handle {
     bool last_hop_separate = false;  // last hop as its own launch instead of inside the final kernel
     bool scan_two_pass = false;      // tile sums in their own launch: the scan proper never waits on another block
     bool pdl = false;                // programmatic dependent launch between the step kernels
-    bool tile_mode = false;          // k_tile: adjacency + features + first hop fused per cell tile (fgnn_tile.cuh)
-    TileGeom geo;                    // its geometry and fp32 pre-filter thresholds
-    dim3 tile_grid;
+    bool pair_mode = false;          // k_pair_adjacency instead of k_adjacency_t: warp-tiled, TMA-staged, fp32 pre-filter (fgnn_pair.cuh)
+    int pair_minb = 6;
+    PairGeom geo;                    // fp32 pre-filter thresholds, cell-index dividers, source-scale table
+    unsigned* d_csr_rows = nullptr;  // fgnn_get_csr in pair mode: complete rows assembled on demand (ELL head + CSR tail)
+    int* d_csr_cols = nullptr;
+    unsigned* d_csr_cursor = nullptr;
     int policy_chunks = 1;           // fgnn_policy to a host buffer: readout chunks overlapped with their D2H copies
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t chunk_event[FGNN_MAX_CHUNKS + 1] = {};
@@ -172,8 +175,8 @@ static int dalloc(fgnn_handle* h, T** ptr, size_t count, bool zero = true) {
 #define FGNN_SCAN_TWO_PASS_DEFAULT true           // measured: 312 -> 294 us/step; blocks spinning on other blocks' status words are slow here
 #endif
 #ifndef FGNN_STEP_MODE_DEFAULT
-#define FGNN_STEP_MODE_DEFAULT 0                 // 1: k_tile (adjacency + features + first hop fused per cell tile).  Measured at N=1M, d~5:
-#endif                                           // 176 us vs 102 + 67 us for k_adjacency_t + k_hop (profiles/r2_tile_kernel.md): opt-in for now
+#define FGNN_STEP_MODE_DEFAULT 1                 // 1: k_pair_adjacency (warp tiles, TMA staging, fp32 pre-filter) where the geometry suits it:
+#endif                                           // measured at N=1M, d~5: 93 us vs 103 us for k_adjacency_t (profiles/r2_pair_adjacency.md)
 #ifndef FGNN_LAST_HOP_SEPARATE_DEFAULT
 #define FGNN_LAST_HOP_SEPARATE_DEFAULT true      // measured: 312 -> 307 us/step (high-occupancy gather + streaming readout)
 #endif
@@ -315,42 +318,39 @@ extern "C" int fgnn_create(const fgnn_config* cfg, fgnn_handle** out) {
     p.dt = cfg->dt;
     p.gain = cfg->action_scalar;
     p.n_tiles = blocks_for(p.C + 1, SCAN_TILE);
-    {   // tile-fused adjacency + first hop (FGNN_STEP_MODE=0 selects the separate kernels of round 1)
+    {   // warp-tiled adjacency (FGNN_STEP_MODE=0 selects k_adjacency_t of round 1)
         const char* sm = getenv("FGNN_STEP_MODE");
-        const char* etw = getenv("FGNN_TILE_W");
-        const char* eth = getenv("FGNN_TILE_H");
-        int tw = etw ? atoi(etw) : 16, th = eth ? atoi(eth) : 8;
-        if (tw > TL_TXMAX) tw = TL_TXMAX;
-        if (th > TL_TYMAX) th = TL_TYMAX;
-        if (tw > G - 4) tw = G - 4;               // a window (tile + two-cell halo) never covers a grid cell twice
-        if (th > Gy - 4) th = Gy - 4;
-        h->tile_mode = (sm ? atoi(sm) != 0 : FGNN_STEP_MODE_DEFAULT != 0) && tw >= 1 && th >= 1;
+        // default: on when grid rows are long enough for most warps to sit inside one row and the expected degree is
+        // moderate (the staged path lists at most PR_LIST neighbours per agent); FGNN_STEP_MODE=0/1 overrides
+        h->pair_mode = sm ? atoi(sm) != 0 : (FGNN_STEP_MODE_DEFAULT != 0 && G >= 64 && cap_per <= 48);
         memset(&h->geo, 0, sizeof h->geo);
-        if (h->tile_mode) {
-            TileGeom& ge = h->geo;
-            ge.tw = tw; ge.th = th;
-            ge.ntx = blocks_for(G, tw); ge.nty = blocks_for(Gy, th);
-            h->tile_grid = dim3((unsigned)ge.ntx, (unsigned)ge.nty, (unsigned)cfg->n_episodes);
-            if (ge.nty > 65535 || cfg->n_episodes > 65535) { delete h; return fail("fgnn_create: tile grid too large"); }
-            // fp32 pre-filter on window-relative coordinates (|coordinate| <= E).  With u = 2^-24: every coordinate carries
-            // u E, a difference u (2 E + |d|), so for r2 <= 4 R^2 the fp32 r2 is within u (16 R E + 24 R^2) of the float64
-            // value; twice that is the margin.  Pairs inside the margin take the float64 test.
-            const double cell = 1.0 / p.inv_cell, R = cfg->comm_radius;
-            const double E = ((tw > th ? tw : th) + 5) * cell;
-            const double margin = std::ldexp(16.0 * R * E + 24.0 * R * R, -23);
-            ge.far32 = (float)E;
-            ge.lo32 = std::nextafterf((float)(p.R2 - margin), -INFINITY);
-            ge.hi32n = std::nextafterf(std::nextafterf((float)(p.R2 + margin), INFINITY), INFINITY);
-            ge.csr_tail_only = (cfg->flags & FGNN_FLAG_CSR_TAIL_ONLY) ? 1 : 0;
-            for (int d = 0; d < 64; ++d) ge.sinvtab[d] = cfg->mean_pooling ? (float)(1.0 / (double)(d > 0 ? d : 1)) : 1.0f;
-            CK(cudaFuncSetAttribute((const void*)k_tile<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(1)));
-            CK(cudaFuncSetAttribute((const void*)k_tile<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(2)));
-            CK(cudaFuncSetAttribute((const void*)k_tile<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(3)));
-            CK(cudaFuncSetAttribute((const void*)k_tile<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(4)));
-            h->last_hop_separate = true;          // the final kernel never gathers in this mode
-        } else if (cfg->flags & FGNN_FLAG_CSR_TAIL_ONLY) {
-            delete h;
-            return fail("fgnn_create: FGNN_FLAG_CSR_TAIL_ONLY needs the tile kernel (grid of at least 5 x 5 cells, FGNN_STEP_MODE != 0)");
+        PairGeom& ge = h->geo;
+        // fp32 pre-filter on warp-relative coordinates (|coordinate| <= E).  With u = 2^-24: every coordinate carries
+        // u E, a difference u (2 E + |d|), so for r2 <= 4 R^2 the fp32 r2 is within u (16 R E + 24 R^2) of the float64
+        // value; twice that is the margin.  Pairs inside the margin take the float64 test.
+        const double cell = 1.0 / p.inv_cell, R = cfg->comm_radius;
+        const double E = (PR_EXT + 3) * cell;
+        const double margin = std::ldexp(16.0 * R * E + 24.0 * R * R, -23);
+        ge.far32 = (float)E;
+        ge.me32 = (float)((PR_EXT + 0.5) * cell);
+        ge.lo32 = std::nextafterf((float)(p.R2 - margin), -INFINITY);
+        ge.hi32 = std::nextafterf(std::nextafterf((float)(p.R2 + margin), INFINITY), INFINITY);
+        auto fastdiv = [](unsigned d) {
+            FastDiv f;
+            f.l = 0;
+            while ((1ull << f.l) < d) ++f.l;
+            f.m = (unsigned)(((1ull << 32) * ((1ull << f.l) - d)) / d + 1);
+            return f;
+        };
+        ge.divG = fastdiv((unsigned)G);
+        ge.divGy = fastdiv((unsigned)Gy);
+        for (int d = 0; d < 64; ++d) ge.sinvtab[d] = cfg->mean_pooling ? (float)(1.0 / (double)(d > 0 ? d : 1)) : 1.0f;
+        if (h->pair_mode) {
+            const char* mb = getenv("FGNN_PR_MINB");
+            h->pair_minb = mb ? atoi(mb) : FGNN_PR_MINBLOCKS;
+            CK(cudaFuncSetAttribute((const void*)k_pair_adjacency<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair_adjacency_smem()));
+            CK(cudaFuncSetAttribute((const void*)k_pair_adjacency<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair_adjacency_smem()));
+            CK(cudaFuncSetAttribute((const void*)k_pair_adjacency<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair_adjacency_smem()));
         }
     }
 
@@ -364,6 +364,7 @@ extern "C" int fgnn_create(const fgnn_config* cfg, fgnn_handle** out) {
     rc |= dalloc(h, &p.tmp_id, M);
     rc |= dalloc(h, &p.sorted_id, M);
     rc |= dalloc(h, &p.sorted_state, M);
+    rc |= dalloc(h, &p.sorted_cell, M);
     rc |= dalloc(h, &p.tile_status, (size_t)p.n_tiles);
     rc |= dalloc(h, &p.tile_counter, 1);
     rc |= dalloc(h, &p.xhist, K * M * ROW);
@@ -373,6 +374,7 @@ extern "C" int fgnn_create(const fgnn_config* cfg, fgnn_handle** out) {
     rc |= dalloc(h, &p.cols, K * (size_t)p.nnz_cap, false);
     rc |= dalloc(h, &p.ell, K * M * ELLW);
     rc |= dalloc(h, &p.nnz_cursor, K);
+    rc |= dalloc(h, &p.edge_total, K);
     rc |= dalloc(h, &p.overflow, 1);
     rc |= dalloc(h, &p.zbuf, K * M * ROW);
     rc |= dalloc(h, &p.ybuf, 2 * K * M * ROW);
@@ -615,15 +617,12 @@ static int enqueue_build(fgnn_handle* h, int advance, cudaStream_t st) {
     if (launch_check(h, "scatter")) return 1;
     launch_step(h, k_canon, gb, 256, 0, st, p);
     if (launch_check(h, "canon")) return 1;
-    if (h->tile_mode) {
-        const size_t smem = tile_smem_bytes(p.K);
-        switch (p.K) {
-            case 1: launch_step(h, k_tile<1>, h->tile_grid, TL_THREADS, smem, st, p, h->geo); break;
-            case 2: launch_step(h, k_tile<2>, h->tile_grid, TL_THREADS, smem, st, p, h->geo); break;
-            case 3: launch_step(h, k_tile<3>, h->tile_grid, TL_THREADS, smem, st, p, h->geo); break;
-            default: launch_step(h, k_tile<4>, h->tile_grid, TL_THREADS, smem, st, p, h->geo); break;
-        }
-        if (launch_check(h, "tile")) return 1;
+    if (h->pair_mode) {
+        const int gp = blocks_for(h->launch_pool, PR_THREADS);
+        if (h->pair_minb >= 8) launch_step(h, k_pair_adjacency<8>, gp, PR_THREADS, pair_adjacency_smem(), st, p, h->geo);
+        else if (h->pair_minb == 6) launch_step(h, k_pair_adjacency<6>, gp, PR_THREADS, pair_adjacency_smem(), st, p, h->geo);
+        else launch_step(h, k_pair_adjacency<5>, gp, PR_THREADS, pair_adjacency_smem(), st, p, h->geo);
+        if (launch_check(h, "pair_adjacency")) return 1;
         h->binned = false;
         if (advance) h->t_host += 1;
         return 0;
@@ -649,8 +648,8 @@ static void launch_hop(fgnn_handle* h, int j, cudaStream_t st) {
 
 static int enqueue_hops(fgnn_handle* h, cudaStream_t st) {
     Params& p = h->p;
-    for (int j = h->tile_mode ? 1 : 0; j + 2 < p.K; ++j) {     // hops 0 .. K-3 ; hop K-2 lives in the final kernel (or below)
-        const int nb = p.K - 1 - j;                          // (tile mode: hop 0 was done by k_tile when the graph was built)
+    for (int j = 0; j + 2 < p.K; ++j) {     // hops 0 .. K-3 ; hop K-2 lives in the final kernel (or below)
+        const int nb = p.K - 1 - j;
         if (nb == 3) launch_hop<3, true>(h, j, st);                   // K = 4, hop 0
         else if (nb == 2 && j == 0) launch_hop<2, true>(h, j, st);    // K = 3, hop 0
         else if (nb == 2) launch_hop<2, false>(h, j, st);             // K = 4, hop 1
@@ -659,7 +658,6 @@ static int enqueue_hops(fgnn_handle* h, cudaStream_t st) {
     }
     if (h->last_hop_separate && p.K >= 2) {  // tap K-1 through graph t-(K-2), written to zbuf[K-1] for the final kernel
         const int j = p.K - 2;
-        if (j == 0 && h->tile_mode) return 0;                // K = 2: the only hop is the first one
         if (j == 0) launch_hop<1, true>(h, j, st);
         else launch_hop<1, false>(h, j, st);
         if (launch_check(h, "hop_last")) return 1;
@@ -726,6 +724,7 @@ extern "C" int fgnn_reset(fgnn_handle* h, const double* x, void* stream) {
     CK(cudaMemsetAsync(p.row_start, 0, K * M * sizeof(unsigned), st));
     CK(cudaMemsetAsync(p.deg, 0, K * M * sizeof(int), st));
     CK(cudaMemsetAsync(p.nnz_cursor, 0, K * sizeof(unsigned), st));
+    CK(cudaMemsetAsync(p.edge_total, 0, K * sizeof(unsigned long long), st));
     CK(cudaMemsetAsync(p.t, 0, sizeof(int), st));
     CK(cudaMemsetAsync(p.cell_count, 0, ((size_t)p.C + 1) * sizeof(int), st));
     CK(cudaMemsetAsync(p.tile_status, 0, (size_t)p.n_tiles * sizeof(unsigned), st));
@@ -1011,10 +1010,26 @@ extern "C" int fgnn_export_network_dense(fgnn_handle* h, int32_t age, float* out
 extern "C" int fgnn_get_csr(fgnn_handle* h, int32_t age, const uint32_t** row_start, const int32_t** deg,
                             const int32_t** cols, const float** src_scale) {
     if (!h) return fail("fgnn_get_csr: null handle");
-    if (h->geo.csr_tail_only) return fail("fgnn_get_csr: the handle keeps CSR rows only for long rows (FGNN_FLAG_CSR_TAIL_ONLY)");
     int g;
     if (age_slot(h, age, &g)) return 1;
     const size_t M = h->p.M;
+    if (h->pair_mode) {
+        // the step keeps the ELL head of every row and the CSR tail of long rows: assemble complete rows on demand
+        CK(cudaSetDevice(h->cfg.device));
+        if (!h->d_csr_cols) {
+            if (dalloc(h, &h->d_csr_rows, M) || dalloc(h, &h->d_csr_cols, (size_t)h->p.nnz_cap, false) || dalloc(h, &h->d_csr_cursor, 1)) return 1;
+        }
+        CK(cudaDeviceSynchronize());
+        CK(cudaMemset(h->d_csr_cursor, 0, sizeof(unsigned)));
+        k_csr_assemble<<<blocks_for((int)M, 256), 256>>>(h->p, g, h->d_csr_cursor, h->d_csr_rows, h->d_csr_cols);
+        if (launch_check(h, "csr_assemble")) return 1;
+        CK(cudaDeviceSynchronize());
+        if (row_start) *row_start = h->d_csr_rows;
+        if (deg) *deg = h->p.deg + g * M;
+        if (cols) *cols = h->d_csr_cols;
+        if (src_scale) *src_scale = h->p.sinv + g * M;
+        return 0;
+    }
     if (row_start) *row_start = h->p.row_start + g * M;
     if (deg) *deg = h->p.deg + g * M;
     if (cols) *cols = h->p.cols + (size_t)g * h->p.nnz_cap;
@@ -1034,6 +1049,12 @@ extern "C" int fgnn_get_stats(fgnn_handle* h, fgnn_stats* out, void* stream) {
     CK(cudaStreamSynchronize(st));
     out->step = t;
     out->n_edges = cur[slot_of(t, h->cfg.k)];
+    if (h->pair_mode) {
+        unsigned long long tot[KMAX] = {0, 0, 0, 0};
+        CK(cudaMemcpyAsync(tot, h->p.edge_total, h->cfg.k * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        out->n_edges = (int64_t)tot[slot_of(t, h->cfg.k)];
+    }
     out->overflow = ovf;
     out->grid_dim = h->p.G;
     out->n_cells = h->p.C;

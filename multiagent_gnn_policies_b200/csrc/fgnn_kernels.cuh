@@ -65,6 +65,7 @@ struct Params {
     int* tmp_id;              // [M] scatter order (atomic, not canonical)
     int* sorted_id;           // [M] canonical: by cell, then by agent id
     double4* sorted_state;    // [M]
+    int* sorted_cell;         // [M] cell of every sorted slot (written by k_canon; k_pair_adjacency reads it instead of re-deriving it)
     unsigned* tile_status;    // scan look-back words
     int* tile_counter;        // scan dynamic tile id
     int n_tiles;
@@ -76,6 +77,7 @@ struct Params {
     int* cols;                // [K][nnz_cap]
     int* ell;                 // [K][M][ELLW] first ELLW neighbours of every row, -1 padded (copy of the CSR head)
     unsigned* nnz_cursor;     // [K]
+    unsigned long long* edge_total;   // [K] directed edges of every ring slot (pair kernels: the CSR cursor counts long rows only)
     int* overflow;            // sticky flag
 
     float* zbuf;              // [K][M][ROW]  z_k, k >= 1
@@ -356,6 +358,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(Params p, int advance, in
         const int tn = *p.t + (advance ? 1 : 0);
         *p.t = tn;
         p.nnz_cursor[slot_of(tn, p.K)] = 0;          // edge cursor of the slot about to be rebuilt
+        p.edge_total[slot_of(tn, p.K)] = 0ull;
     }
     const int n = p.C + 1;
     int4 v[SCAN_ROUNDS];
@@ -462,6 +465,7 @@ __global__ void __launch_bounds__(256) k_canon(Params p) {
     for (int q = q0; q < q1; ++q) rank += (p.tmp_id[q] < a) ? 1 : 0;
     int dst = q0 + rank;
     p.sorted_id[dst] = a;
+    p.sorted_cell[dst] = c;
     stg256(&p.sorted_state[dst], ldg256_nc(&p.state[a]));
 }
 
@@ -1133,6 +1137,32 @@ __global__ void k_export_dense(Params p, int g, float* __restrict__ out) {
     for (int e = 0; e < d; ++e) row[(e < ELLW ? head[e] : cols[e]) % p.N] = sc;
 }
 
+
+// Complete CSR rows for fgnn_get_csr when the step keeps only the ELL head + the tail of long rows (pair kernels):
+// row a = head[0 .. min(d, ELLW)) followed by cols[row_start + ELLW .. row_start + d); rows placed by one atomic per warp.
+__global__ void __launch_bounds__(256) k_csr_assemble(Params p, int g, unsigned* __restrict__ cursor, unsigned* __restrict__ row_out,
+                                                      int* __restrict__ cols_out) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const size_t ga = (size_t)g * p.M + (a < p.M ? a : 0);
+    const int d = a < p.M ? p.deg[ga] : 0;
+    int inc = d;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += y;
+    }
+    unsigned base = 0;
+    if (lane == 31 && inc > 0) base = atomicAdd(cursor, (unsigned)inc);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    if (a >= p.M) return;
+    const unsigned row = base + (unsigned)(inc - d);
+    row_out[a] = row;
+    if (row + (unsigned)d > p.nnz_cap) { *p.overflow = 1; return; }
+    const int* head = p.ell + ga * ELLW;
+    const int* tail = p.cols + (size_t)g * p.nnz_cap + p.row_start[ga];
+    for (int e = 0; e < d; ++e) cols_out[row + e] = e < ELLW ? head[e] : tail[e];
+}
 
 // ------------------------------------------------------------------------------------------
 // Expert controller (gym_flock FlockingRelativeEnv.controller):

@@ -1,0 +1,418 @@
+// fgnn_pair.cuh -- K_P: radius adjacency + degree + 6-d features per warp tile, fp32 pre-filter, TMA staging (sm_100a).
+//
+// The cell-sorted arrays are cell-major, so the 32 agents of a warp (consecutive slots of one grid row) draw all their
+// candidates from THREE contiguous slot ranges (grid rows y-1, y, y+1).  The warp stages those ranges in shared memory
+// once -- TMA bulk copies (cp.async.bulk, one mbarrier per warp, lane r issues range r) of the float64 states -- and works
+// from there; there is no block-wide synchronisation after the prologue.
+//
+//   filter    radius test in fp32 on warp-relative coordinates with a rigorous margin (two sign masks per row, no compare /
+//             select); the rare pair whose fp32 r2 falls inside the margin takes the float64 test numpy evaluates, so the
+//             edge set is bit-exact.
+//   list      accept masks -> list of staged indices in canonical order (row -1, 0, +1; slot order inside)
+//   features  float64 sums over the list (the divergent part runs max-degree-of-the-warp iterations of 40 instructions)
+//   emission  x_t, deg, 1/deg, the ELL head, the CSR tail of rows longer than the head
+//
+// Warps that straddle a grid row, touch the x seam of the wrapped grid, hold an aliased agent or outgrow the stage take a
+// per-lane path over global memory (same order, same arithmetic).  Neighbour order and every floating-point operation
+// equal those of k_adjacency_t: the two leave bit-identical state (scripts/ab_variants.py).
+//
+// Reference arithmetic: gym_flock compute_helpers.
+#pragma once
+#include "fgnn_kernels.cuh"
+
+namespace fgnn {
+
+constexpr int PR_THREADS = 128;
+constexpr int PR_WARPS = PR_THREADS / 32;
+#ifndef FGNN_PR_POOL
+#define FGNN_PR_POOL 144
+#endif
+constexpr int PR_POOL = FGNN_PR_POOL;        // candidates staged per warp (the three row ranges back to back); mean ~107 at 1.6 agents per cell
+constexpr int PR_EXT = 64;                   // widest run of cells a warp's agents may span on the staged path (bounds the fp32 coordinates)
+constexpr float PR_FAR = 1.0e18f;            // staged coordinate of a candidate outside the warp's frame: fails every radius test
+
+struct FastDiv { unsigned m; int l; };       // n / d for n < 2^31: (umulhi(m, n) + n) >> l
+__device__ __forceinline__ unsigned fdiv(const FastDiv d, unsigned n) { return (__umulhi(d.m, n) + n) >> d.l; }
+
+constexpr int PR_LIST = 16;                  // neighbours listed per lane (a longer row sends its warp down the per-lane path)
+#ifndef FGNN_PR_MINBLOCKS
+#define FGNN_PR_MINBLOCKS 6
+#endif
+
+struct PairGeom {
+    float lo32, hi32;       // fp32 r2 < lo32: inside for sure; r2 >= hi32: outside for sure
+    float far32;            // |warp-relative coordinate| beyond this: the candidate cannot be a neighbour of a framed agent
+    float me32;             // ... and an agent of the warp beyond THIS is aliased from another wrap of the grid: per-lane path
+    FastDiv divG, divGy;
+    float sinvtab[64];      // source scale by degree: (float)(1.0 / max(d, 1)) under mean pooling, else 1
+};
+
+constexpr int PR_NBW = 5;                    // words per lane of the byte-list scratch (16 list bytes + 4: odd stride, no bank conflicts)
+__host__ __device__ constexpr size_t pair_adjacency_warp_bytes() {
+    return (size_t)PR_POOL * (sizeof(double4) + sizeof(float2) + sizeof(int)) + (size_t)32 * PR_NBW * sizeof(unsigned);
+}
+__host__ __device__ constexpr size_t pair_adjacency_smem() { return (size_t)PR_WARPS * pair_adjacency_warp_bytes(); }
+#ifdef FGNN_MAIN_TU
+
+namespace pr {
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(mbar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "PR_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra PR_DONE;\n\t"
+        "bra PR_WAIT;\n\t"
+        "PR_DONE:\n\t}\n"
+        :: "r"(mbar), "r"(parity) : "memory");
+}
+// TMA bulk copy global -> shared (SASS: UBLKCP); bytes a multiple of 16, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// The three row ranges of a warp's stage land back to back: lane r (r < 3) issues the bulk copy of range r, lane 0 arms the
+// barrier (one lane issuing all three costs the warp ~3x the issue slots: the sequence runs once per lane either way).
+__device__ __forceinline__ void stage_states(double4* w_st, const double4* __restrict__ sorted_state, uint32_t mbar, int lane,
+                                             const int (&lo)[3], const int (&off)[3], int total) {
+    if (lane == 0) {
+        mbar_init(mbar, 1);
+        mbar_expect_tx(mbar, (uint32_t)total * (uint32_t)sizeof(double4));
+    }
+    __syncwarp();
+    if (lane < 3) {
+        const int o = lane == 0 ? off[0] : lane == 1 ? off[1] : off[2];
+        const int e = lane == 0 ? off[1] : lane == 1 ? off[2] : total;
+        const int l = lane == 0 ? lo[0] : lane == 1 ? lo[1] : lo[2];
+        if (e > o) bulk_g2s(smem_u32(w_st + o), sorted_state + l, (uint32_t)(e - o) * 32u, mbar);
+    }
+}
+
+struct CellPos { int row, cxw, wy, ep; };     // row = ep * Gy + wy
+__device__ __forceinline__ CellPos cell_pos(const Params& p, const PairGeom& geo, int c) {
+    CellPos cp;
+    cp.row = (int)fdiv(geo.divG, (unsigned)c);
+    cp.cxw = c - cp.row * p.G;
+    cp.ep = p.B == 1 ? 0 : (int)fdiv(geo.divGy, (unsigned)cp.row);
+    cp.wy = cp.row - cp.ep * p.Gy;
+    return cp;
+}
+__device__ __forceinline__ int row_base(const Params& p, const CellPos& cp, int r) {      // first cell of grid row wy - 1 + r (wrapped)
+    const int wr = r == 0 ? (cp.wy == 0 ? p.Gy - 1 : cp.wy - 1) : r == 1 ? cp.wy : (cp.wy == p.Gy - 1 ? 0 : cp.wy + 1);
+    return (cp.ep * p.Gy + wr) * p.G;
+}
+// the nine candidate slot ranges of an agent anywhere on the wrapped grid (an interior agent's three cells per row are one range)
+__device__ __forceinline__ void ranges9(const Params& p, const CellPos& cp, int (&q0)[9], int (&q1)[9]) {
+#pragma unroll
+    for (int j = 0; j < 9; ++j) q0[j] = q1[j] = 0;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const int rb = row_base(p, cp, r);
+        if (cp.cxw >= 1 && cp.cxw <= p.G - 2) {
+            q0[3 * r] = __ldg(&p.cell_start[rb + cp.cxw - 1]);
+            q1[3 * r] = __ldg(&p.cell_start[rb + cp.cxw + 2]);
+        } else {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const int wc = c == 0 ? (cp.cxw == 0 ? p.G - 1 : cp.cxw - 1) : c == 1 ? cp.cxw : (cp.cxw == p.G - 1 ? 0 : cp.cxw + 1);
+                q0[3 * r + c] = __ldg(&p.cell_start[rb + wc]);
+                q1[3 * r + c] = __ldg(&p.cell_start[rb + wc + 1]);
+            }
+        }
+    }
+}
+
+// fp32 radius test of `me` against n <= 32 staged candidates: bit k of `in` = r2 < lo (inside for sure), of `le` = r2 < hi
+// (not outside for sure).  Per candidate: r2 (4 instructions) and two funnel shifts that push the SIGN bits of r2 - lo and
+// r2 - hi into the masks (no compare / select / variable shift).
+__device__ __forceinline__ void filter_row(const float2* __restrict__ c, int n, float2 me, float lo, float hi, unsigned& in_,
+                                           unsigned& le_) {
+    unsigned in = 0, le = 0;
+    int k = 0;
+#pragma unroll 1
+    for (; k + 2 <= n; k += 2) {
+        const float2 o0 = c[k], o1 = c[k + 1];
+        const float dx0 = me.x - o0.x, dy0 = me.y - o0.y, dx1 = me.x - o1.x, dy1 = me.y - o1.y;
+        const float r20 = fmaf(dx0, dx0, dy0 * dy0), r21 = fmaf(dx1, dx1, dy1 * dy1);
+        in = __funnelshift_l(__float_as_uint(r20 - lo), in, 1);
+        le = __funnelshift_l(__float_as_uint(r20 - hi), le, 1);
+        in = __funnelshift_l(__float_as_uint(r21 - lo), in, 1);
+        le = __funnelshift_l(__float_as_uint(r21 - hi), le, 1);
+    }
+    if (k < n) {
+        const float2 o0 = c[k];
+        const float dx0 = me.x - o0.x, dy0 = me.y - o0.y;
+        const float r20 = fmaf(dx0, dx0, dy0 * dy0);
+        in = __funnelshift_l(__float_as_uint(r20 - lo), in, 1);
+        le = __funnelshift_l(__float_as_uint(r20 - hi), le, 1);
+    }
+    // candidate k was shifted in first: it sits at bit n-1-k
+    in_ = n > 0 ? __brev(in) >> (32 - n) : 0u;
+    le_ = n > 0 ? __brev(le) >> (32 - n) : 0u;
+}
+}  // namespace pr
+
+// One accepted pair: feature sums in float64 (same operations, same order as k_adjacency_t)
+#define FGNN_PAIR_FEATURES(o)                                                                         \
+    {                                                                                                 \
+        const double dx = me.x - (o).x, dy = me.y - (o).y;                                            \
+        const double inv = fast_rcp(r2_exact(dx, dy));                                                \
+        const double inv2 = inv * inv;                                                                \
+        f0 += me.z - (o).z;                                                                           \
+        f1 += dx * inv2;                                                                              \
+        f2 += dx * inv;                                                                               \
+        f3 += me.w - (o).w;                                                                           \
+        f4 += dy * inv2;                                                                              \
+        f5 += dy * inv;                                                                               \
+    }
+
+// ------------------------------------------------------------------------------------------
+// K_P1  radius adjacency + degree + 6-d relative features (gym_flock compute_helpers) per cell-sorted slot; emits the graph
+//       (ELL head, CSR tail of long rows, deg, 1/deg), x_t, and the record K_P2 walks.
+// ------------------------------------------------------------------------------------------
+template <int MINB>
+__global__ void __launch_bounds__(PR_THREADS, MINB) k_pair_adjacency(Params p, PairGeom geo) {
+    pdl_prologue();
+    extern __shared__ __align__(128) unsigned char s_pair_raw[];
+    __shared__ __align__(8) unsigned long long s_mbar[PR_WARPS];
+    __shared__ float s_tab[64];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int s = blockIdx.x * PR_THREADS + tid;
+    // housekeeping for the next scan
+    for (int i = s; i < p.n_tiles; i += gridDim.x * PR_THREADS) p.tile_status[i] = 0;
+    if (s == 0) *p.tile_counter = 0;
+    if (tid < 64) s_tab[tid] = geo.sinvtab[tid];
+    __syncthreads();
+    const int ns = sorted_count(p);
+    const int s0 = s - lane;
+    if (s0 >= ns) return;                          // (warp-uniform)
+    const bool valid = s < ns;
+    const int nvalid = ns - s0 < 32 ? ns - s0 : 32;
+    unsigned char* wb = s_pair_raw + (size_t)warp * pair_adjacency_warp_bytes();
+    double4* w_st = reinterpret_cast<double4*>(wb);
+    float2* w_xy = reinterpret_cast<float2*>(w_st + PR_POOL);
+    int* w_id = reinterpret_cast<int*>(w_xy + PR_POOL);
+    unsigned* w_nbw = reinterpret_cast<unsigned*>(w_id + PR_POOL) + lane * PR_NBW;      // this lane's byte list
+    auto scale_of = [&](int d) { return d < 64 ? s_tab[d] : (p.mean_pooling ? (float)(1.0 / (double)d) : 1.0f); };
+
+    const int t = *p.t;
+    const int g = slot_of(t, p.K);
+    const size_t M = p.M;
+    int c = 0, a = 0;
+    if (valid) {
+        c = __ldg(&p.sorted_cell[s]);
+        a = __ldg(&p.sorted_id[s]);
+    }
+    const pr::CellPos cp = pr::cell_pos(p, geo, c);
+    const int row_first = __shfl_sync(0xffffffffu, cp.row, 0);
+    const int cx_first = __shfl_sync(0xffffffffu, cp.cxw, 0);
+    const int cx_last = __shfl_sync(0xffffffffu, cp.cxw, nvalid - 1);
+    bool ok = !valid || (cp.row == row_first && cp.cxw >= 1 && cp.cxw <= p.G - 2);
+    int q0[3] = {0, 0, 0}, n[3] = {0, 0, 0};
+    if (valid && ok) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const int rb = pr::row_base(p, cp, r);
+            q0[r] = __ldg(&p.cell_start[rb + cp.cxw - 1]);
+            n[r] = __ldg(&p.cell_start[rb + cp.cxw + 2]) - q0[r];
+        }
+        ok = n[0] <= 32 && n[1] <= 32 && n[2] <= 32;
+    }
+    bool fast = __all_sync(0xffffffffu, ok) && cx_last - cx_first + 3 <= PR_EXT;
+    int lo[3] = {0, 0, 0}, off[3] = {0, 0, 0};
+    int total = 0;
+    if (fast) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            lo[r] = __shfl_sync(0xffffffffu, q0[r], 0);
+            const int hi = __shfl_sync(0xffffffffu, q0[r] + n[r], nvalid - 1);
+            off[r] = total;
+            total += hi - lo[r];
+        }
+        fast = total <= PR_POOL;
+    }
+    double4 me = make_double4(0, 0, 0, 0);
+    double f0 = 0, f1 = 0, f2 = 0, f3 = 0, f4 = 0, f5 = 0;
+    int deg = 0;
+    unsigned in[3] = {0, 0, 0};
+    int base[3] = {0, 0, 0};
+    if (fast) {
+        const uint32_t mbar = pr::smem_u32(&s_mbar[warp]);
+        pr::stage_states(w_st, p.sorted_state, mbar, lane, lo, off, total);
+        {   // ids of the staged agents (graph emission), one round trip for all of them
+            constexpr int NU = (PR_POOL + 31) / 32;
+            int idv[NU];
+#pragma unroll
+            for (int u = 0; u < NU; ++u) {
+                const int i = lane + 32 * u;
+                idv[u] = 0;
+                if (i < total) idv[u] = __ldg(&p.sorted_id[i < off[1] ? lo[0] + i : i < off[2] ? lo[1] + i - off[1] : lo[2] + i - off[2]]);
+            }
+#pragma unroll
+            for (int u = 0; u < NU; ++u) {
+                const int i = lane + 32 * u;
+                if (i < total) w_id[i] = idv[u];
+            }
+        }
+        pr::mbar_wait(mbar, 0);
+        // warp frame: the position of the warp's first agent.  Coordinates relative to it are exact in float64 and carry
+        // at most 2^-24 |coordinate| after the conversion.
+        const double2 org = *reinterpret_cast<const double2*>(&w_st[off[1] + s0 - lo[1]]);
+        for (int i = lane; i < total; i += 32) {
+            const double2 pxy = *reinterpret_cast<const double2*>(&w_st[i]);
+            const float rx = (float)(pxy.x - org.x), ry = (float)(pxy.y - org.y);
+            const bool far = !(fabsf(rx) <= geo.far32) || !(fabsf(ry) <= geo.far32);
+            w_xy[i] = far ? make_float2(PR_FAR, PR_FAR) : make_float2(rx, ry);
+        }
+        __syncwarp();
+        const int self = off[1] + s - lo[1];
+        bool bad = false;                              // aliased agent, or a row too long for the record's list
+        if (valid) {
+            const float2 me32 = w_xy[self];
+            bad = !(fabsf(me32.x) <= geo.me32) || !(fabsf(me32.y) <= geo.me32);
+            me = w_st[self];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                base[r] = off[r] + q0[r] - lo[r];
+                unsigned le;
+                pr::filter_row(w_xy + base[r], n[r], me32, geo.lo32, geo.hi32, in[r], le);
+                if (r == 1) {
+                    const unsigned selfbit = 1u << (s - q0[1]);
+                    in[1] &= ~selfbit;
+                    le &= ~selfbit;
+                }
+                unsigned amb = le & ~in[r];
+                while (amb) {                          // rare: the float64 test numpy evaluates
+                    const int k = __ffs(amb) - 1;
+                    amb &= amb - 1;
+                    const double2 o = *reinterpret_cast<const double2*>(&w_st[base[r] + k]);
+                    if (r2_exact(me.x - o.x, me.y - o.y) < p.R2) in[r] |= 1u << k;
+                }
+                deg += __popc(in[r]);
+            }
+            bad = bad || deg > PR_LIST;
+        }
+        fast = !__any_sync(0xffffffffu, bad);
+    }
+    if (!fast && valid) {
+        // ---- per-lane path over global memory (row straddle, x seam, aliased agent, crowded stage): degree first ----
+        me = ldg256_nc(&p.sorted_state[s]);
+        int r0[9], r1[9];
+        pr::ranges9(p, cp, r0, r1);
+        deg = 0;
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+            for (int q = r0[j]; q < r1[j]; ++q) {
+                const double2 o = *reinterpret_cast<const double2*>(&p.sorted_state[q]);
+                deg += (q != s && r2_exact(me.x - o.x, me.y - o.y) < p.R2) ? 1 : 0;
+            }
+        }
+    }
+    {   // edge count of the graph (fgnn_get_stats): one reduction + one fire-and-forget atomic per warp
+        const int wsum = __reduce_add_sync(0xffffffffu, valid ? deg : 0);
+        if (lane == 0 && wsum > 0) atomicAdd(&p.edge_total[g], (unsigned long long)wsum);
+    }
+    // CSR tail: rows longer than the ELL head keep their entries e >= ELLW in cols[row + e]; one run of edge slots per warp
+    const bool wants_row = valid && deg > ELLW;
+    unsigned row = 0;
+    bool write_row = false;
+    if (__any_sync(0xffffffffu, wants_row)) {
+        int inc = wants_row ? deg : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += y;
+        }
+        unsigned rbase = 0;
+        if (lane == 31) rbase = atomicAdd(&p.nnz_cursor[g], (unsigned)inc);
+        rbase = __shfl_sync(0xffffffffu, rbase, 31);
+        row = wants_row ? rbase + (unsigned)(inc - deg) : 0u;
+        write_row = wants_row;
+        if (wants_row && (row + (unsigned)deg > p.nnz_cap || row + (unsigned)deg < row)) {   // capacity exceeded: drop the row, flag it
+            *p.overflow = 1;
+            row = 0;
+            write_row = false;
+        }
+    }
+    if (!valid) return;
+    int* cols = p.cols + (size_t)g * p.nnz_cap + row;
+    const size_t ga = (size_t)g * M + a;
+    int count = deg;
+    if (fast) {
+        // accept masks -> list of staged indices, canonical order (bytes through this lane's shared-memory scratch)
+        w_nbw[0] = 0; w_nbw[1] = 0; w_nbw[2] = 0; w_nbw[3] = 0;
+        unsigned char* nbp = reinterpret_cast<unsigned char*>(w_nbw);
+        {
+            int e = 0;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                unsigned m = in[r];
+                while (m) {
+                    nbp[e++] = (unsigned char)(base[r] + __ffs(m) - 1);
+                    m &= m - 1;
+                }
+            }
+        }
+        int jn = nbp[0];
+#pragma unroll 1
+        for (int e = 0; e < deg; ++e) {
+            const int j = jn;
+            jn = nbp[e + 1];                                  // (byte PR_LIST is the scratch's pad word)
+            const double4 o = w_st[j];
+            FGNN_PAIR_FEATURES(o)
+            if (e >= ELLW && write_row) cols[e] = w_id[j];
+        }
+        if (wants_row && !write_row) count = 0;           // dropped row (capacity): the graph keeps no edge of it
+        int head[ELLW];
+#pragma unroll
+        for (int u = 0; u < ELLW; ++u) head[u] = u < count ? w_id[nbp[u]] : -1;
+        stg256(p.ell + ga * ELLW, head);
+    } else {
+        int r0[9], r1[9];
+        pr::ranges9(p, cp, r0, r1);
+        int* ell = p.ell + ga * ELLW;
+        int e = 0;
+#pragma unroll
+        for (int j9 = 0; j9 < 9; ++j9) {
+            for (int q = r0[j9]; q < r1[j9]; ++q) {
+                const double4 o = ldg256_nc(&p.sorted_state[q]);
+                if (q == s || !(r2_exact(me.x - o.x, me.y - o.y) < p.R2)) continue;
+                FGNN_PAIR_FEATURES(o)
+                const int id = __ldg(&p.sorted_id[q]);
+                if (e < ELLW) ell[e] = id;
+                else if (write_row) cols[e] = id;
+                ++e;
+            }
+        }
+        if (wants_row && !write_row) count = 0;           // dropped row (capacity): the graph keeps no edge of it
+        for (int u = count < ELLW ? count : ELLW; u < ELLW; ++u) ell[u] = -1;
+    }
+    stg256(p.xhist + ga * ROW, (float)f0, (float)f1, (float)f2, (float)f3, (float)f4, (float)f5, 0.f, 0.f);
+    p.deg[ga] = count;
+    p.row_start[ga] = row;
+    const float sv = scale_of(count);
+    p.sinv[ga] = sv;
+    // the first hop through graph t gathers x_{t-1}[m] * sinv_t[m]: keep the scale in the pad of that very row
+    if (p.K > 1) p.xhist[((size_t)slot_of(t - 1, p.K) * M + a) * ROW + SINV_PAD] = sv;
+}
+#undef FGNN_PAIR_FEATURES
+
+#endif  // FGNN_MAIN_TU
+
+}  // namespace fgnn

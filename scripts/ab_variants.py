@@ -1,6 +1,6 @@
 """A/B the kernel variants of the closed-loop step on the bench workload (one GPU):
     python scripts/ab_variants.py [N] [steps]
-Variants are selected per engine by environment variables read in fgnn_create (FGNN_STEP_MODE, FGNN_TILE_W/H,
+Variants are selected per engine by environment variables read in fgnn_create (FGNN_STEP_MODE,
 FGNN_ADJ_MODE, FGNN_LAST_HOP_SEPARATE, FGNN_SCAN_TWO_PASS, FGNN_PDL).  Every variant must leave the SAME state bit for bit after the same number of steps
 (the sums run in the same order); the script checks that, then prints graph-replay ms/step and per-kernel times."""
 import itertools
@@ -17,12 +17,10 @@ from multiagent_gnn_policies_b200.engine import FlockEngine        # noqa: E402
 
 
 def run(n, steps, env, x0, sd, k=3, hidden=32, readout_mode=0):
-    for key in ("FGNN_ADJ_MODE", "FGNN_LAST_HOP_SEPARATE", "FGNN_SCAN_TWO_PASS", "FGNN_PDL", "FGNN_STEP_MODE", "FGNN_TILE_W",
-                "FGNN_TILE_H"):
+    for key in ("FGNN_ADJ_MODE", "FGNN_LAST_HOP_SEPARATE", "FGNN_SCAN_TWO_PASS", "FGNN_PDL", "FGNN_STEP_MODE", "FGNN_PR_MINB"):
         os.environ.pop(key, None)
     os.environ.update(env)
-    eng = FlockEngine(n_agents=n, k=k, hidden=hidden, n_layers=2, comm_radius=1.0, dt=0.01, readout_mode=readout_mode,
-                      csr_tail_only=env.get("FGNN_STEP_MODE", "1") != "0" and os.environ.get("FGNN_AB_FULL_CSR") != "1")
+    eng = FlockEngine(n_agents=n, k=k, hidden=hidden, n_layers=2, comm_radius=1.0, dt=0.01, readout_mode=readout_mode)
     eng.load_state_dict(sd)
     eng.reset(x0)
     eng.rollout(40)
@@ -54,11 +52,10 @@ def main():
     print(f"N={n} steps={steps}")
     # round-1 step (separate adjacency / hop kernels) first: it defines the reference bits
     variants = [{"FGNN_STEP_MODE": "0"}]
-    tiles = os.environ.get("FGNN_AB_TILES", "16x8,12x8,16x6,24x6,8x8,32x4,16x4").split(",")
-    for tl in tiles:
-        w, h_ = tl.split("x")
-        variants.append({"FGNN_STEP_MODE": "1", "FGNN_TILE_W": w, "FGNN_TILE_H": h_})
-    variants.append({"FGNN_STEP_MODE": "1", "FGNN_PDL": "1"})
+    variants.append({"FGNN_STEP_MODE": "1"})
+    for extra in os.environ.get("FGNN_AB_EXTRA", "").split(";"):
+        if extra:
+            variants.append(dict({"FGNN_STEP_MODE": "1"}, **dict(kv.split("=") for kv in extra.split(","))))
     for env in variants:
         ms, per, st = run(n, steps, env, x0, sd)
         if ref_state is None:

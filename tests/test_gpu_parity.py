@@ -482,20 +482,22 @@ def test_float64_action_path(centralized):
 
 
 @pytest.mark.parametrize("n,episodes,k,radius,tail_only", [
-    (100, 1, 3, 1.0, False),          # 10 x 10 grid: every window wraps around the seam
+    (100, 1, 3, 1.0, False),          # 10 x 10 grid: every warp straddles grid rows (per-lane path)
+    (200000, 1, 3, 1.0, False),       # 447-cell rows: nearly every warp takes the staged path
+    (150000, 1, 3, 1.0, True),
     (3000, 1, 3, 1.0, True),
     (20000, 1, 4, 1.0, False),
     (5000, 1, 2, 1.0, False),
     (4000, 1, 1, 1.0, False),
     (500, 6, 3, 1.0, False),          # batched episodes
     (3000, 1, 3, 3.0, False),         # ~45 neighbours: cell rows longer than 32 candidates, rows longer than the staged
-                                      # neighbour list, windows that must be subdivided to fit the stage
+                                      # neighbour list, warps that outgrow the stage
     (2500, 1, 3, 2.0, True),
 ])
-def test_tile_kernel_equals_separate_kernels(n, episodes, k, radius, tail_only, monkeypatch):
-    """k_tile (FGNN_STEP_MODE=1: adjacency + features + first hop fused per cell tile, TMA-staged, fp32 pre-filter with the
-    float64 test for pairs inside the margin) must leave the same bits as k_adjacency_t + k_hop (FGNN_STEP_MODE=0): degrees,
-    features, aggregated z, actions and the integrated state, over a closed-loop rollout."""
+def test_pair_kernels_equal_separate_kernels(n, episodes, k, radius, tail_only, monkeypatch):
+    """k_pair_filter + k_pair_fused (FGNN_STEP_MODE=1: adjacency + features + first hop from warp-staged row ranges, TMA bulk
+    staging, fp32 pre-filter with the float64 test for pairs inside the margin) must leave the same bits as k_adjacency_t +
+    k_hop (FGNN_STEP_MODE=0): degrees, features, aggregated z, actions and the integrated state, over a closed-loop rollout."""
     from multiagent_gnn_policies_b200.engine import FlockEngine
     rng = np.random.default_rng(n + k)
     sd = _random_state_dict(rng, k, 32, 2)
@@ -518,18 +520,12 @@ def test_tile_kernel_equals_separate_kernels(n, episodes, k, radius, tail_only, 
         eng.rollout(6)                    # ... and the CUDA-graph replay of the same kernels
         out.append((eng.get_degrees(), eng.get_features(), eng.get_state()))
         assert not eng.stats()["overflow"]
-        if mode == "1" and not tail_only:
-            rs, dg, cols, _ = eng.csr()   # full CSR rows in tile mode too: same neighbour order as the ELL head
-            runs.append((out, np.concatenate([cols[rs[a_]:rs[a_] + dg[a_]] for a_ in range(min(n * episodes, 500))])))
-        elif mode == "0":
-            rs, dg, cols, _ = eng.csr()
-            runs.append((out, np.concatenate([cols[rs[a_]:rs[a_] + dg[a_]] for a_ in range(min(n * episodes, 500))])))
-        else:
-            runs.append((out, None))
+        # complete CSR rows (pair mode: assembled on demand from the ELL head + the tail of long rows): same neighbour order
+        rs, dg, cols, _ = eng.csr()
+        runs.append((out, np.concatenate([cols[rs[a_]:rs[a_] + dg[a_]] for a_ in range(min(n * episodes, 2000))])))
         eng.close()
     (a_out, a_cols), (b_out, b_cols) = runs
     for t, (ra, rb) in enumerate(zip(a_out, b_out)):
         for u, v in zip(ra, rb):
             np.testing.assert_array_equal(u, v, err_msg=f"step {t}")
-    if b_cols is not None:
-        np.testing.assert_array_equal(a_cols, b_cols)
+    np.testing.assert_array_equal(a_cols, b_cols)
