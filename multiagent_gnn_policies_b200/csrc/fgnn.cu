@@ -514,7 +514,7 @@ static void pack_tc_weights(fgnn_handle* h) {
     if (!h->raw_w[L].empty()) {
         float* wl = reinterpret_cast<float*>(base + tl.off_wl());
         for (int a = 0; a < 2; ++a)
-            for (int i = 0; i < H; ++i) wl[i * 2 + a] = h->raw_w[L][(size_t)a * H + i];
+            for (int i = 0; i < H; ++i) wl[(i / 2) * 4 + a * 2 + (i & 1)] = h->raw_w[L][(size_t)a * H + i];   // pairs of hidden units (FFMA2)
         memcpy(base + tl.off_bl(), h->raw_b[L].data(), 2 * 4);
     }
 }

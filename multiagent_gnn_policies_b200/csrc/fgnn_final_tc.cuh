@@ -117,12 +117,31 @@ __device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&v)[N]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// x = hi + lo with hi the round-to-nearest tf32 of x; the tensor core ignores lo's low 13 mantissa bits
-__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-    uint32_t h;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
-    hi = __uint_as_float(h);
-    lo = x - hi;
+// x = hi + lo with hi the round-to-nearest (ties away) tf32 of x; the tensor core ignores lo's low 13 mantissa bits.
+// cvt.rna.tf32.f32 compiles to this add-and-mask plus an inf/NaN guard (FSETP + SEL per value): the guard is dropped --
+// every value split here is finite (features of distinct agents, tanh outputs).  Two values at a time: the subtraction is
+// one packed FFMA2 (hi * -1 + x is exactly x - hi).
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
+__device__ __forceinline__ void split2_tf32(float2 x, float2& hi, float2& lo) {
+    hi = make_float2(tf32_hi(x.x), tf32_hi(x.y));
+    lo = __ffma2_rn(hi, make_float2(-1.f, -1.f), x);
+}
+
+// tanh_act (fgnn_final.cuh) of two pre-activations h + b at once, same operations and roundings, packed fp32x2 arithmetic
+// where the pipe has it (sm_100 FADD2 / FMUL2 / FFMA2): 5.5 issue slots per activation instead of 8.
+__device__ __forceinline__ float2 tanh2(float2 h, float2 b) {
+    const float2 x = __fadd2_rn(h, b);
+    const float2 y = __fmul2_rn(x, make_float2(2.885390081777927f, 2.885390081777927f));
+    float e0, e1, r0, r1;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(-fabsf(y.x)));                     // e^{-2|x|}
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(-fabsf(y.y)));
+    const float2 e = make_float2(e0, e1);
+    const float2 den = __fadd2_rn(e, make_float2(1.f, 1.f));
+    const float2 num = __ffma2_rn(e, make_float2(-1.f, -1.f), make_float2(1.f, 1.f));    // 1 - e, one rounding
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(den.x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(den.y));
+    const float2 q = __fmul2_rn(num, make_float2(r0, r1));
+    return make_float2(copysignf(q.x, x.x), copysignf(q.y, x.y));
 }
 
 }  // namespace tc
@@ -176,64 +195,73 @@ __global__ void __launch_bounds__(FINAL_THREADS) k_final_tc(Params p, const uint
     double safe_lo = 1.0, safe_hi = -1.0;                                     // interior interval of the step (k_shard_prepare), read once
     if (CLOSED && p.fuse) { safe_lo = p.fuse->ctl.safe[0]; safe_hi = p.fuse->ctl.safe[1]; }
     const int tile_end = (p.tile_hi > 0 && p.tile_hi < n_tiles) ? p.tile_hi : n_tiles;     // chunked launches (fgnn_policy)
-    for (int tile = p.tile_lo + blockIdx.x; tile < tile_end; tile += gridDim.x) {
+    // inputs of one tile: the agent, its z rows (6K readout inputs) and -- closed loop -- its state for the integrator
+    auto load_tile = [&](int tile, int& a, float (&in)[K0], double4& st_own) {
         const int oi = tile * FINAL_THREADS + tid;
-        const int a = oi < n_owned ? owned_agent(p, oi) : -1;     // -1: beyond the list or a handed-over slot
-        const bool valid = a >= 0;
-        float in[K0];
+        a = (tile < tile_end && oi < n_owned) ? owned_agent(p, oi) : -1;     // -1: beyond the list or a handed-over slot
 #pragma unroll
         for (int i = 0; i < K0; ++i) in[i] = 0.f;
-        double4 st_own = make_double4(0, 0, 0, 0);         // integrator input, fetched early: its latency hides behind the gather
-        if (CLOSED && valid) st_own = ldg256(&p.state[a]);
-        if (valid) {
-            {   // z_0 = x_t
-                float v[F];
-                load_row6(p.xhist + (size_t)slot_of(t, K) * M * ROW, a, v);
+        st_own = make_double4(0, 0, 0, 0);
+        if (a < 0) return;
+        if (CLOSED) st_own = ldg256(&p.state[a]);
+        {   // z_0 = x_t
+            float v[F];
+            load_row6(p.xhist + (size_t)slot_of(t, K) * M * ROW, a, v);
 #pragma unroll
-                for (int f = 0; f < F; ++f) in[f] = v[f];
-            }
-#pragma unroll
-            for (int k = 1; k < K - 1; ++k) {
-                float v[F];
-                load_row6(p.zbuf + (size_t)k * M * ROW, a, v);
-#pragma unroll
-                for (int f = 0; f < F; ++f) in[k * F + f] = v[f];
-            }
-            if (K >= 2 && p.last_hop_done) {          // tap K-1 finished by a separate hop launch
-                float v[F];
-                load_row6(p.zbuf + (size_t)(K - 1) * M * ROW, a, v);
-#pragma unroll
-                for (int f = 0; f < F; ++f) in[(K - 1) * F + f] = v[f];
-            } else if (K >= 2) {
-                constexpr int j = K - 2;
-                const int g = slot_of(t - j, K);
-                const float* __restrict__ src = (j == 0) ? p.xhist + (size_t)slot_of(t - (K - 1), K) * M * ROW
-                                                         : p.ybuf + ((size_t)((j - 1) & 1) * K + (K - 1)) * M * ROW;
-                const float* const srcs[1] = {src};
-                float acc1[1][F];
-                gather_rows<1, (j > 0)>(p, g, a, srcs, acc1);
-                float acc[F];
-#pragma unroll
-                for (int f = 0; f < F; ++f) acc[f] = acc1[0][f];
-#pragma unroll
-                for (int f = 0; f < F; ++f) in[(K - 1) * F + f] = acc[f];
-                if (p.write_z_last) store_row6(p.zbuf + (size_t)(K - 1) * M * ROW, a, acc);
-            }
+            for (int f = 0; f < F; ++f) in[f] = v[f];
         }
+#pragma unroll
+        for (int k = 1; k < K - 1; ++k) {
+            float v[F];
+            load_row6(p.zbuf + (size_t)k * M * ROW, a, v);
+#pragma unroll
+            for (int f = 0; f < F; ++f) in[k * F + f] = v[f];
+        }
+        if (K >= 2 && p.last_hop_done) {          // tap K-1 finished by a separate hop launch
+            float v[F];
+            load_row6(p.zbuf + (size_t)(K - 1) * M * ROW, a, v);
+#pragma unroll
+            for (int f = 0; f < F; ++f) in[(K - 1) * F + f] = v[f];
+        } else if (K >= 2) {
+            constexpr int j = K - 2;
+            const int g = slot_of(t - j, K);
+            const float* __restrict__ src = (j == 0) ? p.xhist + (size_t)slot_of(t - (K - 1), K) * M * ROW
+                                                     : p.ybuf + ((size_t)((j - 1) & 1) * K + (K - 1)) * M * ROW;
+            const float* const srcs[1] = {src};
+            float acc1[1][F];
+            gather_rows<1, (j > 0)>(p, g, a, srcs, acc1);
+            float acc[F];
+#pragma unroll
+            for (int f = 0; f < F; ++f) acc[f] = acc1[0][f];
+#pragma unroll
+            for (int f = 0; f < F; ++f) in[(K - 1) * F + f] = acc[f];
+            if (p.write_z_last) store_row6(p.zbuf + (size_t)(K - 1) * M * ROW, a, acc);
+        }
+    };
+    // Software pipeline over the CTA's tiles: the NEXT tile's rows are requested before the current tile's MLP starts, so
+    // their latency (the kernel's largest stall: every warp of a CTA is in the same phase) hides behind ~1000 instructions.
+    int a_cur;
+    float in[K0];
+    double4 st_own;
+    load_tile(p.tile_lo + blockIdx.x, a_cur, in, st_own);
+    for (int tile = p.tile_lo + blockIdx.x; tile < tile_end; tile += gridDim.x) {
+        const int oi = tile * FINAL_THREADS + tid;
+        const int a = a_cur;
+        const bool valid = a >= 0;
+        const double4 st_cur = st_own;
         // ---- layer 0: A0 = z (tf32 hi/lo), canonical layout, row = tid ----
         {
             const int rowoff = (tid >> 3) * (K0 / 4) * 128 + (tid & 7) * 16;
 #pragma unroll
             for (int c = 0; c < K0 / 4; ++c) {
-                float4 hi, lo;
-                tc::split_tf32(in[4 * c + 0], hi.x, lo.x);
-                tc::split_tf32(in[4 * c + 1], hi.y, lo.y);
-                tc::split_tf32(in[4 * c + 2], hi.z, lo.z);
-                tc::split_tf32(in[4 * c + 3], hi.w, lo.w);
-                *reinterpret_cast<float4*>(s_ahi + rowoff + c * 128) = hi;
-                *reinterpret_cast<float4*>(s_alo + rowoff + c * 128) = lo;
+                float2 h0, l0, h1, l1;
+                tc::split2_tf32(make_float2(in[4 * c + 0], in[4 * c + 1]), h0, l0);
+                tc::split2_tf32(make_float2(in[4 * c + 2], in[4 * c + 3]), h1, l1);
+                *reinterpret_cast<float4*>(s_ahi + rowoff + c * 128) = make_float4(h0.x, h0.y, h1.x, h1.y);
+                *reinterpret_cast<float4*>(s_alo + rowoff + c * 128) = make_float4(l0.x, l0.y, l1.x, l1.y);
             }
         }
+        load_tile(tile + gridDim.x, a_cur, in, st_own);          // prefetch (in[] was consumed above)
         tc::fence_async_smem();
         tc::fence_before_sync();
         __syncthreads();
@@ -260,17 +288,15 @@ __global__ void __launch_bounds__(FINAL_THREADS) k_final_tc(Params p, const uint
         tc::tmem_ld<HP>(tmem_row, h);
         // ---- hidden layers l = 1 .. L-1 ----
         for (int l = 1; l < p.L; ++l) {
-            const float* bprev = s_f32 + tl.off_b(l - 1) / 4;
+            const float2* bprev = reinterpret_cast<const float2*>(s_f32 + tl.off_b(l - 1) / 4);
             const int rowoff = (tid >> 3) * (HP / 4) * 128 + (tid & 7) * 16;
 #pragma unroll
             for (int c = 0; c < HP / 4; ++c) {
-                float4 hi, lo;
-                tc::split_tf32(tanh_act(h[4 * c + 0] + bprev[4 * c + 0]), hi.x, lo.x);
-                tc::split_tf32(tanh_act(h[4 * c + 1] + bprev[4 * c + 1]), hi.y, lo.y);
-                tc::split_tf32(tanh_act(h[4 * c + 2] + bprev[4 * c + 2]), hi.z, lo.z);
-                tc::split_tf32(tanh_act(h[4 * c + 3] + bprev[4 * c + 3]), hi.w, lo.w);
-                *reinterpret_cast<float4*>(s_ahi + rowoff + c * 128) = hi;
-                *reinterpret_cast<float4*>(s_alo + rowoff + c * 128) = lo;
+                float2 h0, l0, h1, l1;
+                tc::split2_tf32(tc::tanh2(make_float2(h[4 * c + 0], h[4 * c + 1]), bprev[2 * c + 0]), h0, l0);
+                tc::split2_tf32(tc::tanh2(make_float2(h[4 * c + 2], h[4 * c + 3]), bprev[2 * c + 1]), h1, l1);
+                *reinterpret_cast<float4*>(s_ahi + rowoff + c * 128) = make_float4(h0.x, h0.y, h1.x, h1.y);
+                *reinterpret_cast<float4*>(s_alo + rowoff + c * 128) = make_float4(l0.x, l0.y, l1.x, l1.y);
             }
             tc::fence_async_smem();
             tc::fence_before_sync();
@@ -297,22 +323,23 @@ __global__ void __launch_bounds__(FINAL_THREADS) k_final_tc(Params p, const uint
             tc::fence_after_sync();
             tc::tmem_ld<HP>(tmem_row + (uint32_t)((l & 1) * HP), h);
         }
-        // ---- output layer on CUDA cores: 2 x HP FFMA ----
-        const float* blast = s_f32 + tl.off_b(p.L - 1) / 4;
-        const float2* wlp = reinterpret_cast<const float2*>(s_w + tl.off_wl());
+        // ---- output layer on CUDA cores: HP FFMA2 (hidden units two at a time: even and odd partial sums) ----
+        const float2* blast = reinterpret_cast<const float2*>(s_f32 + tl.off_b(p.L - 1) / 4);
+        const float4* wlp = reinterpret_cast<const float4*>(s_w + tl.off_wl());      // [HP/2]: (w_i^0, w_{i+1}^0, w_i^1, w_{i+1}^1)
         const float* bl = s_f32 + tl.off_bl() / 4;
-        float o0 = bl[0], o1 = bl[1];
+        float2 acc0 = make_float2(bl[0], 0.f), acc1 = make_float2(bl[1], 0.f);
 #pragma unroll
-        for (int i = 0; i < HP; ++i) {
-            const float hv = tanh_act(h[i] + blast[i]);
-            const float2 ww = wlp[i];
-            o0 = fmaf(hv, ww.x, o0);
-            o1 = fmaf(hv, ww.y, o1);
+        for (int i = 0; i < HP; i += 2) {
+            const float2 hv = tc::tanh2(make_float2(h[i], h[i + 1]), blast[i / 2]);
+            const float4 ww = wlp[i / 2];
+            acc0 = __ffma2_rn(hv, make_float2(ww.x, ww.y), acc0);
+            acc1 = __ffma2_rn(hv, make_float2(ww.z, ww.w), acc1);
         }
+        const float o0 = acc0.x + acc0.y, o1 = acc1.x + acc1.y;
         if (valid) {
             reinterpret_cast<float2*>(p.action)[a] = make_float2(o0, o1);
             if (CLOSED) {
-                const double4 st_new = integrate_and_bin(p, a, st_own, o0, o1, racc);
+                const double4 st_new = integrate_and_bin(p, a, st_cur, o0, o1, racc);
                 if (p.fuse) shard_pack_agent(p, *p.fuse, oi, a, st_new, klo, khi, safe_lo, safe_hi);
             }
         }
