@@ -437,8 +437,7 @@ def main():
     peak, peak_src = measured_peaks()
     # SURVEY.md 8(d) algorithmic bytes per agent per launch (K=3; fp32 values, int32 CSR, 16 B state)
     d = deg_prof
-    alg_bytes = {"adjacency": 44 + 4 * d, "hop0": 104 + 4 * d, "final": 120 + 4 * d,
-                 "tile": 148 + 8 * d}          # k_tile = adjacency + features + first hop in one kernel: K1 + K2 of SURVEY 8(d)
+    alg_bytes = {"adjacency": 44 + 4 * d, "pair_adjacency": 44 + 4 * d, "hop0": 104 + 4 * d, "final": 120 + 4 * d}
     if "hop_last" in prof:
         # the last hop runs as its own launch: SURVEY's K3 row splits into the gather (CSR 4d+4, deg 4, source rows 24,
         # z_2 written 24) and the streaming readout + integrator (x_t, z_1, z_2 24 each, state 16 in / 16 out, action 8)
@@ -460,7 +459,7 @@ def main():
                           "achieved": step_bytes * value / world / 1e9, "frac": step_bytes * value / world / 1e9 / peak}
     roof["per_kernel_frac"] = {k_: round(alg_bytes[k_] * N / (v * 1e-3) / 1e9 / peak, 4) for k_, v in prof.items()
                                if k_ in alg_bytes and args.k == 3}
-    if dom in ("adjacency", "tile"):
+    if dom in ("adjacency", "pair_adjacency"):
         roof["note"] = ("the dominant kernel is the float64 pair test + feature kernel: 64 algorithmic bytes per agent but "
                         "~14 candidate pairs per agent in float64 -- issue/fp64-pipe bound, not HBM bound (profiles/)")
 

@@ -120,6 +120,7 @@ struct fgnn_handle {
     // sharding
     bool sharded = false;
     bool shard_configured = false;
+    bool shard_fold = true;          // p2p step: k_shard_prepare's work in block 0 of the last hop
     ShardCtl ctl;
     int* d_own = nullptr;
     int* d_ghost = nullptr;
@@ -396,6 +397,9 @@ extern "C" int fgnn_create(const fgnn_config* cfg, fgnn_handle** out) {
         rc |= dalloc(h, &h->d_xminmax, (size_t)2 * (blocks_for(p.pool_cap, FINAL_THREADS) + 1));
         rc |= dalloc(h, &h->d_shift, 1);
         rc |= dalloc(h, &h->d_safe, 2);
+        rc |= dalloc(h, &p.n_ghost_snap, 1);
+        const char* sf = getenv("FGNN_SHARD_FOLD");
+        if (sf) h->shard_fold = atoi(sf) != 0;
         p.own = h->d_own;
         p.n_own_d = h->d_counts + 0;
         p.ghost = h->d_ghost;
@@ -468,6 +472,7 @@ extern "C" int fgnn_create(const fgnn_config* cfg, fgnn_handle** out) {
             int tiles = blocks_for(h->sharded ? p.pool_cap : p.n_own, FINAL_THREADS);
             if (grid > tiles) grid = tiles;
             (closed ? h->tc_grid_closed : h->tc_grid_open) = grid;
+            if (getenv("FGNN_DEBUG")) fprintf(stderr, "[fgnn] final_tc closed=%d regs=%d smem=%zu occ=%d grid=%d tiles=%d sharded=%d\n", closed, fa.numRegs, h->tc_smem, occ, grid, tiles, (int)h->sharded);
         }
     }
     *out = h;
@@ -642,11 +647,14 @@ static int enqueue_build(fgnn_handle* h, int advance, cudaStream_t st) {
 }
 
 template <int NB, bool FIRST>
-static void launch_hop(fgnn_handle* h, int j, cudaStream_t st) {
-    launch_step(h, k_hop<NB, FIRST>, blocks_for(h->launch_pool, 256), 256, 0, st, h->p, j);
+static void launch_hop(fgnn_handle* h, int j, cudaStream_t st, int tail = 0) {
+    Params p = h->p;
+    if (tail) p.fuse = h->d_fuse;
+    launch_step(h, k_hop<NB, FIRST>, blocks_for(h->launch_pool, 256), 256, 0, st, p, j, tail);
 }
 
-static int enqueue_hops(fgnn_handle* h, cudaStream_t st) {
+// prepare_tail: p2p step of a sharded rank -- block 0 of the LAST hop launch also does k_shard_prepare's work
+static int enqueue_hops(fgnn_handle* h, cudaStream_t st, bool prepare_tail = false) {
     Params& p = h->p;
     for (int j = 0; j + 2 < p.K; ++j) {     // hops 0 .. K-3 ; hop K-2 lives in the final kernel (or below)
         const int nb = p.K - 1 - j;
@@ -658,8 +666,8 @@ static int enqueue_hops(fgnn_handle* h, cudaStream_t st) {
     }
     if (h->last_hop_separate && p.K >= 2) {  // tap K-1 through graph t-(K-2), written to zbuf[K-1] for the final kernel
         const int j = p.K - 2;
-        if (j == 0) launch_hop<1, true>(h, j, st);
-        else launch_hop<1, false>(h, j, st);
+        if (j == 0) launch_hop<1, true>(h, j, st, prepare_tail ? 1 : 0);
+        else launch_hop<1, false>(h, j, st, prepare_tail ? 1 : 0);
         if (launch_check(h, "hop_last")) return 1;
     }
     return 0;
@@ -1434,9 +1442,15 @@ extern "C" int fgnn_p2p_seed(fgnn_handle* h, const double* gathered, void* strea
 }
 
 static int enqueue_p2p_step(fgnn_handle* h, const ShardFuse& f, int final_grid, long long parity_stride, cudaStream_t cs) {
-    if (enqueue_hops(h, cs)) return 1;
-    k_shard_prepare<<<1, 256, 0, cs>>>(h->p, f, 1);
-    if (launch_check(h, "shard_prepare")) return 1;
+    // k_shard_prepare's work rides on block 0 of the last hop: one one-block launch less on the critical path of the step
+    // (FGNN_SHARD_FOLD=0: the separate launch).  The same was tried for k_shard_flag -- "last block done" epilogue of the final
+    // kernel -- and dropped: the per-block fence + ticket cost the kernel what the launch had cost (and 36 registers).
+    const bool fold = h->shard_fold && h->last_hop_separate && h->p.K >= 2;
+    if (enqueue_hops(h, cs, fold)) return 1;
+    if (!fold) {
+        k_shard_prepare<<<1, 256, 0, cs>>>(h->p, f, 1);
+        if (launch_check(h, "shard_prepare")) return 1;
+    }
     if (enqueue_final(h, true, 0, cs, true)) return 1;
     k_shard_flag<<<1, 256, 0, cs>>>(h->p, f, final_grid);
     if (launch_check(h, "shard_flag")) return 1;

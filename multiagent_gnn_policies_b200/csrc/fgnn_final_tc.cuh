@@ -149,7 +149,7 @@ __device__ __forceinline__ float2 tanh2(float2 h, float2 b) {
 __host__ __device__ constexpr int tc_tmem_cols(int HP) { return 2 * HP < 32 ? 32 : 2 * HP; }
 
 template <int K, int HP, bool CLOSED>
-__global__ void __launch_bounds__(FINAL_THREADS) k_final_tc(Params p, const uint8_t* __restrict__ tcw) {
+__global__ void __launch_bounds__(FINAL_THREADS, 4) k_final_tc(Params p, const uint8_t* __restrict__ tcw) {
     pdl_prologue();
     static_assert(HP == 16 || HP == 32 || HP == 64, "tensor-core readout supports HP in {16,32,64}");
     constexpr int K0 = (F * K + 7) & ~7;

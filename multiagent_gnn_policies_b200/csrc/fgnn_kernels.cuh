@@ -45,6 +45,8 @@ struct Params {
     const int* ghost;         // [pool_cap] agents received from other ranks this step
     const int* n_ghost_d;     // device count of ghosts
     const struct ShardFuse* fuse;   // non-null: the closed final kernel also packs the halo records (fgnn_shard_step_begin)
+    int* n_ghost_snap;        // ghost count as of the last graph build (written by the adjacency kernel): what the hop kernels walk,
+                              //     so that the ghost counter itself may be reset while they run
     int mean_pooling;
     int half_accel;
     int sums_in_bin;          // every binning site also accumulates the per-scan-tile sums (no k_scan_sums launch)
@@ -170,6 +172,8 @@ __device__ __forceinline__ int pool_agent(const Params& p, int i) {
     const int no = *p.n_own_d;
     return i < no ? p.own[i] : p.ghost[i - no];
 }
+// the same pool as the hop kernels see it: ghost count from the snapshot taken when the graph was built
+__device__ __forceinline__ int hop_pool_size(const Params& p) { return p.own ? *p.n_own_d + *p.n_ghost_snap : p.M; }
 
 // r2 exactly as numpy evaluates dx*dx + dy*dy (two roundings of the products, one of the sum; no FMA)
 __device__ __forceinline__ double r2_exact(double dx, double dy) {
@@ -525,7 +529,10 @@ __global__ void __launch_bounds__(ADJ_THREADS, WS ? 8 : 1) k_adjacency_t(Params 
     const int warp = tid >> 5;
     // housekeeping for the next scan
     for (int i = s; i < p.n_tiles; i += gridDim.x * ADJ_THREADS) p.tile_status[i] = 0;
-    if (s == 0) *p.tile_counter = 0;
+    if (s == 0) {
+        *p.tile_counter = 0;
+        if (p.own) *p.n_ghost_snap = *p.n_ghost_d;
+    }
 
     const int t = *p.t;
     const int g = slot_of(t, p.K);
@@ -833,11 +840,18 @@ __device__ __forceinline__ void gather_rows(const Params& p, int g, int a, const
 #ifndef FGNN_HOP_MIN_BLOCKS
 #define FGNN_HOP_MIN_BLOCKS 4
 #endif
+struct ShardFuse;
+__device__ void shard_prepare_block(const Params& p);      // (defined with the k_shard_* kernels below)
+
 template <int NB, bool FIRST>
-__global__ void __launch_bounds__(256, NB == 2 ? FGNN_HOP_MIN_BLOCKS : 1) k_hop(Params p, int j) {
+__global__ void __launch_bounds__(256, NB == 2 ? FGNN_HOP_MIN_BLOCKS : 1) k_hop(Params p, int j, int prepare) {
     pdl_prologue();
+    // p2p step of a sharded rank: block 0 of the last hop launch also zeroes the per-step counters, advances the frame and
+    // works out the interior interval for the pack that follows (the hops walk the ghost-count SNAPSHOT, so the counter may be
+    // reset under them): the one-block k_shard_prepare launch leaves the step's critical path
+    if (prepare && blockIdx.x == 0) shard_prepare_block(p);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= pool_size(p)) return;
+    if (i >= hop_pool_size(p)) return;
     const int a = pool_agent(p, i);
     if (a < 0) return;
     const int t = *p.t;
@@ -1020,6 +1034,40 @@ __device__ __forceinline__ void shard_interval_flush(const ShardCtl& c, long lon
         for (int w = 1; w < THREADS / 32; ++w) { klo = min(klo, s_klo[w]); khi = max(khi, s_khi[w]); }
         c.xminmax[2 * blockIdx.x] = klo;
         c.xminmax[2 * blockIdx.x + 1] = khi;
+    }
+}
+
+// p2p transport, after the final kernel has stored the records into the peers' inboxes: header [count, x_lo, x_hi] of this
+// rank into every peer's inbox (and its own), then -- fenced -- the flag word t + 1 that tells the peer its half t & 1 is
+// complete.  One block; thread q serves peer q.
+template <int THREADS>
+__device__ __forceinline__ void shard_flag_body(const Params& p, const ShardFuse& f, int n_blocks) {
+    __shared__ long long s_lo[THREADS / 32], s_hi[THREADS / 32];
+    const ShardCtl& c = f.ctl;
+    long long klo = 0x7fffffffffffffffll, khi = -0x7fffffffffffffffll - 1;
+    for (int i = threadIdx.x; i < n_blocks; i += THREADS) {
+        klo = min(klo, c.xminmax[2 * i]);
+        khi = max(khi, c.xminmax[2 * i + 1]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        klo = min(klo, __shfl_xor_sync(0xffffffffu, klo, o));
+        khi = max(khi, __shfl_xor_sync(0xffffffffu, khi, o));
+    }
+    if ((threadIdx.x & 31) == 0) { s_lo[threadIdx.x >> 5] = klo; s_hi[threadIdx.x >> 5] = khi; }
+    __syncthreads();
+    for (int w = 0; w < THREADS / 32; ++w) { klo = min(klo, s_lo[w]); khi = max(khi, s_hi[w]); }
+    const int t = *p.t;
+    for (int q = threadIdx.x; q < c.world; q += THREADS) {
+        double* hdr = f.peer_inbox[q] + inbox_offset(f, t & 1, c.rank);
+        hdr[0] = q == c.rank ? 0.0 : (double)f.dest_count[q];
+        hdr[1] = dunkey(klo); hdr[2] = dunkey(khi);
+        hdr[3] = 0.0; hdr[4] = 0.0; hdr[5] = 0.0;
+        __threadfence_system();
+        if (q != c.rank) {
+            volatile int* flag = f.peer_flags[q] + (t & 1) * c.world + c.rank;
+            *flag = t + 1;
+        }
     }
 }
 
@@ -1257,10 +1305,10 @@ __global__ void __launch_bounds__(128) k_controller(Params p, int centralized, i
 // absolute x inside which an owned agent (a) lies strictly inside this rank's strip, so it is not handed over, and (b) is
 // outside every other rank's window (strip +- depth united with its announced owned interval +- depth), so nobody wants
 // its record.  Conservative: empty when some other rank's window covers the middle of what this rank owns.
-__global__ void k_shard_prepare(Params p, ShardFuse f, int advance) {
+__device__ __forceinline__ void shard_prepare_body(const Params& p, const ShardFuse& f, int advance) {
     const ShardCtl& c = f.ctl;
     if (f.dest_count && threadIdx.x < c.world) f.dest_count[threadIdx.x] = 0;
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
+    if (threadIdx.x == 0) {
         *c.n_ghost = 0; *c.counter = 0;
         double shift = *c.shift;
         if (advance) { shift += c.dshift; *c.shift = shift; }
@@ -1283,6 +1331,12 @@ __global__ void k_shard_prepare(Params p, ShardFuse f, int advance) {
         c.safe[1] = hi;
     }
 }
+
+__global__ void k_shard_prepare(Params p, ShardFuse f, int advance) {
+    if (blockIdx.x == 0) shard_prepare_body(p, f, advance);
+}
+
+__device__ void shard_prepare_block(const Params& p) { shard_prepare_body(p, *p.fuse, 1); }
 
 __global__ void __launch_bounds__(256) k_shard_pack(Params p, ShardFuse f) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1314,39 +1368,7 @@ __global__ void __launch_bounds__(256) k_shard_header(ShardCtl c, double* __rest
     }
 }
 
-// p2p transport, after the final kernel has stored the records into the peers' inboxes: header [count, x_lo, x_hi] of this
-// rank into every peer's inbox (and its own), then -- fenced -- the flag word t + 1 that tells the peer its half t & 1 is
-// complete.  One block; thread q serves peer q.
-__global__ void __launch_bounds__(256) k_shard_flag(Params p, ShardFuse f, int n_blocks) {
-    __shared__ long long s_lo[8], s_hi[8];
-    const ShardCtl& c = f.ctl;
-    long long klo = 0x7fffffffffffffffll, khi = -0x7fffffffffffffffll - 1;
-    for (int i = threadIdx.x; i < n_blocks; i += blockDim.x) {
-        klo = min(klo, c.xminmax[2 * i]);
-        khi = max(khi, c.xminmax[2 * i + 1]);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        klo = min(klo, __shfl_xor_sync(0xffffffffu, klo, o));
-        khi = max(khi, __shfl_xor_sync(0xffffffffu, khi, o));
-    }
-    if ((threadIdx.x & 31) == 0) { s_lo[threadIdx.x >> 5] = klo; s_hi[threadIdx.x >> 5] = khi; }
-    __syncthreads();
-    for (int w = 0; w < 8; ++w) { klo = min(klo, s_lo[w]); khi = max(khi, s_hi[w]); }
-    const int t = *p.t;
-    const int q = threadIdx.x;
-    if (q < c.world) {
-        double* hdr = f.peer_inbox[q] + inbox_offset(f, t & 1, c.rank);
-        hdr[0] = q == c.rank ? 0.0 : (double)f.dest_count[q];
-        hdr[1] = dunkey(klo); hdr[2] = dunkey(khi);
-        hdr[3] = 0.0; hdr[4] = 0.0; hdr[5] = 0.0;
-        __threadfence_system();
-        if (q != c.rank) {
-            volatile int* flag = f.peer_flags[q] + (t & 1) * c.world + c.rank;
-            *flag = t + 1;
-        }
-    }
-}
+__global__ void __launch_bounds__(256) k_shard_flag(Params p, ShardFuse f, int n_blocks) { shard_flag_body<256>(p, f, n_blocks); }
 
 // grid = (record chunks, world): a block of sender q leaves at once when q sent fewer records than its first slot.
 // parity_stride != 0 (p2p inbox): this step's records sit in half t & 1 of `recv`.

@@ -196,7 +196,10 @@ __global__ void __launch_bounds__(PR_THREADS, MINB) k_pair_adjacency(Params p, P
     const int s = blockIdx.x * PR_THREADS + tid;
     // housekeeping for the next scan
     for (int i = s; i < p.n_tiles; i += gridDim.x * PR_THREADS) p.tile_status[i] = 0;
-    if (s == 0) *p.tile_counter = 0;
+    if (s == 0) {
+        *p.tile_counter = 0;
+        if (p.own) *p.n_ghost_snap = *p.n_ghost_d;
+    }
     if (tid < 64) s_tab[tid] = geo.sinvtab[tid];
     __syncthreads();
     const int ns = sorted_count(p);

@@ -16,7 +16,7 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
         "l1tex__t_sector_hit_rate.pct", "smsp__thread_inst_executed_per_inst_executed.ratio"]
 SHORT = {"k_final_tc": "final", "k_final": "final", "k_scan_sums": "scan_sums", "k_scan": "scan", "k_scatter": "scatter",
-         "k_canon": "canon", "k_adjacency_t": "adjacency", "k_tile": "tile", "k_hop<2": "hop0", "k_hop<3": "hop0",
+         "k_canon": "canon", "k_adjacency_t": "adjacency", "k_pair_adjacency": "pair_adjacency", "k_hop<2": "hop0", "k_hop<3": "hop0",
          "k_hop<(int)2": "hop0", "k_hop<(int)3": "hop0", "k_hop<1": "hop_last", "k_hop<(int)1": "hop_last"}
 
 

@@ -44,13 +44,15 @@ def main():
     sd, _ = make_weights(32, 3, 2)
     side = np.sqrt(n / DENSITY)
     cap = int(max(24, 3.2 * np.pi * DENSITY + 16))
-    eng = FlockEngine(n_agents=n, k=3, hidden=32, n_layers=2, comm_radius=1.0, dt=0.01, edge_capacity=cap)
-    eng.load_state_dict(sd)
-    eng.reset(x0)
-    eng.rollout(30)
-    ms_plain = timed(lambda: eng.rollout(1), steps)
-    per_plain = profile(eng)
-    eng.close()
+    ms_plain, per_plain = 0.0, {}
+    if os.environ.get("FGNN_SHARD_ONLY") != "1":
+        eng = FlockEngine(n_agents=n, k=3, hidden=32, n_layers=2, comm_radius=1.0, dt=0.01, edge_capacity=cap)
+        eng.load_state_dict(sd)
+        eng.reset(x0)
+        eng.rollout(30)
+        ms_plain = timed(lambda: eng.rollout(1), steps)
+        per_plain = profile(eng)
+        eng.close()
 
     depth = parallel.halo_depth(3, 1.0)
     halo_cap = int(1.5 * (depth + 2.0) * side * DENSITY * 2) + 1024
