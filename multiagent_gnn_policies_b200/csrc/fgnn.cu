@@ -1421,6 +1421,13 @@ extern "C" int fgnn_p2p_connect(fgnn_handle* h, const void* handles, void* const
         inbox[q] = reinterpret_cast<double*>(base);
         flags[q] = reinterpret_cast<int*>(inbox[q] + p2p_inbox_doubles(world, h->p2p_cap));
     }
+    // touch every peer's inbox once from this device: the lazily enabled peer access of the IPC mappings (hundreds of ms per
+    // peer) is paid here, not inside the first step's wait loops
+    for (int q = 0; q < world; ++q) {
+        if (q == rank) continue;
+        double probe = 0.0;
+        CK(cudaMemcpy(&probe, inbox[q], sizeof(double), cudaMemcpyDeviceToHost));
+    }
     CK(cudaMemcpy(h->d_peer_inbox, inbox.data(), world * sizeof(double*), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->d_peer_flags, flags.data(), world * sizeof(int*), cudaMemcpyHostToDevice));
     h->p2p_connected = true;

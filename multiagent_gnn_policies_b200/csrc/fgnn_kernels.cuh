@@ -1377,13 +1377,16 @@ __global__ void __launch_bounds__(256) k_shard_unpack(Params p, ShardCtl c, cons
     const int q = blockIdx.y, r = blockIdx.x * blockDim.x + threadIdx.x;
     if (q == c.rank) return;
     if (wait_flags) {                  // p2p: the blocks of sender q wait for q's flag of this step themselves (no separate launch).
-        if (threadIdx.x == 0) {        // A peer that never arrives must not hang the GPU: after ~2 s give up, overflow = 2.
+        if (threadIdx.x == 0) {        // A peer that never arrives must not hang the GPU: after ~30 s give up, overflow = 2.
+                                       // (Not less: the first steps of a many-rank job see seconds of skew -- graph
+                                       // instantiation, lazily enabled peer mappings -- and a wait that gives up early
+                                       // installs a stale half of the inbox.)
             const int t = *p.t;
             volatile const int* flag = wait_flags + (t & 1) * c.world + q;
             const long long t0 = clock64();
             while (*flag != t + 1) {
                 __nanosleep(100);
-                if (clock64() - t0 > 4000000000ll) { *p.overflow = 2; break; }
+                if (clock64() - t0 > 60000000000ll) { *p.overflow = 2; break; }
             }
             __threadfence_system();
         }

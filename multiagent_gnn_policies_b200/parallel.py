@@ -208,6 +208,8 @@ class ShardedFlock:
         handles = all_gather_object(handle)
         self.backend.p2p_connect(handles=b"".join(handles))
         self.backend.p2p_seed(self.recv)
+        self.backend.engine.sync()
+        all_gather_object(b"ready")               # every inbox is mapped and seeded before anybody's first step stores into it
 
     def step(self):
         """One closed-loop step: local policy + integrator for owned agents, halo exchange, rebuild."""
