@@ -561,7 +561,7 @@ def sharded_rollout(args, rank, world, local_rank, n_per_rank, sd, edge_cap, bar
            "mean_degree": st["n_edges"] / max(1, cnt + int(st.get("n_ghosts", 0))), "transport": transport,
            "halo_cap": flock.cap, "depth": flock.depth, "rows_io": be.engine.rows_io}
     if want_e2e:
-        # e2e: the same step through host buffers (select_action -> pinned host -> env.step), gather transport
+        # e2e: the same step through host buffers (select_action -> pinned host -> env.step), halo over the same transport
         e2e_steps = args.e2e_steps or min(steps, 50)
         act_host = torch.empty((be.engine.rows_io, 2), dtype=torch.float32, pin_memory=True).numpy()
         for _ in range(3):

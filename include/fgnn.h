@@ -188,12 +188,16 @@ int fgnn_shard_step(fgnn_handle* h, double* send_buf, double* recv_buf, int32_t 
  *                     pointers (ranks in this process); the own entry is ignored
  *   fgnn_p2p_seed     after the reset-time exchange (fgnn_shard_pack / all-gather / fgnn_shard_unpack): the gathered buffer
  *                     becomes both halves of the inbox (its headers are the first step's windows)
- *   fgnn_shard_step_p2p  one closed-loop step.  A peer that never signals makes the wait give up after ~2 s and raises
- *                     fgnn_stats.overflow = 2 instead of hanging the device. */
+ *   fgnn_shard_step_p2p  one closed-loop step.  A peer that never signals makes the wait give up after ~30 s and raises
+ *                     fgnn_stats.overflow = 2 instead of hanging the device.
+ *   fgnn_shard_exchange_p2p  the halo exchange alone (pack into the peers' inboxes, flags, wait, unpack) for a step whose
+ *                     integrator ran on its own (fgnn_integrate with a host action -- the reference-facing loop,
+ *                     learner/gnn_dagger.py:196-201); follow with fgnn_build_graph(advance). */
 int fgnn_p2p_alloc(fgnn_handle* h, int32_t world, int32_t rank, int32_t cap, void* ipc_handle_64, void** local_ptr);
 int fgnn_p2p_connect(fgnn_handle* h, const void* handles, void* const* direct_ptrs);
 int fgnn_p2p_seed(fgnn_handle* h, const double* gathered, void* stream);
 int fgnn_shard_step_p2p(fgnn_handle* h, void* stream);
+int fgnn_shard_exchange_p2p(fgnn_handle* h, int32_t advance, void* stream);
 
 /* ---- environment variants named by the reference's cfgs (gym_flock, un-vendored) ----
  * FlockingLeader-v0 (cfg/dagger_leader.cfg:24): mask_bn (B*N,) bytes [h/d], 0 = leader -- the integrator ignores

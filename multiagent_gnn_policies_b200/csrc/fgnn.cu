@@ -1130,10 +1130,10 @@ static int enqueue_shard_pack(fgnn_handle* h, const double* windows, int64_t win
 }
 
 static int enqueue_shard_unpack(fgnn_handle* h, const double* recv_buf, int cap, cudaStream_t st, long long parity_stride = 0,
-                                const int* wait_flags = nullptr) {
+                                const int* wait_flags = nullptr, const ShardFuse* flag_fuse = nullptr, int n_pack_blocks = 0) {
     Params& p = h->p;
     k_shard_unpack<<<dim3((unsigned)blocks_for(cap, 256), (unsigned)h->ctl.world), 256, 0, st>>>(p, h->ctl, recv_buf, cap, parity_stride,
-                                                                                                  wait_flags);
+                                                                                                  wait_flags, flag_fuse, n_pack_blocks);
     if (launch_check(h, "shard_unpack")) return 1;
     h->binned = true;
     return 0;
@@ -1449,9 +1449,10 @@ extern "C" int fgnn_p2p_seed(fgnn_handle* h, const double* gathered, void* strea
 }
 
 static int enqueue_p2p_step(fgnn_handle* h, const ShardFuse& f, int final_grid, long long parity_stride, cudaStream_t cs) {
-    // k_shard_prepare's work rides on block 0 of the last hop: one one-block launch less on the critical path of the step
-    // (FGNN_SHARD_FOLD=0: the separate launch).  The same was tried for k_shard_flag -- "last block done" epilogue of the final
-    // kernel -- and dropped: the per-block fence + ticket cost the kernel what the launch had cost (and 36 registers).
+    // k_shard_prepare's work rides on block 0 of the last hop, k_shard_flag's on block (0, 0) of the unpack: two one-block
+    // launches less on the critical path of the step (FGNN_SHARD_FOLD=0: the separate launches).  (A "last block done" epilogue
+    // of the final kernel for the flag was tried and dropped: the per-block fence + ticket cost the kernel what the launch had
+    // cost, and 36 registers.)
     const bool fold = h->shard_fold && h->last_hop_separate && h->p.K >= 2;
     if (enqueue_hops(h, cs, fold)) return 1;
     if (!fold) {
@@ -1459,11 +1460,13 @@ static int enqueue_p2p_step(fgnn_handle* h, const ShardFuse& f, int final_grid, 
         if (launch_check(h, "shard_prepare")) return 1;
     }
     if (enqueue_final(h, true, 0, cs, true)) return 1;
-    k_shard_flag<<<1, 256, 0, cs>>>(h->p, f, final_grid);
-    if (launch_check(h, "shard_flag")) return 1;
-    // (the unpack blocks of sender q wait for q's flag themselves)
+    if (!fold) {
+        k_shard_flag<<<1, 256, 0, cs>>>(h->p, f, final_grid);
+        if (launch_check(h, "shard_flag")) return 1;
+    }
+    // (the unpack blocks of sender q wait for q's flag themselves; folded: block (0, 0) raises this rank's flags first)
     const int* my_flags = reinterpret_cast<const int*>(h->p2p_inbox + p2p_inbox_doubles(h->p2p_world, h->p2p_cap));
-    if (enqueue_shard_unpack(h, h->p2p_inbox, h->p2p_cap, cs, parity_stride, my_flags)) return 1;
+    if (enqueue_shard_unpack(h, h->p2p_inbox, h->p2p_cap, cs, parity_stride, my_flags, fold ? h->d_fuse : nullptr, final_grid)) return 1;
     return enqueue_build(h, 1, cs);
 }
 
@@ -1492,6 +1495,32 @@ extern "C" int fgnn_shard_step_p2p(fgnn_handle* h, void* stream) {
     h->binned = false;
     h->t_host += 1;
     return 0;
+}
+
+// The halo exchange alone over the p2p transport, for steps whose integrator ran on its own (fgnn_integrate with a host
+// action: the reference-facing loop).  prepare -> pack (records into the peers' inboxes) -> unpack (+ flags, wait).
+extern "C" int fgnn_shard_exchange_p2p(fgnn_handle* h, int32_t advance, void* stream) {
+    if (!h || !h->sharded) return fail("fgnn_shard_exchange_p2p: handle is not sharded");
+    if (!h->p2p_connected) return fail("fgnn_shard_exchange_p2p: call fgnn_p2p_alloc / fgnn_p2p_connect / fgnn_p2p_seed first");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(h->cfg.device));
+    ShardFuse f;
+    memset(&f, 0, sizeof f);
+    f.ctl = h->ctl; f.cap = h->p2p_cap; f.p2p = 1;
+    f.peer_inbox = h->d_peer_inbox; f.peer_flags = h->d_peer_flags; f.dest_count = h->d_dest_count;
+    if (memcmp(&f, &h->fuse_host, sizeof f) != 0) {
+        h->fuse_host = f;
+        CK(cudaMemcpyAsync(h->d_fuse, &h->fuse_host, sizeof f, cudaMemcpyHostToDevice, st));
+    }
+    const Params& p = h->p;
+    const int n_blocks = blocks_for(p.pool_cap, 256);
+    k_shard_prepare<<<1, 256, 0, st>>>(p, f, advance);
+    if (launch_check(h, "shard_prepare")) return 1;
+    k_shard_pack<<<n_blocks, 256, 0, st>>>(p, f);
+    if (launch_check(h, "shard_pack")) return 1;
+    const long long parity_stride = (long long)(p2p_inbox_doubles(h->p2p_world, h->p2p_cap) / 2);
+    const int* my_flags = reinterpret_cast<const int*>(h->p2p_inbox + p2p_inbox_doubles(h->p2p_world, h->p2p_cap));
+    return enqueue_shard_unpack(h, h->p2p_inbox, h->p2p_cap, st, parity_stride, my_flags, h->d_fuse, n_blocks);
 }
 
 extern "C" int fgnn_profile_step(fgnn_handle* h, int32_t max_kernels, float* ms_out, char* names_out, int32_t* n_out,

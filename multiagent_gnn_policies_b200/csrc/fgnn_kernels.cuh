@@ -1064,10 +1064,8 @@ __device__ __forceinline__ void shard_flag_body(const Params& p, const ShardFuse
         hdr[1] = dunkey(klo); hdr[2] = dunkey(khi);
         hdr[3] = 0.0; hdr[4] = 0.0; hdr[5] = 0.0;
         __threadfence_system();
-        if (q != c.rank) {
-            volatile int* flag = f.peer_flags[q] + (t & 1) * c.world + c.rank;
-            *flag = t + 1;
-        }
+        volatile int* flag = f.peer_flags[q] + (t & 1) * c.world + c.rank;      // (own entry: "my header of this step is written")
+        *flag = t + 1;
     }
 }
 
@@ -1372,9 +1370,17 @@ __global__ void __launch_bounds__(256) k_shard_flag(Params p, ShardFuse f, int n
 
 // grid = (record chunks, world): a block of sender q leaves at once when q sent fewer records than its first slot.
 // parity_stride != 0 (p2p inbox): this step's records sit in half t & 1 of `recv`.
+// flag_fuse != null (p2p): block (0, 0) first does k_shard_flag's work -- headers and flags of THIS rank to every peer -- so the
+// step needs no separate one-block launch for it; every block then waits for its sender's flag and for this rank's own
+// (the own header, which the window test below reads, is written by block (0, 0) of this very grid).
 __global__ void __launch_bounds__(256) k_shard_unpack(Params p, ShardCtl c, const double* __restrict__ recv /* [world][cap+1][SREC] */,
-                                                      int cap, long long parity_stride, const int* wait_flags) {
+                                                      int cap, long long parity_stride, const int* wait_flags,
+                                                      const ShardFuse* flag_fuse, int n_pack_blocks) {
     const int q = blockIdx.y, r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (flag_fuse && blockIdx.x == 0 && blockIdx.y == 0) {
+        shard_flag_body<256>(p, *flag_fuse, n_pack_blocks);
+        __syncthreads();
+    }
     if (q == c.rank) return;
     if (wait_flags) {                  // p2p: the blocks of sender q wait for q's flag of this step themselves (no separate launch).
         if (threadIdx.x == 0) {        // A peer that never arrives must not hang the GPU: after ~30 s give up, overflow = 2.
@@ -1382,11 +1388,13 @@ __global__ void __launch_bounds__(256) k_shard_unpack(Params p, ShardCtl c, cons
                                        // instantiation, lazily enabled peer mappings -- and a wait that gives up early
                                        // installs a stale half of the inbox.)
             const int t = *p.t;
-            volatile const int* flag = wait_flags + (t & 1) * c.world + q;
             const long long t0 = clock64();
-            while (*flag != t + 1) {
-                __nanosleep(100);
-                if (clock64() - t0 > 60000000000ll) { *p.overflow = 2; break; }
+            for (int w = 0; w < 2; ++w) {
+                volatile const int* flag = wait_flags + (t & 1) * c.world + (w == 0 ? q : c.rank);
+                while (*flag != t + 1) {
+                    __nanosleep(100);
+                    if (clock64() - t0 > 60000000000ll) { *p.overflow = 2; break; }
+                }
             }
             __threadfence_system();
         }

@@ -21,7 +21,7 @@ ABI_SYMBOLS = [
     "fgnn_shard_configure", "fgnn_shard_local_step", "fgnn_shard_pack", "fgnn_shard_unpack", "fgnn_shard_step_begin",
     "fgnn_shard_step_end", "fgnn_shard_owned", "fgnn_profile_step", "fgnn_memcpy_sync", "fgnn_launch_count",
     "fgnn_set_agent_mask", "fgnn_set_dt", "fgnn_comm_unique_id", "fgnn_comm_init", "fgnn_shard_step",
-    "fgnn_p2p_alloc", "fgnn_p2p_connect", "fgnn_p2p_seed", "fgnn_shard_step_p2p",
+    "fgnn_p2p_alloc", "fgnn_p2p_connect", "fgnn_p2p_seed", "fgnn_shard_step_p2p", "fgnn_shard_exchange_p2p",
     "fgnn_trainer_create", "fgnn_trainer_destroy", "fgnn_trainer_param_count", "fgnn_trainer_launch_count",
     "fgnn_trainer_step",
 ]
@@ -114,6 +114,7 @@ def load_library(path=None):
     lib.fgnn_p2p_connect.argtypes = [vp, vp, vp]
     lib.fgnn_p2p_seed.argtypes = [vp, vp, vp]
     lib.fgnn_shard_step_p2p.argtypes = [vp, vp]
+    lib.fgnn_shard_exchange_p2p.argtypes = [vp, i32, vp]
     lib.fgnn_set_agent_mask.argtypes = [vp, vp, vp]
     lib.fgnn_set_dt.argtypes = [vp, dbl]
     lib.fgnn_trainer_create.argtypes = [i32, i32, i32, i32, ctypes.POINTER(vp)]
@@ -483,6 +484,9 @@ class FlockEngine:
     def shard_step_p2p(self):
         self._check(self.lib.fgnn_shard_step_p2p(self._h, self.stream))
         self.step_index += 1
+
+    def shard_exchange_p2p(self, advance=True):
+        self._check(self.lib.fgnn_shard_exchange_p2p(self._h, int(bool(advance)), self.stream))
 
     def shard_owned(self):
         """Currently owned agents (global ids, int32, list order) -- synchronises."""

@@ -132,6 +132,9 @@ class CudaShardBackend:
     def step_p2p(self):
         self.engine.shard_step_p2p()
 
+    def exchange_p2p(self, advance):
+        self.engine.shard_exchange_p2p(advance)
+
     def owned(self):
         return self.engine.shard_owned()
 
@@ -234,7 +237,10 @@ class ShardedFlock:
         select_action -> host array -> env.step(host array).  ``action_host``: (list capacity, 2) fp32, pinned."""
         self.backend.policy(action_host)          # D2H (synchronises)
         self.backend.integrate(action_host)       # H2D
-        self._exchange(self.recv, (self.cap + 1) * RECORD, advance=True)
+        if getattr(self.backend, "p2p", False):   # halo records stored straight into the peers' inboxes: no collective
+            self.backend.exchange_p2p(True)
+        else:
+            self._exchange(self.recv, (self.cap + 1) * RECORD, advance=True)
         self.backend.build(True)
 
 

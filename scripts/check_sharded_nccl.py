@@ -1,6 +1,6 @@
 """torchrun check of the multi-GPU halo paths on REAL ranks (run on >= 2 GPUs; tests/test_gpu_sharding_ranks.py spawns it):
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
-        scripts/check_sharded_nccl.py [p2p|gather|native]
+        scripts/check_sharded_nccl.py [p2p|p2p_host|gather|native]
 Every rank shards one flock by index, rolls out T steps, and rank 0 compares the owned slices of all ranks with a single
 unsharded engine, bit for bit.  Transports: p2p (default: records stored straight into the peers' inboxes over NVLink, one
 CUDA graph per step), gather (torch.distributed all-gather between two graph halves), native (ncclAllGather inside the graph)."""
@@ -39,10 +39,17 @@ def main():
     flock.reset(x0, ranges)
     if mode == "native":
         be.init_comm(rank, world)              # one CUDA graph per step with ncclAllGather inside
-    elif mode == "p2p":
+    elif mode in ("p2p", "p2p_host"):
         flock.enable_p2p(parallel.torch_all_gather_object(world))
-    for _ in range(steps):
-        flock.step()
+    if mode == "p2p_host":
+        # the reference-facing loop on every rank: select_action -> pinned host array -> env.step(host array), halo over p2p
+        # (bit-identical to the closed loop: the API-split path leaves the same bits as the fused step)
+        act_host = torch.empty((be.engine.rows_io, 2), dtype=torch.float32, pin_memory=True).numpy()
+        for _ in range(steps):
+            flock.step_host(act_host)
+    else:
+        for _ in range(steps):
+            flock.step()
     torch.cuda.synchronize()
     if os.environ.get("FGNN_CHECK_PROFILE") == "1" and mode == "p2p":
         # the p2p step kernel by kernel (CUDA events, un-graphed) on every rank, then the graph-replayed step time

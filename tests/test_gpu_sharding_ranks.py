@@ -18,11 +18,11 @@ def _device_count():
 
 
 @pytest.mark.parametrize("world", [2, 4, 8])
-@pytest.mark.parametrize("mode", ["p2p", "gather"])
+@pytest.mark.parametrize("mode", ["p2p", "p2p_host", "gather"])
 def test_real_ranks_reproduce_single_engine(world, mode):
     if _device_count() < world:
         pytest.skip(f"needs {world} GPUs")
-    port = 29600 + world + (10 if mode == "p2p" else 0)
+    port = 29600 + world + {"p2p": 10, "p2p_host": 20, "gather": 0}[mode]
     env = dict(os.environ, FGNN_CHECK_N="120000", FGNN_CHECK_STEPS="40")
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
                           "--master-addr", "127.0.0.1", "--master-port", str(port),
