@@ -44,6 +44,9 @@ def _units():
             units.append((os.path.join(OBJ, f"fgnn_final_k{k}_hp{hp}.o"), os.path.join(CSRC, "fgnn_final.cu"),
                           [f"-DFGNN_K={k}", f"-DFGNN_HP={hp}"],
                           common_deps + [os.path.join(CSRC, "fgnn_final.cuh"), os.path.join(CSRC, "fgnn_final_tc.cuh")]))
+            units.append((os.path.join(OBJ, f"fgnn_mini_k{k}_hp{hp}.o"), os.path.join(CSRC, "fgnn_mini.cu"),
+                          [f"-DFGNN_K={k}", f"-DFGNN_HP={hp}"],
+                          common_deps + [os.path.join(CSRC, "fgnn_final.cuh"), os.path.join(CSRC, "fgnn_final_tc.cuh")]))
     return units
 
 

@@ -110,6 +110,10 @@ struct fgnn_handle {
     int policy_chunks = 1;           // fgnn_policy to a host buffer: readout chunks overlapped with their D2H copies
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t chunk_event[FGNN_MAX_CHUNKS + 1] = {};
+    // small flocks (B*N <= 128): the whole closed-loop step in one CTA, T steps per launch (fgnn_mini.cu)
+    void (*mini_kernel)(Params, const uint8_t*, int, int, int) = nullptr;
+    size_t mini_smem = 0;
+    int mini_adj_off = 0;
     // tensor-core readout (tcgen05, 3xTF32)
     bool use_tc = false;
     std::vector<uint8_t> tc_host;    // TcLayout pack, host mirror
@@ -190,13 +194,14 @@ typedef void (*dense_kernel_t)(const float*, const float*, float*, const float*,
 
 namespace fgnn {
 typedef void (*final_tc_kernel_t)(Params, const uint8_t*);
+typedef void (*mini_rollout_kernel_t)(Params, const uint8_t*, int, int, int);
 #define FGNN_DECL(K, HP) final_kernel_t get_final_k##K##_hp##HP(bool closed); dense_kernel_t get_dense_k##K##_hp##HP(); \
-    final_tc_kernel_t get_final_tc_k##K##_hp##HP(bool closed);
+    final_tc_kernel_t get_final_tc_k##K##_hp##HP(bool closed); mini_rollout_kernel_t get_mini_rollout_k##K##_hp##HP();
 #define FGNN_DECL_K(K) FGNN_DECL(K, 16) FGNN_DECL(K, 32) FGNN_DECL(K, 64) FGNN_DECL(K, 128)
 FGNN_DECL_K(1) FGNN_DECL_K(2) FGNN_DECL_K(3) FGNN_DECL_K(4)
 }
 
-#define FGNN_CASE_HP(K, HP) case HP: return closed_or_dense == 2 ? (void*)get_dense_k##K##_hp##HP() \
+#define FGNN_CASE_HP(K, HP) case HP: return closed_or_dense == 5 ? (void*)get_mini_rollout_k##K##_hp##HP() : closed_or_dense == 2 ? (void*)get_dense_k##K##_hp##HP() \
     : closed_or_dense >= 3 ? (void*)get_final_tc_k##K##_hp##HP(closed_or_dense == 4) : (void*)get_final_k##K##_hp##HP(closed_or_dense == 1);
 #define FGNN_CASE_K(K) case K: switch (HP) { FGNN_CASE_HP(K, 16) FGNN_CASE_HP(K, 32) FGNN_CASE_HP(K, 64) default: FGNN_CASE_HP(K, 128) } break;
 static void* kernel_lookup(int K, int HP, int closed_or_dense) {
@@ -206,6 +211,7 @@ static void* kernel_lookup(int K, int HP, int closed_or_dense) {
 static final_kernel_t final_kernel(int K, int HP, bool closed) { return (final_kernel_t)kernel_lookup(K, HP, closed ? 1 : 0); }
 static dense_kernel_t dense_kernel(int K, int HP) { return (dense_kernel_t)kernel_lookup(K, HP, 2); }
 static final_tc_kernel_t final_tc_kernel(int K, int HP, bool closed) { return (final_tc_kernel_t)kernel_lookup(K, HP, closed ? 4 : 3); }
+static mini_rollout_kernel_t mini_rollout_kernel(int K, int HP) { return HP <= 64 ? (mini_rollout_kernel_t)kernel_lookup(K, HP, 5) : nullptr; }
 static size_t final_smem_bytes(const fgnn_handle* h) {
     WeightLayout wl{F * h->cfg.k, h->HP, h->cfg.n_layers};
     if (h->HP > 64) return (size_t)2 * h->HP * FINAL_THREADS * sizeof(float);
@@ -473,6 +479,15 @@ extern "C" int fgnn_create(const fgnn_config* cfg, fgnn_handle** out) {
             if (grid > tiles) grid = tiles;
             (closed ? h->tc_grid_closed : h->tc_grid_open) = grid;
             if (getenv("FGNN_DEBUG")) fprintf(stderr, "[fgnn] final_tc closed=%d regs=%d smem=%zu occ=%d grid=%d tiles=%d sharded=%d\n", closed, fa.numRegs, h->tc_smem, occ, grid, tiles, (int)h->sharded);
+        }
+    }
+    {   // single-CTA path for small flocks (FGNN_MINI=0: the general kernels)
+        const char* mn = getenv("FGNN_MINI");
+        if ((!mn || atoi(mn) != 0) && !h->sharded && p.M <= 128 && h->use_tc) {
+            h->mini_kernel = mini_rollout_kernel(p.K, h->HP);
+            h->mini_adj_off = (int)((h->tc_smem + 127) & ~(size_t)127);
+            h->mini_smem = (size_t)h->mini_adj_off + (size_t)h->adj_stage * ADJ_THREADS * sizeof(int);
+            if (h->mini_kernel) CK(cudaFuncSetAttribute((const void*)h->mini_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->mini_smem));
         }
     }
     *out = h;
@@ -872,7 +887,11 @@ extern "C" int fgnn_step(fgnn_handle* h, float* action, double* reward_b, void* 
     CK(cudaSetDevice(h->cfg.device));
     if (h->sharded) return fail("fgnn_step: sharded handle -- use fgnn_shard_local_step / pack / unpack / build_graph");
     if (h->binned) return fail("fgnn_step: state was integrated but the graph not rebuilt (call fgnn_build_graph)");
-    if (enqueue_closed_step(h, st)) return 1;
+    if (h->mini_kernel && !h->profiling) {
+        h->mini_kernel<<<1, FINAL_THREADS, h->mini_smem, st>>>(h->p, (const uint8_t*)h->d_tc_weights, 1, h->adj_stage, h->mini_adj_off);
+        if (launch_check(h, "mini_step")) return 1;
+        h->t_host += 1;
+    } else if (enqueue_closed_step(h, st)) return 1;
     if (copy_out(action, h->p.action, (size_t)h->p.M * 2 * sizeof(float), st)) return 1;
     return copy_out(reward_b, h->p.reward, (size_t)h->p.B * sizeof(double), st);
 }
@@ -894,6 +913,17 @@ extern "C" int fgnn_rollout(fgnn_handle* h, int32_t T, double* reward_bt, void* 
         h->reward_log_cap = cap;
         if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
         if (h->graph) { cudaGraphDestroy(h->graph); h->graph = nullptr; }
+    }
+    if (h->mini_kernel) {           // small flock: T steps inside one CTA, one launch
+        Params pp = p;
+        pp.reward_log = h->d_reward_log;
+        CK(cudaMemsetAsync(p.log_index, 0, sizeof(int), st));
+        h->mini_kernel<<<1, FINAL_THREADS, h->mini_smem, st>>>(pp, (const uint8_t*)h->d_tc_weights, T, h->adj_stage, h->mini_adj_off);
+        if (launch_check(h, "mini_rollout")) return 1;
+        h->t_host += T;
+        h->binned = false;
+        if (want_log) return copy_out(reward_bt, h->d_reward_log, (size_t)T * p.B * sizeof(double), st);
+        return 0;
     }
     if (!h->graph_exec) {
         // capture one closed-loop step; the device step counter makes the same graph valid for every t

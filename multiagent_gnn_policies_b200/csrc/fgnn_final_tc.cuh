@@ -148,42 +148,70 @@ __device__ __forceinline__ float2 tanh2(float2 h, float2 b) {
 
 __host__ __device__ constexpr int tc_tmem_cols(int HP) { return 2 * HP < 32 ? 32 : 2 * HP; }
 
-template <int K, int HP, bool CLOSED>
-__global__ void __launch_bounds__(FINAL_THREADS, 4) k_final_tc(Params p, const uint8_t* __restrict__ tcw) {
-    pdl_prologue();
+struct TcCtx {                 // per-CTA state of the tensor-core readout between its setup / tile / teardown parts
+    uint8_t* s_w;              // weight pack (canonical layout) in shared memory
+    uint8_t* s_ahi;            // A operand tiles (tf32 hi / lo)
+    uint8_t* s_alo;
+    uint32_t mbar;             // mbarrier (shared address) the MMAs commit to
+    uint32_t tmem_base;        // TMEM allocation
+    uint32_t phase;            // mbarrier phase
+};
+
+// weights -> smem (already in canonical layout), barrier init, TMEM allocation.  Every thread of the CTA.
+template <int K, int HP>
+__device__ __forceinline__ void final_tc_setup(const Params& p, const uint8_t* __restrict__ tcw, uint8_t* smem_raw, TcCtx& c) {
     static_assert(HP == 16 || HP == 32 || HP == 64, "tensor-core readout supports HP in {16,32,64}");
     constexpr int K0 = (F * K + 7) & ~7;
     constexpr int KA = K0 > HP ? K0 : HP;                  // widest A operand
     constexpr int TM_COLS = tc_tmem_cols(HP);
-    constexpr uint32_t IDESC = tc::make_idesc(128, HP);
-    extern __shared__ __align__(128) uint8_t smem_raw[];
     TcLayout tl;
     tl.K0 = K0; tl.HP = HP; tl.L = p.L;
     // smem: [weight pack][A_hi 128xKA][A_lo 128xKA][mbarrier][tmem slot]
-    uint8_t* s_w = smem_raw;
-    uint8_t* s_ahi = smem_raw + tl.total_bytes();
-    uint8_t* s_alo = s_ahi + 128 * KA * 4;
-    uint64_t* s_mbar = reinterpret_cast<uint64_t*>(s_alo + 128 * KA * 4);
+    c.s_w = smem_raw;
+    c.s_ahi = smem_raw + tl.total_bytes();
+    c.s_alo = c.s_ahi + 128 * KA * 4;
+    uint64_t* s_mbar = reinterpret_cast<uint64_t*>(c.s_alo + 128 * KA * 4);
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_mbar + 1);
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
+    const int n16 = tl.total_bytes() / 16;
+    const uint4* g = reinterpret_cast<const uint4*>(tcw);
+    uint4* sw = reinterpret_cast<uint4*>(c.s_w);
+    for (int i = tid; i < n16; i += FINAL_THREADS) sw[i] = __ldg(g + i);
+    if (tid == 0) tc::mbar_init(tc::smem_u32(s_mbar), 1);
+    if (warp == 0) tc::tmem_alloc<TM_COLS>(tc::smem_u32(s_tmem));
+    tc::fence_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    c.tmem_base = *s_tmem;
+    c.mbar = tc::smem_u32(s_mbar);
+    c.phase = 0;
+}
 
-    {   // weights -> smem (already in canonical layout), barrier init, TMEM allocation
-        const int n16 = tl.total_bytes() / 16;
-        const uint4* g = reinterpret_cast<const uint4*>(tcw);
-        uint4* s = reinterpret_cast<uint4*>(s_w);
-        for (int i = tid; i < n16; i += FINAL_THREADS) s[i] = __ldg(g + i);
-        if (tid == 0) tc::mbar_init(tc::smem_u32(s_mbar), 1);
-        if (warp == 0) tc::tmem_alloc<TM_COLS>(tc::smem_u32(s_tmem));
-        tc::fence_async_smem();
-        tc::fence_before_sync();
-        __syncthreads();
-        tc::fence_after_sync();
-    }
-    const uint32_t tmem_base = *s_tmem;
+template <int HP>
+__device__ __forceinline__ void final_tc_teardown(const TcCtx& c) {
+    tc::fence_before_sync();
+    __syncthreads();
+    if ((threadIdx.x >> 5) == 0) tc::tmem_dealloc<tc_tmem_cols(HP)>(c.tmem_base);
+}
+
+// the CTA's tiles of one launch (persistent loop), then the per-block reward / interval partials
+template <int K, int HP, bool CLOSED>
+__device__ __forceinline__ void final_tc_tiles(const Params& p, TcCtx& c) {
+    constexpr int K0 = (F * K + 7) & ~7;
+    constexpr uint32_t IDESC = tc::make_idesc(128, HP);
+    TcLayout tl;
+    tl.K0 = K0; tl.HP = HP; tl.L = p.L;
+    uint8_t* const s_w = c.s_w;
+    uint8_t* const s_ahi = c.s_ahi;
+    uint8_t* const s_alo = c.s_alo;
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const uint32_t tmem_base = c.tmem_base;
     const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16);      // this warp's lane quadrant
-    const uint32_t mbar = tc::smem_u32(s_mbar);
-    uint32_t phase = 0;
+    const uint32_t mbar = c.mbar;
+    uint32_t phase = c.phase;
     const float* s_f32 = reinterpret_cast<const float*>(s_w);
 
     const int t = *p.t;
@@ -346,9 +374,17 @@ __global__ void __launch_bounds__(FINAL_THREADS, 4) k_final_tc(Params p, const u
     }
     if (CLOSED) reward_block_flush<FINAL_THREADS>(p, racc);
     if (CLOSED && p.fuse) shard_interval_flush<FINAL_THREADS>(p.fuse->ctl, klo, khi);
-    tc::fence_before_sync();
-    __syncthreads();
-    if (warp == 0) tc::tmem_dealloc<TM_COLS>(tmem_base);
+    c.phase = phase;
+}
+
+template <int K, int HP, bool CLOSED>
+__global__ void __launch_bounds__(FINAL_THREADS, 4) k_final_tc(Params p, const uint8_t* __restrict__ tcw) {
+    pdl_prologue();
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    TcCtx c;
+    final_tc_setup<K, HP>(p, tcw, smem_raw, c);
+    final_tc_tiles<K, HP, CLOSED>(p, c);
+    final_tc_teardown<HP>(c);
 }
 #endif  // __CUDACC__
 

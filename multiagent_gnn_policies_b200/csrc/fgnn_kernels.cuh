@@ -7,6 +7,17 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// FGNN_COHERENT_LOADS (the single-CTA small-flock kernels, fgnn_mini.cu): every stage of a step runs inside ONE kernel, so
+// data written by an earlier stage of the SAME kernel is read back -- the non-coherent path (ld.global.nc / __ldg) is only
+// valid for data written by an earlier kernel.  With the switch every read-only load of the shared device code becomes a
+// plain load (coherent within the SM, and the whole kernel is one CTA).
+#ifdef FGNN_COHERENT_LOADS
+#define __ldg(ptr) (*(ptr))
+#define FGNN_NC ""
+#else
+#define FGNN_NC ".nc"
+#endif
+
 namespace fgnn {
 
 constexpr int F = 6;          // features per agent (n_states)
@@ -186,18 +197,18 @@ __device__ __forceinline__ double r2_exact(double dx, double dy) {
 // record instead of a 128-bit + 64-bit (or two 128-bit) pair halves the wavefronts of every scattered record read.
 // `.nc` variants: data written by an EARLIER kernel only.
 __device__ __forceinline__ void ldg256_nc(const float* p, float (&v)[8]) {
-    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+    asm volatile("ld.global" FGNN_NC ".v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
                  : "l"(p));
 }
 __device__ __forceinline__ void ldg256_nc(const int* p, int (&v)[8]) {
-    asm volatile("ld.global.nc.v8.s32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+    asm volatile("ld.global" FGNN_NC ".v8.s32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                  : "l"(p));
 }
 __device__ __forceinline__ double4 ldg256_nc(const double4* p) {
     double4 v;
-    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+    asm volatile("ld.global" FGNN_NC ".v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
     return v;
 }
 __device__ __forceinline__ double4 ldg256(const double4* p) {            // coherent: the kernel also writes this array
@@ -228,6 +239,7 @@ __device__ __forceinline__ void store_row6(float* base, int idx, const float (&v
     stg256(base + (size_t)idx * ROW, v[0], v[1], v[2], v[3], v[4], v[5], 0.f, 0.f);
 }
 
+#if defined(FGNN_MAIN_TU) || defined(FGNN_MINI_TU)
 #ifdef FGNN_MAIN_TU
 // ------------------------------------------------------------------------------------------
 // K_A  bin: cell of every agent + per-cell population count
@@ -244,6 +256,8 @@ __global__ void __launch_bounds__(256) k_bin(Params p) {      // owned agents (g
     p.cell_of[a] = c;
     bin_agent(p, c);
 }
+
+#endif  // FGNN_MAIN_TU (k_bin)
 
 // reward_b = -(var(vx) + var(vy)) per episode from the accumulated sums; clears the sums.
 // B == 1: per-block partials summed in a fixed order (bit-reproducible); B > 1: RSLOTS atomic slots per episode.
@@ -296,6 +310,7 @@ static __device__ __forceinline__ void finalize_reward(const Params& p) {
     }
 }
 
+#ifdef FGNN_MAIN_TU
 __global__ void __launch_bounds__(256) k_finalize_reward(Params p) { finalize_reward(p); }
 
 // ------------------------------------------------------------------------------------------
@@ -473,6 +488,8 @@ __global__ void __launch_bounds__(256) k_canon(Params p) {
     stg256(&p.sorted_state[dst], ldg256_nc(&p.state[a]));
 }
 
+#endif  // FGNN_MAIN_TU (scan / scatter / canon kernels)
+
 // ------------------------------------------------------------------------------------------
 // K_D  adjacency + degree + 6-d relative features (gym_flock compute_helpers), CSR/ELL emission.
 //      One thread per agent, in cell-sorted order; float64 arithmetic for the radius cut and the
@@ -519,9 +536,7 @@ __device__ __forceinline__ double fast_rcp(double x) {
 // long_scoreboard 36 %, L1 wavefronts 38 % of peak) become shared-memory reads.  Warps that straddle a row, touch
 // the grid seam or overflow the tile take the per-lane global path.  Neighbour order is identical in both paths.
 template <bool WS>
-__global__ void __launch_bounds__(ADJ_THREADS, WS ? 8 : 1) k_adjacency_t(Params p, int stage_cap) {
-    pdl_prologue();
-    extern __shared__ __align__(16) unsigned char s_adj_raw[];
+__device__ __forceinline__ void adjacency_body(const Params& p, int stage_cap, unsigned char* s_adj_raw) {
     int* s_stage = reinterpret_cast<int*>(s_adj_raw);     // [stage_cap][ADJ_THREADS] accepted neighbour ids
     const int tid = threadIdx.x;
     const int s = blockIdx.x * ADJ_THREADS + tid;
@@ -755,7 +770,16 @@ __global__ void __launch_bounds__(ADJ_THREADS, WS ? 8 : 1) k_adjacency_t(Params 
 }
 #undef FGNN_ADJ_ACCEPT
 
-#endif  // FGNN_MAIN_TU
+#ifdef FGNN_MAIN_TU
+template <bool WS>
+__global__ void __launch_bounds__(ADJ_THREADS, WS ? 8 : 1) k_adjacency_t(Params p, int stage_cap) {
+    pdl_prologue();
+    extern __shared__ __align__(16) unsigned char s_adj_raw[];
+    adjacency_body<WS>(p, stage_cap, s_adj_raw);
+}
+#endif
+
+#endif  // FGNN_MAIN_TU || FGNN_MINI_TU
 
 // ------------------------------------------------------------------------------------------
 // Neighbour gather shared by the hop kernels and the fused final kernel:
@@ -843,14 +867,9 @@ __device__ __forceinline__ void gather_rows(const Params& p, int g, int a, const
 struct ShardFuse;
 __device__ void shard_prepare_block(const Params& p);      // (defined with the k_shard_* kernels below)
 
+// one thread = pool agent i
 template <int NB, bool FIRST>
-__global__ void __launch_bounds__(256, NB == 2 ? FGNN_HOP_MIN_BLOCKS : 1) k_hop(Params p, int j, int prepare) {
-    pdl_prologue();
-    // p2p step of a sharded rank: block 0 of the last hop launch also zeroes the per-step counters, advances the frame and
-    // works out the interior interval for the pack that follows (the hops walk the ghost-count SNAPSHOT, so the counter may be
-    // reset under them): the one-block k_shard_prepare launch leaves the step's critical path
-    if (prepare && blockIdx.x == 0) shard_prepare_block(p);
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void hop_body(const Params& p, int j, int i) {
     if (i >= hop_pool_size(p)) return;
     const int a = pool_agent(p, i);
     if (a < 0) return;
@@ -878,6 +897,16 @@ __global__ void __launch_bounds__(256, NB == 2 ? FGNN_HOP_MIN_BLOCKS : 1) k_hop(
             store_row6(dst[b], a, acc[b]);
         }
     }
+}
+
+template <int NB, bool FIRST>
+__global__ void __launch_bounds__(256, NB == 2 ? FGNN_HOP_MIN_BLOCKS : 1) k_hop(Params p, int j, int prepare) {
+    pdl_prologue();
+    // p2p step of a sharded rank: block 0 of the last hop launch also zeroes the per-step counters, advances the frame and
+    // works out the interior interval for the pack that follows (the hops walk the ghost-count SNAPSHOT, so the counter may be
+    // reset under them): the one-block k_shard_prepare launch leaves the step's critical path
+    if (prepare && blockIdx.x == 0) shard_prepare_block(p);
+    hop_body<NB, FIRST>(p, j, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
 // ---- multi-GPU halo / hand-over control block (see the k_shard_* kernels at the end of this file) ----

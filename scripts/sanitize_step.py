@@ -1,5 +1,5 @@
 """Workload for compute-sanitizer (memcheck / racecheck / synccheck): a 10k-agent flock through every kernel of the step --
-the separate kernels (FGNN_STEP_MODE=0), the tile-fused kernel (FGNN_STEP_MODE=1), graph replay, the API-split path with
+k_adjacency_t (FGNN_STEP_MODE=0), the warp-tiled k_pair_adjacency with its TMA staging (FGNN_STEP_MODE=1), graph replay, the API-split path with
 float32 and float64 actions, the expert controller, and two in-process ranks over the p2p halo transport.
     compute-sanitizer --tool memcheck python scripts/sanitize_step.py"""
 import os
