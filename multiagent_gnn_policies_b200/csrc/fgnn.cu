@@ -393,6 +393,7 @@ extern "C" int fgnn_create(const fgnn_config* cfg, fgnn_handle** out) {
     rc |= dalloc(h, &p.reward, (size_t)p.B);
     rc |= dalloc(h, &p.reward_pending, 1);
     rc |= dalloc(h, &p.log_index, 1);
+    if (getenv("FGNN_MINI_CLOCK")) rc |= dalloc(h, &p.mini_clock, 4);
     if (h->sharded) {
         rc |= dalloc(h, &h->d_own, (size_t)p.pool_cap);
         rc |= dalloc(h, &h->d_ghost, (size_t)p.pool_cap);
@@ -483,7 +484,7 @@ extern "C" int fgnn_create(const fgnn_config* cfg, fgnn_handle** out) {
     }
     {   // single-CTA path for small flocks (FGNN_MINI=0: the general kernels)
         const char* mn = getenv("FGNN_MINI");
-        if ((!mn || atoi(mn) != 0) && !h->sharded && p.M <= 128 && h->use_tc) {
+        if ((!mn || atoi(mn) != 0) && !h->sharded && p.M <= 128 && p.C <= MINI_MAX_CELLS && h->use_tc) {
             h->mini_kernel = mini_rollout_kernel(p.K, h->HP);
             h->mini_adj_off = (int)((h->tc_smem + 127) & ~(size_t)127);
             h->mini_smem = (size_t)h->mini_adj_off + (size_t)h->adj_stage * ADJ_THREADS * sizeof(int);
@@ -1098,6 +1099,13 @@ extern "C" int fgnn_get_stats(fgnn_handle* h, fgnn_stats* out, void* stream) {
     out->n_cells = h->p.C;
     out->edge_capacity = h->p.nnz_cap;
     out->n_ghosts = 0;
+    if (h->p.mini_clock && getenv("FGNN_MINI_CLOCK")) {       // debugging aid: cycles per stage of the single-CTA kernel so far
+        long long ck[4];
+        CK(cudaMemcpyAsync(ck, h->p.mini_clock, sizeof ck, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        fprintf(stderr, "[fgnn] mini kernel cycles: hops %lld  readout+integrator %lld  sort %lld  adjacency %lld (over %d steps)\n", ck[0], ck[1],
+                ck[2], ck[3], t);
+    }
     if (h->sharded) {
         int ng = 0;
         CK(cudaMemcpyAsync(&ng, h->d_counts + 2, sizeof(int), cudaMemcpyDeviceToHost, st));

@@ -11,11 +11,10 @@
 // data written by an earlier stage of the SAME kernel is read back -- the non-coherent path (ld.global.nc / __ldg) is only
 // valid for data written by an earlier kernel.  With the switch every read-only load of the shared device code becomes a
 // plain load (coherent within the SM, and the whole kernel is one CTA).
+// The 256-bit record accesses become generic there too: the single-CTA kernel keeps the cell-sorted arrays of its flock in
+// SHARED memory and hands the shared device code pointers to them.
 #ifdef FGNN_COHERENT_LOADS
 #define __ldg(ptr) (*(ptr))
-#define FGNN_NC ""
-#else
-#define FGNN_NC ".nc"
 #endif
 
 namespace fgnn {
@@ -29,6 +28,7 @@ constexpr int FINAL_THREADS = 128;   // block size of the fused final kernel and
 constexpr int DENSE_MT = 32;         // m-tile of the dense Actor kernel
 constexpr int RSLOTS = 64;          // reward accumulators per episode (spreads same-address atomics)
 constexpr int ELLW = 8;             // neighbours kept inline per agent: one dependent load less per gather
+constexpr int MINI_MAX_CELLS = 1280;        // single-CTA path (fgnn_mini.cu): cells of the flock's grid it keeps in shared memory
 #ifndef FGNN_HOP_UNROLL
 #define FGNN_HOP_UNROLL 2
 #endif
@@ -106,6 +106,7 @@ struct Params {
     int* reward_pending;
     double* reward_log;       // [T][B] or null
     int* log_index;
+    long long* mini_clock;    // [4] or null: cycles the single-CTA kernel spent in hops / readout + integrator / cell sort / adjacency
 };
 
 // Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-serialization attribute may become
@@ -196,19 +197,20 @@ __device__ __forceinline__ double r2_exact(double dx, double dy) {
 // bound by the L1TEX wavefront pipe, which charges per instruction AND per line touched: one 256-bit access per
 // record instead of a 128-bit + 64-bit (or two 128-bit) pair halves the wavefronts of every scattered record read.
 // `.nc` variants: data written by an EARLIER kernel only.
+#ifndef FGNN_COHERENT_LOADS
 __device__ __forceinline__ void ldg256_nc(const float* p, float (&v)[8]) {
-    asm volatile("ld.global" FGNN_NC ".v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
                  : "l"(p));
 }
 __device__ __forceinline__ void ldg256_nc(const int* p, int (&v)[8]) {
-    asm volatile("ld.global" FGNN_NC ".v8.s32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+    asm volatile("ld.global.nc.v8.s32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                  : "l"(p));
 }
 __device__ __forceinline__ double4 ldg256_nc(const double4* p) {
     double4 v;
-    asm volatile("ld.global" FGNN_NC ".v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
     return v;
 }
 __device__ __forceinline__ double4 ldg256(const double4* p) {            // coherent: the kernel also writes this array
@@ -227,6 +229,35 @@ __device__ __forceinline__ void stg256(int* p, const int (&v)[8]) {
     asm volatile("st.global.v8.s32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
                  :: "l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
 }
+#else
+// single-CTA kernels: generic, coherent accesses (the pointer may be into shared memory, where 256-bit accesses do not
+// exist): two 128-bit halves
+__device__ __forceinline__ void ldg256_nc(const float* p, float (&v)[8]) {
+    const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void ldg256_nc(const int* p, int (&v)[8]) {
+    const int4 a = reinterpret_cast<const int4*>(p)[0], b = reinterpret_cast<const int4*>(p)[1];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ double4 ldg256_nc(const double4* p) {
+    const double2 a = reinterpret_cast<const double2*>(p)[0], b = reinterpret_cast<const double2*>(p)[1];
+    return make_double4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ double4 ldg256(const double4* p) { return ldg256_nc(p); }
+__device__ __forceinline__ void stg256(double4* p, const double4 v) {
+    reinterpret_cast<double2*>(p)[0] = make_double2(v.x, v.y);
+    reinterpret_cast<double2*>(p)[1] = make_double2(v.z, v.w);
+}
+__device__ __forceinline__ void stg256(float* p, float a, float b, float c, float d, float e, float f, float g, float h) {
+    reinterpret_cast<float4*>(p)[0] = make_float4(a, b, c, d);
+    reinterpret_cast<float4*>(p)[1] = make_float4(e, f, g, h);
+}
+__device__ __forceinline__ void stg256(int* p, const int (&v)[8]) {
+    reinterpret_cast<int4*>(p)[0] = make_int4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<int4*>(p)[1] = make_int4(v[4], v[5], v[6], v[7]);
+}
+#endif
 
 __device__ __forceinline__ void load_row6(const float* __restrict__ base, int idx, float (&v)[F]) {
     float r[8];

@@ -20,6 +20,7 @@ namespace fgnn {
 #if FGNN_HP <= 64
 constexpr int MINI_THREADS = 128;
 static_assert(MINI_THREADS == FINAL_THREADS && MINI_THREADS == ADJ_THREADS, "one readout tile = one adjacency block");
+static_assert(MINI_MAX_CELLS >= 9 * 128, "any episode split of <= 128 agents on the smallest (3 x 3) grids");
 
 // bin -> scan -> scatter -> canon of the general path for M <= 128 agents (cell_of / cell_count come from the integrator's
 // binning): canonical slot = rank of (cell, id); also what the small kernels of the general path do on the side (k_scan:
@@ -44,7 +45,7 @@ static __device__ __forceinline__ void mini_sort(const Params& p, int advance, i
         }
         p.sorted_id[rank] = tid;
         p.sorted_cell[rank] = c;
-        stg256(&p.sorted_state[rank], ldg256(&p.state[tid]));
+        p.sorted_state[rank] = p.state[tid];
     }
     for (int cc = tid; cc <= p.C; cc += MINI_THREADS) {
         int n = 0;
@@ -78,6 +79,15 @@ __global__ void __launch_bounds__(MINI_THREADS, 1) k_mini_rollout(Params p, cons
                                                                   int adj_smem_offset) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ int s_cell[MINI_THREADS];
+    // the flock's cell-sorted arrays live in shared memory for the whole launch (the adjacency stage scans ~14 candidates per
+    // agent one dependent load after the other: 6 us of L2 round trips per step from global memory); written back at the end
+    __shared__ __align__(32) double4 s_sorted_state[MINI_THREADS];
+    __shared__ int s_sorted_id[MINI_THREADS], s_sorted_cell[MINI_THREADS], s_cell_of[MINI_THREADS];
+    __shared__ int s_cell_start[MINI_MAX_CELLS + 1], s_cell_count[MINI_MAX_CELLS + 1];
+    const Params pg = p;               // (global arrays)
+    for (int i = threadIdx.x; i <= pg.C; i += MINI_THREADS) s_cell_count[i] = 0;
+    p.sorted_state = s_sorted_state; p.sorted_id = s_sorted_id; p.sorted_cell = s_sorted_cell; p.cell_of = s_cell_of;
+    p.cell_start = s_cell_start; p.cell_count = s_cell_count;
     TcCtx c;
     final_tc_setup<K, HP>(p, tcw, smem_raw, c);
     unsigned char* s_adj = smem_raw + adj_smem_offset;
@@ -86,14 +96,31 @@ __global__ void __launch_bounds__(MINI_THREADS, 1) k_mini_rollout(Params p, cons
     pf.write_z_last = 0;
     pf.tile_lo = 0; pf.tile_hi = 0;
     pf.fuse = nullptr;
+    long long ck[5] = {0, 0, 0, 0, 0};
+    const bool clk = p.mini_clock != nullptr && threadIdx.x == 0;
     for (int step = 0; step < T; ++step) {
+        if (clk) ck[0] = clock64();
         mini_hops<K>(p);
+        if (clk) ck[1] = clock64();
         final_tc_tiles<K, HP, true>(pf, c);
         __syncthreads();
+        if (clk) ck[2] = clock64();
         mini_sort(p, 1, s_cell);
+        if (clk) ck[3] = clock64();
         adjacency_body<false>(p, stage_cap, s_adj);
         __syncthreads();
+        if (clk) {
+            ck[4] = clock64();
+            for (int q = 0; q < 4; ++q) p.mini_clock[q] += ck[q + 1] - ck[q];
+        }
     }
+    for (int i = threadIdx.x; i < pg.M; i += MINI_THREADS) {
+        pg.sorted_state[i] = s_sorted_state[i];
+        pg.sorted_id[i] = s_sorted_id[i];
+        pg.sorted_cell[i] = s_sorted_cell[i];
+        pg.cell_of[i] = s_cell_of[i];
+    }
+    for (int i = threadIdx.x; i <= pg.C; i += MINI_THREADS) pg.cell_start[i] = s_cell_start[i];
     final_tc_teardown<HP>(c);
 }
 #endif
