@@ -36,7 +36,7 @@ __device__ __forceinline__ unsigned fdiv(const FastDiv d, unsigned n) { return (
 
 constexpr int PR_LIST = 16;                  // neighbours listed per lane (a longer row sends its warp down the per-lane path)
 #ifndef FGNN_PR_MINBLOCKS
-#define FGNN_PR_MINBLOCKS 6
+#define FGNN_PR_MINBLOCKS 8
 #endif
 
 struct PairGeom {
@@ -139,26 +139,30 @@ __device__ __forceinline__ void ranges9(const Params& p, const CellPos& cp, int 
 }
 
 // fp32 radius test of `me` against n <= 32 staged candidates: bit k of `in` = r2 < lo (inside for sure), of `le` = r2 < hi
-// (not outside for sure).  Per candidate: r2 (4 instructions) and two funnel shifts that push the SIGN bits of r2 - lo and
+// (not outside for sure).  Per candidate: r2 (3 instructions, packed) and two funnel shifts that push the SIGN bits of r2 - lo and
 // r2 - hi into the masks (no compare / select / variable shift).
 __device__ __forceinline__ void filter_row(const float2* __restrict__ c, int n, float2 me, float lo, float hi, unsigned& in_,
                                            unsigned& le_) {
     unsigned in = 0, le = 0;
     int k = 0;
+    // packed fp32x2 arithmetic (FFMA2 / FMUL2 / FADD2): the (x, y) pair of a candidate is one operand; the two thresholds of
+    // two candidates are subtracted by one instruction each
+    const float2 neg1 = make_float2(-1.f, -1.f), nlo = make_float2(-lo, -lo), nhi = make_float2(-hi, -hi);
 #pragma unroll 1
     for (; k + 2 <= n; k += 2) {
-        const float2 o0 = c[k], o1 = c[k + 1];
-        const float dx0 = me.x - o0.x, dy0 = me.y - o0.y, dx1 = me.x - o1.x, dy1 = me.y - o1.y;
-        const float r20 = fmaf(dx0, dx0, dy0 * dy0), r21 = fmaf(dx1, dx1, dy1 * dy1);
-        in = __funnelshift_l(__float_as_uint(r20 - lo), in, 1);
-        le = __funnelshift_l(__float_as_uint(r20 - hi), le, 1);
-        in = __funnelshift_l(__float_as_uint(r21 - lo), in, 1);
-        le = __funnelshift_l(__float_as_uint(r21 - hi), le, 1);
+        const float2 d0 = __ffma2_rn(c[k], neg1, me), d1 = __ffma2_rn(c[k + 1], neg1, me);      // me - o, exact
+        const float2 s0 = __fmul2_rn(d0, d0), s1 = __fmul2_rn(d1, d1);
+        const float2 r2 = make_float2(s0.x + s0.y, s1.x + s1.y);
+        const float2 a = __fadd2_rn(r2, nlo), b = __fadd2_rn(r2, nhi);
+        in = __funnelshift_l(__float_as_uint(a.x), in, 1);
+        le = __funnelshift_l(__float_as_uint(b.x), le, 1);
+        in = __funnelshift_l(__float_as_uint(a.y), in, 1);
+        le = __funnelshift_l(__float_as_uint(b.y), le, 1);
     }
     if (k < n) {
-        const float2 o0 = c[k];
-        const float dx0 = me.x - o0.x, dy0 = me.y - o0.y;
-        const float r20 = fmaf(dx0, dx0, dy0 * dy0);
+        const float2 d0 = __ffma2_rn(c[k], neg1, me);
+        const float2 s0 = __fmul2_rn(d0, d0);
+        const float r20 = s0.x + s0.y;
         in = __funnelshift_l(__float_as_uint(r20 - lo), in, 1);
         le = __funnelshift_l(__float_as_uint(r20 - hi), le, 1);
     }
