@@ -11,6 +11,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -112,6 +114,8 @@ struct fgnn_handle {
     cudaEvent_t chunk_event[FGNN_MAX_CHUNKS + 1] = {};
     // small flocks (B*N <= 128): the whole closed-loop step in one CTA, T steps per launch (fgnn_mini.cu)
     void (*mini_kernel)(Params, const uint8_t*, int, int, int) = nullptr;
+    void (*mini_policy)(Params, const uint8_t*) = nullptr;
+    void (*mini_envstep)(Params, const void*, int, int, int) = nullptr;
     size_t mini_smem = 0;
     int mini_adj_off = 0;
     // tensor-core readout (tcgen05, 3xTF32)
@@ -195,13 +199,17 @@ typedef void (*dense_kernel_t)(const float*, const float*, float*, const float*,
 namespace fgnn {
 typedef void (*final_tc_kernel_t)(Params, const uint8_t*);
 typedef void (*mini_rollout_kernel_t)(Params, const uint8_t*, int, int, int);
+typedef void (*mini_policy_kernel_t)(Params, const uint8_t*);
+typedef void (*mini_envstep_kernel_t)(Params, const void*, int, int, int);
 #define FGNN_DECL(K, HP) final_kernel_t get_final_k##K##_hp##HP(bool closed); dense_kernel_t get_dense_k##K##_hp##HP(); \
-    final_tc_kernel_t get_final_tc_k##K##_hp##HP(bool closed); mini_rollout_kernel_t get_mini_rollout_k##K##_hp##HP();
+    final_tc_kernel_t get_final_tc_k##K##_hp##HP(bool closed); mini_rollout_kernel_t get_mini_rollout_k##K##_hp##HP(); \
+    mini_policy_kernel_t get_mini_policy_k##K##_hp##HP(); mini_envstep_kernel_t get_mini_envstep_k##K##_hp##HP();
 #define FGNN_DECL_K(K) FGNN_DECL(K, 16) FGNN_DECL(K, 32) FGNN_DECL(K, 64) FGNN_DECL(K, 128)
 FGNN_DECL_K(1) FGNN_DECL_K(2) FGNN_DECL_K(3) FGNN_DECL_K(4)
 }
 
-#define FGNN_CASE_HP(K, HP) case HP: return closed_or_dense == 5 ? (void*)get_mini_rollout_k##K##_hp##HP() : closed_or_dense == 2 ? (void*)get_dense_k##K##_hp##HP() \
+#define FGNN_CASE_HP(K, HP) case HP: return closed_or_dense == 7 ? (void*)get_mini_envstep_k##K##_hp##HP() : closed_or_dense == 6 ? (void*)get_mini_policy_k##K##_hp##HP() \
+    : closed_or_dense == 5 ? (void*)get_mini_rollout_k##K##_hp##HP() : closed_or_dense == 2 ? (void*)get_dense_k##K##_hp##HP() \
     : closed_or_dense >= 3 ? (void*)get_final_tc_k##K##_hp##HP(closed_or_dense == 4) : (void*)get_final_k##K##_hp##HP(closed_or_dense == 1);
 #define FGNN_CASE_K(K) case K: switch (HP) { FGNN_CASE_HP(K, 16) FGNN_CASE_HP(K, 32) FGNN_CASE_HP(K, 64) default: FGNN_CASE_HP(K, 128) } break;
 static void* kernel_lookup(int K, int HP, int closed_or_dense) {
@@ -219,6 +227,21 @@ static size_t final_smem_bytes(const fgnn_handle* h) {
 }
 
 static inline int blocks_for(int n, int threads) { return (n + threads - 1) / threads; }
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a process-wide property of the FUNCTION: handles with different shapes
+// (layers, stage depth) share the kernels, so the limit is only ever raised.
+static cudaError_t raise_smem_limit(const void* func, size_t bytes) {
+    static std::map<std::pair<int, const void*>, size_t> limit;      // (per device: the attribute lives in the device's context)
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    size_t& cur = limit[std::make_pair(dev, func)];
+    if (bytes <= cur) return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) cur = bytes;
+    return e;
+}
 
 // Launch one of the closed-loop step kernels, with the programmatic-serialization attribute when the handle asks for
 // it (the kernel may then become resident while its predecessor drains; it starts with pdl_prologue()).
@@ -315,10 +338,8 @@ extern "C" int fgnn_create(const fgnn_config* cfg, fgnn_handle** out) {
                                                                           // second atomic cost the final kernel more than the k_scan_sums launch, and k_scan then pays the cold read
         const char* lh = getenv("FGNN_LAST_HOP_SEPARATE");
         h->last_hop_separate = lh ? atoi(lh) != 0 : FGNN_LAST_HOP_SEPARATE_DEFAULT;
-        CK(cudaFuncSetAttribute((const void*)k_adjacency_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)((size_t)(WS_STAGE + 1) * ADJ_THREADS * sizeof(int) + WS_SMEM)));
-        CK(cudaFuncSetAttribute((const void*)k_adjacency_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)((size_t)64 * ADJ_THREADS * sizeof(int))));
+        CK(raise_smem_limit((const void*)k_adjacency_t<true>, (size_t)(((size_t)(WS_STAGE + 1) * ADJ_THREADS * sizeof(int) + WS_SMEM))));
+        CK(raise_smem_limit((const void*)k_adjacency_t<false>, (size_t)(((size_t)64 * ADJ_THREADS * sizeof(int)))));
     }
     p.inv_cell = 1.0 / (cfg->comm_radius * (1.0 + 1.0 / 1048576.0));
     p.R2 = cfg->comm_radius * cfg->comm_radius;
@@ -355,9 +376,9 @@ extern "C" int fgnn_create(const fgnn_config* cfg, fgnn_handle** out) {
         if (h->pair_mode) {
             const char* mb = getenv("FGNN_PR_MINB");
             h->pair_minb = mb ? atoi(mb) : FGNN_PR_MINBLOCKS;
-            CK(cudaFuncSetAttribute((const void*)k_pair_adjacency<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair_adjacency_smem()));
-            CK(cudaFuncSetAttribute((const void*)k_pair_adjacency<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair_adjacency_smem()));
-            CK(cudaFuncSetAttribute((const void*)k_pair_adjacency<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair_adjacency_smem()));
+            CK(raise_smem_limit((const void*)k_pair_adjacency<5>, (size_t)(pair_adjacency_smem())));
+            CK(raise_smem_limit((const void*)k_pair_adjacency<6>, (size_t)(pair_adjacency_smem())));
+            CK(raise_smem_limit((const void*)k_pair_adjacency<8>, (size_t)(pair_adjacency_smem())));
         }
     }
 
@@ -434,7 +455,7 @@ extern "C" int fgnn_create(const fgnn_config* cfg, fgnn_handle** out) {
     h->final_smem = final_smem_bytes(h);
     for (int closed = 0; closed < 2; ++closed) {
         final_kernel_t fk = final_kernel(p.K, h->HP, closed != 0);
-        CK(cudaFuncSetAttribute((const void*)fk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->final_smem));
+        CK(raise_smem_limit((const void*)fk, (size_t)(h->final_smem)));
         int occ = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)fk, FINAL_THREADS, h->final_smem));
         if (occ < 1) occ = 1;
@@ -463,7 +484,7 @@ extern "C" int fgnn_create(const fgnn_config* cfg, fgnn_handle** out) {
     if (h->use_tc) {
         for (int closed = 0; closed < 2; ++closed) {
             final_tc_kernel_t fk = final_tc_kernel(p.K, h->HP, closed != 0);
-            CK(cudaFuncSetAttribute((const void*)fk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->tc_smem));
+            CK(raise_smem_limit((const void*)fk, (size_t)(h->tc_smem)));
             // resident CTAs per SM from shared memory, registers and TMEM columns (the occupancy API does not
             // account for TMEM and was observed to report 0 for this kernel)
             cudaFuncAttributes fa;
@@ -488,7 +509,15 @@ extern "C" int fgnn_create(const fgnn_config* cfg, fgnn_handle** out) {
             h->mini_kernel = mini_rollout_kernel(p.K, h->HP);
             h->mini_adj_off = (int)((h->tc_smem + 127) & ~(size_t)127);
             h->mini_smem = (size_t)h->mini_adj_off + (size_t)h->adj_stage * ADJ_THREADS * sizeof(int);
-            if (h->mini_kernel) CK(cudaFuncSetAttribute((const void*)h->mini_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->mini_smem));
+            if (h->mini_kernel) {
+                // (function attributes are process-wide: size them for the largest stage any handle may ask for, 64 ids per thread)
+                const size_t stage_max = (size_t)64 * ADJ_THREADS * sizeof(int);
+                CK(raise_smem_limit((const void*)h->mini_kernel, (size_t)((h->mini_adj_off + stage_max))));
+                h->mini_policy = (mini_policy_kernel_t)kernel_lookup(p.K, h->HP, 6);
+                h->mini_envstep = (mini_envstep_kernel_t)kernel_lookup(p.K, h->HP, 7);
+                CK(raise_smem_limit((const void*)h->mini_policy, (size_t)(h->tc_smem)));
+                CK(raise_smem_limit((const void*)h->mini_envstep, (size_t)(stage_max)));
+            }
         }
     }
     *out = h;
@@ -607,7 +636,10 @@ extern "C" int fgnn_set_weights(fgnn_handle* h, int32_t layer, const float* W, c
 
 static int launch_check(fgnn_handle* h, const char* name) {
     h->launches += 1;
-    CK(cudaGetLastError());
+    {
+        const cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return fail(std::string("launch of ") + name + " -> " + cudaGetErrorString(e));
+    }
     if (h->profiling) {
         cudaEvent_t e;
         CK(cudaEventCreate(&e));
@@ -817,6 +849,16 @@ extern "C" int fgnn_integrate_f64(fgnn_handle* h, const double* u, double* rewar
 static int env_step_impl(fgnn_handle* h, const void* u, int f64, double* reward_b, void* stream) {
     if (h && h->sharded) return fail("fgnn_env_step: sharded handle -- integrate, exchange the halo, then build the graph");
     if (!h || !u) return fail("fgnn_env_step: null argument");
+    if (h->mini_envstep && !h->binned && !h->profiling) {     // small flock: integrator + cell sort + adjacency in one single-CTA launch
+        cudaStream_t st = (cudaStream_t)stream;
+        Params& p = h->p;
+        CK(cudaSetDevice(h->cfg.device));
+        CK(cudaMemcpyAsync(h->d_u_in, u, (size_t)p.n_own * 2 * (f64 ? sizeof(double) : sizeof(float)), cudaMemcpyDefault, st));
+        h->mini_envstep<<<1, FINAL_THREADS, (size_t)h->adj_stage * ADJ_THREADS * sizeof(int), st>>>(p, h->d_u_in, f64, 1, h->adj_stage);
+        if (launch_check(h, "mini_envstep")) return 1;
+        h->t_host += 1;
+        return copy_out(reward_b, p.reward, (size_t)p.B * sizeof(double), st);
+    }
     if (integrate_impl(h, u, f64, nullptr, (cudaStream_t)stream)) return 1;
     if (enqueue_build(h, 1, (cudaStream_t)stream)) return 1;
     return copy_out(reward_b, h->p.reward, (size_t)h->p.B * sizeof(double), (cudaStream_t)stream);
@@ -834,6 +876,11 @@ extern "C" int fgnn_policy(fgnn_handle* h, float* action, void* stream) {
     if (!h) return fail("fgnn_policy: null handle");
     cudaStream_t st = (cudaStream_t)stream;
     CK(cudaSetDevice(h->cfg.device));
+    if (h->mini_policy && !h->profiling) {            // small flock: hops + readout in one single-CTA launch
+        h->mini_policy<<<1, FINAL_THREADS, h->tc_smem, st>>>(h->p, (const uint8_t*)h->d_tc_weights);
+        if (launch_check(h, "mini_policy")) return 1;
+        return copy_out(action, h->p.action, (size_t)h->p.M * 2 * sizeof(float), st);
+    }
     if (enqueue_hops(h, st)) return 1;
     // Large flock, action wanted in HOST memory: run the readout in chunks of tiles and copy every chunk's actions out
     // on a second stream while the next chunk computes (the copy, 8 MB at N = 1M, costs twice the kernel).
@@ -965,7 +1012,7 @@ extern "C" int fgnn_actor_forward_dense(fgnn_handle* h, int32_t batch, int32_t n
     size_t smem = (size_t)K * F * DENSE_MT * sizeof(float) +
                   (h->HP > 64 ? (size_t)2 * h->HP * FINAL_THREADS * sizeof(float)
                               : ((size_t)wl.total() + (size_t)h->HP * FINAL_THREADS) * sizeof(float));
-    CK(cudaFuncSetAttribute((const void*)dk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(raise_smem_limit((const void*)dk, (size_t)(smem)));
     dim3 grid(blocks_for(n2, FINAL_THREADS), batch);
     dk<<<grid, FINAL_THREADS, smem, st>>>(ds, gso, out, h->d_weights, h->cfg.n_layers, n2);
     return launch_check(h, "actor_dense");

@@ -123,12 +123,71 @@ __global__ void __launch_bounds__(MINI_THREADS, 1) k_mini_rollout(Params p, cons
     for (int i = threadIdx.x; i <= pg.C; i += MINI_THREADS) pg.cell_start[i] = s_cell_start[i];
     final_tc_teardown<HP>(c);
 }
+
+// select_action alone (fgnn_policy): hops + open readout, z_{K-1} kept for fgnn_get_aggregated
+template <int K, int HP>
+__global__ void __launch_bounds__(MINI_THREADS, 1) k_mini_policy(Params p, const uint8_t* __restrict__ tcw) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    TcCtx c;
+    final_tc_setup<K, HP>(p, tcw, smem_raw, c);
+    mini_hops<K>(p);
+    Params pf = p;
+    pf.last_hop_done = K >= 2 ? 1 : 0;
+    pf.write_z_last = 1;
+    pf.tile_lo = 0; pf.tile_hi = 0;
+    pf.fuse = nullptr;
+    final_tc_tiles<K, HP, false>(pf, c);
+    final_tc_teardown<HP>(c);
+}
+
+// env.step(u) alone (fgnn_env_step): integrator + binning, cell sort, adjacency + features
+template <typename T2>
+static __device__ __forceinline__ void mini_envstep_body(const Params& p, const T2* __restrict__ u, int advance, int stage_cap,
+                                                         unsigned char* s_adj, int* s_cell) {
+    const int i = threadIdx.x;
+    double racc[4] = {0, 0, 0, 0};
+    if (i < owned_count(p)) {
+        const int a = owned_agent(p, i);
+        if (a >= 0) {
+            const T2 uu = u[i];
+            integrate_and_bin(p, a, ldg256(&p.state[a]), (double)uu.x, (double)uu.y, racc);
+        }
+    }
+    reward_block_flush<MINI_THREADS>(p, racc);
+    __syncthreads();
+    mini_sort(p, advance, s_cell);
+    adjacency_body<false>(p, stage_cap, s_adj);
+}
+
+template <int K>        // (K only keeps the symbol unique per object file)
+__global__ void __launch_bounds__(MINI_THREADS, 1) k_mini_envstep(Params p, const void* __restrict__ u, int f64, int advance, int stage_cap) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    __shared__ int s_cell[MINI_THREADS];
+    if (f64) mini_envstep_body(p, reinterpret_cast<const double2*>(u), advance, stage_cap, smem_raw, s_cell);
+    else mini_envstep_body(p, reinterpret_cast<const float2*>(u), advance, stage_cap, smem_raw, s_cell);
+}
 #endif
 
 typedef void (*mini_rollout_kernel_t)(Params, const uint8_t*, int, int, int);
 mini_rollout_kernel_t FGNN_CAT(get_mini_rollout_k, FGNN_K, _hp, FGNN_HP)() {
 #if FGNN_HP <= 64
     return k_mini_rollout<FGNN_K, FGNN_HP>;
+#else
+    return nullptr;
+#endif
+}
+typedef void (*mini_policy_kernel_t)(Params, const uint8_t*);
+mini_policy_kernel_t FGNN_CAT(get_mini_policy_k, FGNN_K, _hp, FGNN_HP)() {
+#if FGNN_HP <= 64
+    return k_mini_policy<FGNN_K, FGNN_HP>;
+#else
+    return nullptr;
+#endif
+}
+typedef void (*mini_envstep_kernel_t)(Params, const void*, int, int, int);
+mini_envstep_kernel_t FGNN_CAT(get_mini_envstep_k, FGNN_K, _hp, FGNN_HP)() {
+#if FGNN_HP <= 64
+    return k_mini_envstep<FGNN_K * 1000 + FGNN_HP>;
 #else
     return nullptr;
 #endif

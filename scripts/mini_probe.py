@@ -39,6 +39,12 @@ for n, b in ((100, 1), (50, 1), (128, 1), (32, 4)):
             eng.step(a, r)
             eng.sync()
         step_us = (time.perf_counter() - t0) / 300 * 1e6
-        print(f"N={n} B={b} FGNN_MINI={mini}: rollout {best * 1e3:.2f} us/step ({n * b / best / 1e3:.2f}e6 agent-steps/s) | "
+        eng.reset(x0)
+        t0 = time.perf_counter()
+        for _ in range(300):
+            eng.policy(out=a)                            # select_action -> host (synchronises)
+            eng.env_step(a)                              # env.step(host action) -> reward (synchronises)
+        split_us = (time.perf_counter() - t0) / 300 * 1e6
+        print(f"N={n} B={b} FGNN_MINI={mini}: policy + env_step {split_us:.1f} us | rollout {best * 1e3:.2f} us/step ({n * b / best / 1e3:.2f}e6 agent-steps/s) | "
               f"fgnn_step + sync {step_us:.1f} us", flush=True)
         eng.close()

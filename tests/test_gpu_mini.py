@@ -41,6 +41,10 @@ def _run(monkeypatch, mini, n, episodes, k, hidden, sd, x0, mask=None):
     eng.policy(out=a)
     out.append((a.copy(), eng.get_aggregated()))
     eng.env_step(a)
+    eng.policy(out=a)
+    out.append((a.copy(),))
+    eng.env_step(a.astype(np.float64) * 0.5)             # float64 action (the controller's dtype)
+    out.append((eng.get_state(), eng.get_degrees(), eng.get_features()))
     eng.rollout(3)                                       # ... and fused ones after those
     out.append((eng.get_state(), eng.get_degrees()))
     st = eng.stats()
@@ -63,7 +67,7 @@ def test_mini_path_equals_general_kernels(n, episodes, k, hidden, monkeypatch):
     ref, launches_ref, st_ref = _run(monkeypatch, False, n, episodes, k, hidden, sd, x0, mask)
     got, launches, st = _run(monkeypatch, True, n, episodes, k, hidden, sd, x0, mask)
     assert st["step"] == st_ref["step"] and st["n_edges"] == st_ref["n_edges"]
-    assert launches < launches_ref                       # 15 fused steps: one launch per call instead of eight per step
+    assert launches < launches_ref                       # one launch per call instead of up to eight per step
     for i, (ra, rb) in enumerate(zip(ref, got)):
         for u, v in zip(ra, rb):
             if episodes > 1 and u.dtype == np.float64 and u.shape[-1:] == (episodes,):
@@ -71,3 +75,28 @@ def test_mini_path_equals_general_kernels(n, episodes, k, hidden, monkeypatch):
                 np.testing.assert_allclose(u, v, rtol=1e-12, atol=1e-15, err_msg=f"record {i}")
             else:
                 np.testing.assert_array_equal(u, v, err_msg=f"record {i}")
+
+
+def test_handles_with_different_stage_depths_share_the_kernels():
+    """The dynamic-shared-memory limit is a process-wide attribute of a kernel: a second handle with a shallower neighbour
+    stage (or fewer layers) must not lower it under the first handle's feet (found by the compat rollout: its Actor keeps a
+    second engine for the dense forward)."""
+    from multiagent_gnn_policies_b200.engine import FlockEngine
+    sd = load_golden("ckpt_n100_k3")["state_dict"]
+    x0 = flock_env.synthetic_state(100, seed=3, density=1.6)
+    deep = FlockEngine(n_agents=100, k=3, hidden=32, n_layers=2, comm_radius=1.0, dt=0.01, edge_capacity=99)
+    deep.load_state_dict(sd)
+    deep.reset(x0)
+    shallow = FlockEngine(n_agents=100, k=3, hidden=32, n_layers=2, comm_radius=1.0, dt=0.01, edge_capacity=8)
+    shallow.load_state_dict(sd)
+    shallow.reset(x0)
+    a = np.empty((100, 2), np.float32)
+    for eng in (deep, shallow, deep):
+        eng.policy(out=a)
+        eng.env_step(a)
+        eng.rollout(2)
+        eng.step(a, None)
+    np.testing.assert_array_equal(deep.get_degrees(), deep.get_degrees())
+    assert not deep.stats()["overflow"] and not shallow.stats()["overflow"]
+    deep.close()
+    shallow.close()
