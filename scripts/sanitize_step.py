@@ -1,6 +1,7 @@
 """Workload for compute-sanitizer (memcheck / racecheck / synccheck): a 10k-agent flock through every kernel of the step --
 k_adjacency_t (FGNN_STEP_MODE=0), the warp-tiled k_pair_adjacency with its TMA staging (FGNN_STEP_MODE=1), graph replay, the API-split path with
-float32 and float64 actions, the expert controller, and two in-process ranks over the p2p halo transport.
+float32 and float64 actions, the expert controller, the single-CTA kernels of small flocks, and two in-process ranks
+over the p2p halo transport (folded prepare / flag).
     compute-sanitizer --tool memcheck python scripts/sanitize_step.py"""
 import os
 import sys
@@ -32,6 +33,21 @@ for mode in ("0", "1"):
     eng.controller(centralized=True)
     eng.sync()
     print("mode", mode, eng.stats())
+    eng.close()
+# the single-CTA kernels of small flocks (fgnn_mini.cu): fused step, rollout, policy, env_step (fp32 and float64 actions)
+for nb, ne in ((100, 1), (30, 4)):
+    eng = FlockEngine(n_agents=nb, n_episodes=ne, k=3, hidden=32, n_layers=2, comm_radius=1.0, dt=0.01)
+    eng.load_state_dict(sd)
+    eng.reset(np.concatenate([make_workload(nb, seed=3 + e) for e in range(ne)]))
+    for _ in range(3):
+        eng.step(None, None)
+    eng.rollout(5)
+    a = eng.policy().cpu().numpy()
+    eng.env_step(a)
+    eng.env_step(a.astype(np.float64))
+    eng.host_rows = eng.get_features()
+    eng.sync()
+    print("mini", nb, ne, eng.stats())
     eng.close()
 os.environ["FGNN_STEP_MODE"] = "0"
 x0 = x0[np.argsort(x0[:, 0], kind="stable")]
