@@ -27,6 +27,10 @@ constexpr int LMAX = 4;       // hidden layers supported
 constexpr int FINAL_THREADS = 128;   // block size of the fused final kernel and the dense Actor kernel
 constexpr int DENSE_MT = 32;         // m-tile of the dense Actor kernel
 constexpr int RSLOTS = 64;          // reward accumulators per episode (spreads same-address atomics)
+// ... of which a handle with many episodes uses fewer: an episode of N agents feeds its sums from ~N/128 blocks, and the
+// finalisation walks every slot of every episode (with 64 slots and 256 episodes that walk was 38 us on the critical path
+// of k_scatter -- config C3)
+__host__ __device__ inline int rslots_of(int B) { return B >= 64 ? 4 : B >= 8 ? 16 : RSLOTS; }
 constexpr int ELLW = 8;             // neighbours kept inline per agent: one dependent load less per gather
 constexpr int MINI_MAX_CELLS = 1280;        // single-CTA path (fgnn_mini.cu): cells of the flock's grid it keeps in shared memory
 #ifndef FGNN_HOP_UNROLL
@@ -323,10 +327,19 @@ static __device__ __forceinline__ void finalize_reward(const Params& p) {
     } else {
         for (int b = threadIdx.x; b < p.B; b += blockDim.x) {
             double q[4] = {0, 0, 0, 0};
-            for (int sidx = 0; sidx < RSLOTS; ++sidx) {
+            const int nslots = rslots_of(p.B);
+            // loads first (independent: several slots in flight), stores after -- interleaved they form one dependent chain
+            // of L2 round trips per slot
+#pragma unroll 8
+            for (int sidx = 0; sidx < nslots; ++sidx) {
+                const double* src = p.racc + ((size_t)sidx * p.B + b) * 4;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) q[k] += src[k];
+            }
+            for (int sidx = 0; sidx < nslots; ++sidx) {
                 double* src = p.racc + ((size_t)sidx * p.B + b) * 4;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) { q[k] += src[k]; src[k] = 0.0; }
+                for (int k = 0; k < 4; ++k) src[k] = 0.0;
             }
             const double mx = q[0] / n, my = q[1] / n;
             const double r = -((q[2] / n - mx * mx) + (q[3] / n - my * my));
@@ -1159,7 +1172,7 @@ __device__ __forceinline__ double4 integrate_and_bin(const Params& p, int a, con
         const unsigned mask = __activemask();
         const int ep0 = __shfl_sync(mask, ep, __ffs(mask) - 1);
         const bool uniform = __all_sync(mask, ep == ep0);
-        double* dst = p.racc + ((size_t)(blockIdx.x % RSLOTS) * p.B + ep) * 4;
+        double* dst = p.racc + ((size_t)(blockIdx.x % rslots_of(p.B)) * p.B + ep) * 4;
         if (uniform && mask == 0xffffffffu) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {

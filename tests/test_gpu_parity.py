@@ -490,6 +490,7 @@ def test_float64_action_path(centralized):
     (5000, 1, 2, 1.0, False),
     (4000, 1, 1, 1.0, False),
     (500, 6, 3, 1.0, False),          # batched episodes
+    (20000, 3, 3, 1.0, False),        # batched episodes with grid rows long enough for the staged path (episode > 0)
     (3000, 1, 3, 3.0, False),         # ~45 neighbours: cell rows longer than 32 candidates, rows longer than the staged
                                       # neighbour list, warps that outgrow the stage
     (2500, 1, 3, 2.0, True),
