@@ -348,9 +348,12 @@ extern "C" int fgnn_create(const fgnn_config* cfg, fgnn_handle** out) {
     p.n_tiles = blocks_for(p.C + 1, SCAN_TILE);
     {   // warp-tiled adjacency (FGNN_STEP_MODE=0 selects k_adjacency_t of round 1)
         const char* sm = getenv("FGNN_STEP_MODE");
-        // default: on when grid rows are long enough for most warps to sit inside one row and the expected degree is
-        // moderate (the staged path lists at most PR_LIST neighbours per agent); FGNN_STEP_MODE=0/1 overrides
-        h->pair_mode = sm ? atoi(sm) != 0 : (FGNN_STEP_MODE_DEFAULT != 0 && G >= 64 && cap_per <= 48);
+        // default: on for large flocks of moderate expected degree (the staged path lists at most PR_LIST neighbours per agent).
+        // Its chain of dependent steps per warp (cell table -> TMA -> convert -> filter -> list -> features) is longer than
+        // k_adjacency_t's, and the warps that straddle a grid row take the slow per-lane path: below a few waves of blocks that
+        // latency is the kernel's time (26 us at N = 10k .. 100k against ~20 us), above it the lower instruction count wins
+        // (89.5 against 102 us at N = 1M).  FGNN_STEP_MODE=0/1 overrides.
+        h->pair_mode = sm ? atoi(sm) != 0 : (FGNN_STEP_MODE_DEFAULT != 0 && G >= 400 && cap_per <= 48);
         memset(&h->geo, 0, sizeof h->geo);
         PairGeom& ge = h->geo;
         // fp32 pre-filter on warp-relative coordinates (|coordinate| <= E).  With u = 2^-24: every coordinate carries

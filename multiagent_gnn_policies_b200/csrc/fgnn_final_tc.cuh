@@ -378,7 +378,7 @@ __device__ __forceinline__ void final_tc_tiles(const Params& p, TcCtx& c) {
 }
 
 template <int K, int HP, bool CLOSED>
-__global__ void __launch_bounds__(FINAL_THREADS, 4) k_final_tc(Params p, const uint8_t* __restrict__ tcw) {
+__global__ void __launch_bounds__(FINAL_THREADS, HP <= 32 ? 4 : 2) k_final_tc(Params p, const uint8_t* __restrict__ tcw) {
     pdl_prologue();
     extern __shared__ __align__(128) uint8_t smem_raw[];
     TcCtx c;

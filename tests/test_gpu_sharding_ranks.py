@@ -24,6 +24,8 @@ def test_real_ranks_reproduce_single_engine(world, mode):
         pytest.skip(f"needs {world} GPUs")
     port = 29600 + world + {"p2p": 10, "p2p_host": 20, "gather": 0}[mode]
     env = dict(os.environ, FGNN_CHECK_N="120000", FGNN_CHECK_STEPS="40")
+    if mode != "gather":
+        env["FGNN_STEP_MODE"] = "1"      # the warp-tiled adjacency on sharded pools too (by default it starts at larger shards)
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
                           "--master-addr", "127.0.0.1", "--master-port", str(port),
                           os.path.join(ROOT, "scripts", "check_sharded_nccl.py"), mode],
