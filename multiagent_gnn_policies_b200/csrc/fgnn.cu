@@ -69,9 +69,12 @@ int nccl_check(int rc, const char* what) {
 }
 }  // namespace
 
-#define FGNN_MAX_CHUNKS 8
+#define FGNN_MAX_CHUNKS 32
 #ifndef FGNN_POLICY_CHUNKS_DEFAULT
 #define FGNN_POLICY_CHUNKS_DEFAULT 4              // measured: e2e 0.664 -> 0.626 ms/step at N=1M (scripts/policy_chunks_check.py)
+#endif
+#ifndef FGNN_POLICY_PIPE_DEFAULT
+#define FGNN_POLICY_PIPE_DEFAULT 2                // waves of the readout grid per chunk of the pipelined host path (0: equal chunks)
 #endif
 
 struct fgnn_handle {
@@ -110,6 +113,7 @@ struct fgnn_handle {
     int* d_csr_cols = nullptr;
     unsigned* d_csr_cursor = nullptr;
     int policy_chunks = 1;           // fgnn_policy to a host buffer: readout chunks overlapped with their D2H copies
+    int policy_pipe = 0;             // > 0: chunks of this many waves of the readout grid, the LAST hop inside each chunk's readout
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t chunk_event[FGNN_MAX_CHUNKS + 1] = {};
     // small flocks (B*N <= 128): the whole closed-loop step in one CTA, T steps per launch (fgnn_mini.cu)
@@ -329,6 +333,8 @@ extern "C" int fgnn_create(const fgnn_config* cfg, fgnn_handle** out) {
         h->adj_warp_staged = mode ? atoi(mode) != 0 : (FGNN_ADJ_DEFAULT_WS && cap_per <= 48);
         const char* pc = getenv("FGNN_POLICY_CHUNKS");
         h->policy_chunks = pc ? atoi(pc) : FGNN_POLICY_CHUNKS_DEFAULT;
+        const char* pp = getenv("FGNN_POLICY_PIPE");
+        h->policy_pipe = pp ? atoi(pp) : FGNN_POLICY_PIPE_DEFAULT;
         const char* pd = getenv("FGNN_PDL");
         h->pdl = pd ? atoi(pd) != 0 : FGNN_PDL_DEFAULT;
         const char* tp = getenv("FGNN_SCAN_TWO_PASS");
@@ -705,7 +711,8 @@ static void launch_hop(fgnn_handle* h, int j, cudaStream_t st, int tail = 0) {
 }
 
 // prepare_tail: p2p step of a sharded rank -- block 0 of the LAST hop launch also does k_shard_prepare's work
-static int enqueue_hops(fgnn_handle* h, cudaStream_t st, bool prepare_tail = false) {
+// skip_last: the caller runs the last hop inside the final kernel (last_hop_done = 0)
+static int enqueue_hops(fgnn_handle* h, cudaStream_t st, bool prepare_tail = false, bool skip_last = false) {
     Params& p = h->p;
     for (int j = 0; j + 2 < p.K; ++j) {     // hops 0 .. K-3 ; hop K-2 lives in the final kernel (or below)
         const int nb = p.K - 1 - j;
@@ -715,7 +722,7 @@ static int enqueue_hops(fgnn_handle* h, cudaStream_t st, bool prepare_tail = fal
         else return fail("internal: unexpected hop shape");
         if (launch_check(h, j == 0 ? "hop0" : "hop1")) return 1;
     }
-    if (h->last_hop_separate && p.K >= 2) {  // tap K-1 through graph t-(K-2), written to zbuf[K-1] for the final kernel
+    if (h->last_hop_separate && !skip_last && p.K >= 2) {  // tap K-1 through graph t-(K-2), written to zbuf[K-1] for the final kernel
         const int j = p.K - 2;
         if (j == 0) launch_hop<1, true>(h, j, st, prepare_tail ? 1 : 0);
         else launch_hop<1, false>(h, j, st, prepare_tail ? 1 : 0);
@@ -725,12 +732,12 @@ static int enqueue_hops(fgnn_handle* h, cudaStream_t st, bool prepare_tail = fal
 }
 
 static int enqueue_final(fgnn_handle* h, bool closed, int write_z, cudaStream_t st, bool fuse_pack = false, int tile_lo = 0,
-                         int tile_hi = 0) {
+                         int tile_hi = 0, bool hop_inside = false) {
     Params p = h->p;
     p.tile_lo = tile_lo;
     p.tile_hi = tile_hi;
     p.write_z_last = write_z;
-    p.last_hop_done = (h->last_hop_separate && p.K >= 2) ? 1 : 0;
+    p.last_hop_done = (h->last_hop_separate && !hop_inside && p.K >= 2) ? 1 : 0;
     p.fuse = fuse_pack ? h->d_fuse : nullptr;
     if (h->use_tc) {
         final_tc_kernel_t fk = final_tc_kernel(p.K, h->HP, closed);
@@ -884,36 +891,53 @@ extern "C" int fgnn_policy(fgnn_handle* h, float* action, void* stream) {
         if (launch_check(h, "mini_policy")) return 1;
         return copy_out(action, h->p.action, (size_t)h->p.M * 2 * sizeof(float), st);
     }
-    if (enqueue_hops(h, st)) return 1;
     // Large flock, action wanted in HOST memory: run the readout in chunks of tiles and copy every chunk's actions out
     // on a second stream while the next chunk computes (the copy, 8 MB at N = 1M, costs twice the kernel).
+    // Pipelined form (policy_pipe > 0): the LAST hop runs inside each chunk's readout (the final kernel's own gather,
+    // same row order, same bits) instead of as a launch over the whole flock in front of the first chunk, the first
+    // chunk is one wave of the persistent readout grid and the others policy_pipe waves: the first copy starts one
+    // wave after hop 0 and the copies then run back to back (they are slower than the chunks that feed them).
+    bool host_chunks = false;
     if (!h->sharded && action && h->policy_chunks > 1 && h->p.M >= (1 << 18)) {
         cudaPointerAttributes attr;
         const bool on_device = cudaPointerGetAttributes(&attr, action) == cudaSuccess &&
                                (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged);
         cudaGetLastError();
-        if (!on_device) {
-            if (!h->copy_stream) {
-                CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-                for (int c = 0; c <= FGNN_MAX_CHUNKS; ++c) CK(cudaEventCreateWithFlags(&h->chunk_event[c], cudaEventDisableTiming));
-            }
-            const int n_tiles = blocks_for(h->p.M, FINAL_THREADS);
-            const int C = h->policy_chunks < FGNN_MAX_CHUNKS ? h->policy_chunks : FGNN_MAX_CHUNKS;
-            const int per = blocks_for(n_tiles, C);
-            for (int c = 0; c < C; ++c) {
-                const int lo = c * per, hi = (c + 1) * per < n_tiles ? (c + 1) * per : n_tiles;
-                if (lo >= hi) break;
-                if (enqueue_final(h, false, 1, st, false, lo, hi)) return 1;
-                CK(cudaEventRecord(h->chunk_event[c], st));
-                CK(cudaStreamWaitEvent(h->copy_stream, h->chunk_event[c], 0));
-                const size_t a0 = (size_t)lo * FINAL_THREADS, a1 = (size_t)hi * FINAL_THREADS < (size_t)h->p.M ? (size_t)hi * FINAL_THREADS : (size_t)h->p.M;
-                CK(cudaMemcpyAsync(action + a0 * 2, h->p.action + a0 * 2, (a1 - a0) * 2 * sizeof(float), cudaMemcpyDeviceToHost,
-                                   h->copy_stream));
-            }
-            CK(cudaEventRecord(h->chunk_event[FGNN_MAX_CHUNKS], h->copy_stream));
-            CK(cudaStreamWaitEvent(st, h->chunk_event[FGNN_MAX_CHUNKS], 0));     // the caller's stream covers the copies
-            return 0;
+        host_chunks = !on_device;
+    }
+    const bool pipe = host_chunks && h->policy_pipe > 0 && h->p.K >= 2;
+    if (enqueue_hops(h, st, false, pipe)) return 1;
+    if (host_chunks) {
+        if (!h->copy_stream) {
+            CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+            for (int c = 0; c <= FGNN_MAX_CHUNKS; ++c) CK(cudaEventCreateWithFlags(&h->chunk_event[c], cudaEventDisableTiming));
         }
+        const int n_tiles = blocks_for(h->p.M, FINAL_THREADS);
+        int first, per;                                   // tiles of chunk 0 / of every later chunk
+        if (pipe) {
+            const int wave = h->use_tc ? h->tc_grid_open : h->final_grid_open;
+            first = wave;
+            per = wave * h->policy_pipe;
+            while (first + (long long)per * (FGNN_MAX_CHUNKS - 1) < n_tiles) per += wave;
+        } else {
+            const int C = h->policy_chunks < FGNN_MAX_CHUNKS ? h->policy_chunks : FGNN_MAX_CHUNKS;
+            first = per = blocks_for(n_tiles, C);
+        }
+        int c = 0;
+        for (int lo = 0; lo < n_tiles; ++c) {
+            int hi = lo + (c == 0 ? first : per);
+            if (hi > n_tiles) hi = n_tiles;
+            if (enqueue_final(h, false, 1, st, false, lo, hi, pipe)) return 1;
+            CK(cudaEventRecord(h->chunk_event[c], st));
+            CK(cudaStreamWaitEvent(h->copy_stream, h->chunk_event[c], 0));
+            const size_t a0 = (size_t)lo * FINAL_THREADS, a1 = (size_t)hi * FINAL_THREADS < (size_t)h->p.M ? (size_t)hi * FINAL_THREADS : (size_t)h->p.M;
+            CK(cudaMemcpyAsync(action + a0 * 2, h->p.action + a0 * 2, (a1 - a0) * 2 * sizeof(float), cudaMemcpyDeviceToHost,
+                               h->copy_stream));
+            lo = hi;
+        }
+        CK(cudaEventRecord(h->chunk_event[FGNN_MAX_CHUNKS], h->copy_stream));
+        CK(cudaStreamWaitEvent(st, h->chunk_event[FGNN_MAX_CHUNKS], 0));     // the caller's stream covers the copies
+        return 0;
     }
     if (enqueue_final(h, false, 1, st)) return 1;
     if (h->sharded) {           // owned-list order, pool_cap rows
@@ -1611,6 +1635,18 @@ extern "C" int fgnn_shard_exchange_p2p(fgnn_handle* h, int32_t advance, void* st
     return enqueue_shard_unpack(h, h->p2p_inbox, h->p2p_cap, st, parity_stride, my_flags, h->d_fuse, n_blocks);
 }
 
+// Keeps the stream busy for `ns` nanoseconds: fgnn_profile_step puts it in front of its first event so that the step's
+// kernels are already queued when the clock starts (on an idle stream the first interval would also hold the host's
+// launch latency: hop 0 read ~20 us too long).
+__global__ void k_delay(unsigned long long ns) {
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    do {
+        __nanosleep(1000);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    } while (t1 - t0 < ns);
+}
+
 extern "C" int fgnn_profile_step(fgnn_handle* h, int32_t max_kernels, float* ms_out, char* names_out, int32_t* n_out,
                                  void* stream) {
     if (!h || !ms_out || !n_out) return fail("fgnn_profile_step: null argument");
@@ -1622,6 +1658,7 @@ extern "C" int fgnn_profile_step(fgnn_handle* h, int32_t max_kernels, float* ms_
     h->prof_names.clear();
     cudaEvent_t e0;
     CK(cudaEventCreate(&e0));
+    k_delay<<<1, 1, 0, st>>>(100000ull);
     CK(cudaEventRecord(e0, st));
     h->profiling = true;
     h->prof_stream = st;

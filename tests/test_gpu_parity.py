@@ -530,3 +530,41 @@ def test_pair_kernels_equal_separate_kernels(n, episodes, k, radius, tail_only, 
         for u, v in zip(ra, rb):
             np.testing.assert_array_equal(u, v, err_msg=f"step {t}")
     np.testing.assert_array_equal(a_cols, b_cols)
+
+
+@pytest.mark.parametrize("n,k,hidden", [(300001, 3, 32), (270000, 2, 16), (262144, 4, 64), (280000, 1, 32), (300001, 3, 128)])
+def test_host_buffer_policy_chunked_equals_single_launch(n, k, hidden, monkeypatch):
+    """fgnn_policy into a HOST buffer (select_action -> numpy, the reference-facing call) at sizes that take the chunked
+    path (M >= 2^18): the pipelined form (FGNN_POLICY_PIPE: last hop inside every chunk's readout, copies on a second stream)
+    and the equal-chunk form must fill the same actions / aggregated z as ONE readout launch into device memory, and the
+    step that follows must leave the same state."""
+    import torch
+    from multiagent_gnn_policies_b200.engine import FlockEngine
+    rng = np.random.default_rng(n + k)
+    sd = _random_state_dict(rng, k, hidden, 2)
+    x0 = flock_env.synthetic_state(n, seed=3, density=1.6)
+    runs = []
+    for chunks, pipe, host in ((1, 0, False), (4, 0, True), (4, 1, True), (4, 2, True), (4, 5, True)):
+        monkeypatch.setenv("FGNN_POLICY_CHUNKS", str(chunks))
+        monkeypatch.setenv("FGNN_POLICY_PIPE", str(pipe))
+        eng = FlockEngine(n_agents=n, k=k, hidden=hidden, n_layers=2, comm_radius=1.0, dt=0.01)
+        eng.load_state_dict(sd)
+        eng.reset(x0)
+        eng.rollout(k + 1)
+        out = []
+        for t in range(3):
+            if host:
+                a = torch.full((n, 2), float("nan"), dtype=torch.float32).pin_memory().numpy()
+                eng.policy(out=a)
+            else:
+                a = eng.policy().cpu().numpy()
+            assert np.isfinite(a).all()
+            out += [a.copy(), eng.get_aggregated(), eng.get_action()]
+            eng.env_step(a * 0.05)
+            out.append(eng.get_state())
+        assert not eng.stats()["overflow"]
+        runs.append(out)
+        eng.close()
+    for r in runs[1:]:
+        for u, v in zip(runs[0], r):
+            np.testing.assert_array_equal(u, v)
