@@ -349,6 +349,11 @@ def main():
 
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # before any pinned allocation: the rank and its host buffers on the GPU's own NUMA node (FGNN_BIND_CPUS=0: leave it)
+        if os.environ.get("FGNN_BIND_CPUS", "1") != "0":
+            from multiagent_gnn_policies_b200 import parallel
+            cpus = parallel.bind_to_local_cpus(local_rank)
+            config["cpu_binding"] = f"rank 0 bound to {len(cpus)} GPU-local cpus" if cpus else "unchanged"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     N = args.n_agents

@@ -24,6 +24,33 @@ FAR = 1.0e30        # x coordinate given to agents a rank knows nothing about at
 INF = 1.0e300
 
 
+def bind_to_local_cpus(device_index):
+    """One process per GPU: run this rank on the CPUs NVML names as local to its GPU, so that its pinned host buffers
+    (first touch) and the driver's copies stay on the GPU's own NUMA node.  With eight ranks moving 8 MB down and 8 MB up per
+    step through host buffers, a rank floating on the other socket sends all of it across the inter-socket link.  Best
+    effort: returns the sorted CPU list it bound to, or None when NVML is missing, the mask is empty inside this process's
+    cpuset, or it already equals the allowed set (then nothing is changed)."""
+    import os
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        uuid = "GPU-" + str(torch.cuda.get_device_properties(device_index).uuid)
+        try:
+            handle = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+        except Exception:
+            handle = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+        allowed = os.sched_getaffinity(0)
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (max(allowed) + 64) // 64)
+        local = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1} & allowed
+        if not local or local == allowed:
+            return None
+        os.sched_setaffinity(0, local)
+        return sorted(local)
+    except Exception:
+        return None
+
+
 def shard_ranges(n_total, world):
     """Contiguous, balanced index ranges: [(lo, count)] * world."""
     base, rem = divmod(n_total, world)
