@@ -128,13 +128,17 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+NOT_STEP_SOURCES = ("fgnn_dense.cu",)      # dense Actor.forward for ind_agg > 0 (compat surface): no kernel of the step lives there
+
+
 def kernel_source_sha():
-    """sha1 over the CUDA sources: profiles/r2_traffic.json records the build its ncu capture was taken from."""
+    """sha1 over the CUDA sources of the step (every .cu / .cuh under csrc/ except NOT_STEP_SOURCES): profiles/r2_traffic.json
+    records the build its ncu capture was taken from."""
     import hashlib
     h = hashlib.sha1()
     csrc = os.path.join(ROOT, "multiagent_gnn_policies_b200", "csrc")
     for name in sorted(os.listdir(csrc)):
-        if name.endswith((".cu", ".cuh")):
+        if name.endswith((".cu", ".cuh")) and name not in NOT_STEP_SOURCES:
             h.update(open(os.path.join(csrc, name), "rb").read())
     return h.hexdigest()[:16]
 

@@ -126,6 +126,22 @@ int fgnn_rollout(fgnn_handle* h, int32_t T, double* reward_bt, void* stream);
 int fgnn_actor_forward_dense(fgnn_handle* h, int32_t batch, int32_t n_agents, const float* delay_state,
                              const float* delay_gso, float* out, void* stream);
 
+/* Actor.forward(delay_state, delay_gso) on dense tensors for ANY aggregation index and layer widths the reference's
+ * constructor accepts (learner/actor.py:9-43: kernel (K,1) at layer ind_agg, (1,1) elsewhere; forward: actor.py:45-86;
+ * ind_agg > 0 is what learner/gnn_ddpg.py:126 builds).  No engine handle: the caller passes the layer parameters.
+ *   widths      n_layers + 1 ints: n_s, hidden widths ..., n_a
+ *   W[l], b[l]  conv_layers[l].weight (widths[l+1], widths[l], step_l, 1) contiguous with step_l = K at l == ind_agg,
+ *               1 elsewhere, and conv_layers[l].bias (widths[l+1]); fp32 DEVICE pointers (the array of pointers is host)
+ *   delay_state (B,K,n_s,N), delay_gso (B,K,N,N), out (B,1,n_a,N); fp32 DEVICE pointers
+ *   workspace   DEVICE scratch of fgnn_actor_general_workspace(...) bytes (that call returns -1 on bad shapes)
+ * ind_agg outside 0..n_layers-1 is accepted only for K = 1 (otherwise K rows remain and the reference's final view
+ * fails too).  Small-N compatibility surface (dense operators), not the rollout path. */
+int64_t fgnn_actor_general_workspace(int32_t batch, int32_t n_agents, int32_t k, int32_t n_layers, const int32_t* widths);
+int fgnn_actor_forward_general(int32_t device, int32_t batch, int32_t n_agents, int32_t k, int32_t n_layers,
+                               const int32_t* widths, int32_t ind_agg, const float* const* W, const float* const* b,
+                               const float* delay_state, const float* delay_gso, float* out, float* workspace,
+                               void* stream);
+
 /* Read-back (tests, small-N compatibility with the dense reference API). */
 int fgnn_get_state(fgnn_handle* h, double* x_bn4, void* stream);
 int fgnn_get_features(fgnn_handle* h, int32_t age, float* values_bn6, void* stream);       /* x_{t-age} */

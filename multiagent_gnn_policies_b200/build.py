@@ -39,6 +39,8 @@ def _units():
                              os.path.join(CSRC, "fgnn_final_tc.cuh"), os.path.join(CSRC, "fgnn_pair.cuh")])]
     units.append((os.path.join(OBJ, "fgnn_train.o"), os.path.join(CSRC, "fgnn_train.cu"), [],
                   [os.path.join(INCLUDE, "fgnn.h")]))
+    units.append((os.path.join(OBJ, "fgnn_dense.o"), os.path.join(CSRC, "fgnn_dense.cu"), [],
+                  [os.path.join(INCLUDE, "fgnn.h")]))
     for k in KS:
         for hp in HPS:
             units.append((os.path.join(OBJ, f"fgnn_final_k{k}_hp{hp}.o"), os.path.join(CSRC, "fgnn_final.cu"),

@@ -2,15 +2,19 @@
 ``forward(delay_state, delay_gso)`` contract (learner/actor.py:7-86).
 
 Inference (no autograd) runs in libfgnn.so: the dense-tensor kernel ``fgnn_actor_forward_dense``
-(per-agent K-tap aggregation + readout on CUDA cores / tensor cores).  When autograd is recording
+(per-agent K-tap aggregation + readout on CUDA cores / tensor cores) for DAGGER's shape (ind_agg = 0, equal hidden
+widths), ``fgnn_actor_forward_general`` for everything else the constructor accepts (ind_agg > 0 as in
+learner/gnn_ddpg.py:126, unequal widths, n_s != 6).  When autograd is recording
 (DAGGER.gradient_step, learner/gnn_dagger.py:76-96) the same arithmetic is expressed with torch ops on
 the GPU so gradients flow -- training is a "next" row of SURVEY.md section 8(f), not the hot path.
 There is no CPU path: tensors must live on a CUDA device.
 """
+import ctypes
+
 import torch
 import torch.nn as nn
 
-from multiagent_gnn_policies_b200.engine import FlockEngine, FgnnError
+from multiagent_gnn_policies_b200.engine import FlockEngine, FgnnError, load_library
 
 
 class Actor(nn.Module):
@@ -56,6 +60,33 @@ class Actor(nn.Module):
         self.sync_engine(self._engine)
         return self._engine
 
+    def _forward_general(self, delay_state, delay_gso):
+        """learner/actor.py:45-86 for any ``ind_agg`` / layer widths: three plain CUDA kernels behind
+        ``fgnn_actor_forward_general`` (csrc/fgnn_dense.cu), parameters read in place from the conv tensors."""
+        lib = load_library()
+        dev = delay_state.device
+        B, K, _, N = delay_state.shape
+        L = self.n_layers
+        ds = delay_state.detach().to(torch.float32).contiguous()
+        gso = delay_gso.detach().to(device=dev, dtype=torch.float32).contiguous()
+        ws = [c.weight.detach().to(torch.float32).contiguous() for c in self.conv_layers]
+        bs = [c.bias.detach().to(torch.float32).contiguous() for c in self.conv_layers]
+        if any(t.device != dev for t in ws + bs):
+            raise FgnnError(f"Actor.forward: parameters on {ws[0].device}, inputs on {dev}")
+        widths = (ctypes.c_int32 * (L + 1))(*self.layers)
+        need = lib.fgnn_actor_general_workspace(B, N, K, L, widths)
+        if need < 0:
+            raise FgnnError(lib.fgnn_last_error().decode())
+        work = torch.empty((need // 4,), dtype=torch.float32, device=dev)
+        out = torch.empty((B, 1, self.n_a, N), dtype=torch.float32, device=dev)
+        wp = (ctypes.c_void_p * L)(*[t.data_ptr() for t in ws])
+        bp = (ctypes.c_void_p * L)(*[t.data_ptr() for t in bs])
+        rc = lib.fgnn_actor_forward_general(dev.index, B, N, K, L, widths, self.ind_agg, wp, bp, ds.data_ptr(), gso.data_ptr(),
+                                            out.data_ptr(), work.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+        if rc != 0:
+            raise FgnnError(lib.fgnn_last_error().decode())
+        return out
+
     # -- forward ----------------------------------------------------------------------------
     def forward(self, delay_state, delay_gso):
         batch_size = delay_state.shape[0]
@@ -73,7 +104,9 @@ class Actor(nn.Module):
         if not needs_grad and self._engine_supported():
             eng = self._dense_engine(delay_state.device)
             return eng.actor_forward_dense(delay_state, delay_gso)
-        # autograd path (training on dense tensors, ind_agg > 0): same arithmetic, torch ops on the GPU.  TF32 is
+        if not needs_grad and (0 <= self.ind_agg < self.n_layers or self.k == 1):
+            return self._forward_general(delay_state, delay_gso)
+        # autograd path (training on dense tensors): same arithmetic, torch ops on the GPU so that gradients flow.  TF32 is
         # switched off for it (cuDNN convolutions default to TF32): the reference computes in fp32 on the CPU.
         matmul_tf32 = torch.backends.cuda.matmul.allow_tf32
         torch.backends.cuda.matmul.allow_tf32 = False

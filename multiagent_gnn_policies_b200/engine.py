@@ -23,7 +23,7 @@ ABI_SYMBOLS = [
     "fgnn_set_agent_mask", "fgnn_set_dt", "fgnn_comm_unique_id", "fgnn_comm_init", "fgnn_shard_step",
     "fgnn_p2p_alloc", "fgnn_p2p_connect", "fgnn_p2p_seed", "fgnn_shard_step_p2p", "fgnn_shard_exchange_p2p",
     "fgnn_trainer_create", "fgnn_trainer_destroy", "fgnn_trainer_param_count", "fgnn_trainer_launch_count",
-    "fgnn_trainer_step",
+    "fgnn_trainer_step", "fgnn_actor_general_workspace", "fgnn_actor_forward_general",
 ]
 
 
@@ -87,6 +87,9 @@ def load_library(path=None):
     lib.fgnn_step.argtypes = [vp, vp, vp, vp]
     lib.fgnn_rollout.argtypes = [vp, i32, vp, vp]
     lib.fgnn_actor_forward_dense.argtypes = [vp, i32, i32, vp, vp, vp, vp]
+    lib.fgnn_actor_general_workspace.argtypes = [i32, i32, i32, i32, vp]
+    lib.fgnn_actor_general_workspace.restype = i64
+    lib.fgnn_actor_forward_general.argtypes = [i32, i32, i32, i32, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp]
     lib.fgnn_get_state.argtypes = [vp, vp, vp]
     lib.fgnn_get_features.argtypes = [vp, i32, vp, vp]
     lib.fgnn_get_degrees.argtypes = [vp, i32, vp, vp]

@@ -63,11 +63,39 @@ def aggregate(delay_state, delay_gso):
     return np.matmul(delay_state.astype(np.float32), delay_gso.astype(np.float32))
 
 
-def actor_forward(layers, delay_state, delay_gso, ind_agg=0, return_intermediates=False):
-    """Actor.forward for ind_agg == 0 (the only DAGGER setting, gnn_dagger.py:43).
+def actor_forward_any(layers, delay_state, delay_gso, ind_agg):
+    """Actor.forward for ANY aggregation index (actor.py:59-86): layers in front of ``ind_agg`` act on every tap k
+    separately (kernel (1,1)), the graph aggregation ``x[b,k] @ delay_gso[b,k]`` is applied to the input of layer ``ind_agg``
+    (actor.py:68-71), whose kernel (K,1) collapses the taps (actor.py:32-38), the layers behind it are per-agent.
 
     delay_state (B,K,F,N), delay_gso (B,K,N,N) -> (B,1,n_a,N)."""
-    assert ind_agg == 0
+    B, K, F, N = delay_state.shape
+    assert delay_gso.shape == (B, K, N, N)
+    x = np.transpose(delay_state.astype(np.float32), (0, 2, 1, 3))          # (B,F,K,N)   actor.py:63-64
+    n_layers = len(layers)
+    for i, (w, b) in enumerate(layers):
+        if i == ind_agg:                                                    # actor.py:68-71
+            x = np.transpose(np.matmul(np.transpose(x, (0, 2, 1, 3)), delay_gso.astype(np.float32)), (0, 2, 1, 3))
+        step = w.shape[2]
+        assert step == (K if i == ind_agg else 1) and x.shape[2] % step == 0
+        if step == 1:
+            x = np.einsum('gc,bckn->bgkn', w[:, :, 0], x, dtype=np.float32)
+        else:                                                               # kernel (K,1), stride (K,1): one output row
+            assert x.shape[2] == K
+            x = np.einsum('gck,bckn->bgn', w, x, dtype=np.float32)[:, :, None, :]
+        x = (x + b.reshape(1, -1, 1, 1)).astype(np.float32)
+        if i < n_layers - 1:                                                # actor.py:75-77
+            x = np.tanh(x)
+    return x.reshape(B, 1, layers[-1][0].shape[0], N).astype(np.float32)     # actor.py:82
+
+
+def actor_forward(layers, delay_state, delay_gso, ind_agg=0, return_intermediates=False):
+    """Actor.forward for ind_agg == 0 (the only DAGGER setting, gnn_dagger.py:43); other indices: actor_forward_any.
+
+    delay_state (B,K,F,N), delay_gso (B,K,N,N) -> (B,1,n_a,N)."""
+    if ind_agg != 0:
+        assert not return_intermediates
+        return actor_forward_any(layers, delay_state, delay_gso, ind_agg)
     B, K, F, N = delay_state.shape
     assert delay_gso.shape == (B, K, N, N)
     z = aggregate(delay_state, delay_gso)                       # (B,K,F,N)

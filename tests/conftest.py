@@ -34,7 +34,21 @@ def _all_golden():
 
 def golden_names():
     """Rollout fixtures (oracle/gen_golden.py)."""
-    return [n for n in _all_golden() if not n.startswith("train_")]
+    return [n for n in _all_golden() if not n.startswith(("train_", "agg"))]
+
+
+def agg_golden_names():
+    """Actor.forward fixtures for ind_agg != 0 / unequal layer widths (oracle/gen_golden_agg.py)."""
+    return [n for n in _all_golden() if n.startswith("agg")]
+
+
+def load_agg_golden(name):
+    g = dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz")))
+    g["state_dict"] = {k[3:]: v for k, v in g.items() if k.startswith("sd.")}
+    for key in ("n_agents", "k", "ind_agg", "batch", "seed"):
+        g[key] = int(g[key])
+    g["layers"] = [int(v) for v in g["layers"]]
+    return g
 
 
 def train_golden_names():

@@ -82,3 +82,25 @@ def test_argument_errors_are_reported_without_a_gpu():
     assert lib.fgnn_trainer_step(None, 1, 1, None, None, None, None, None, 1, 1e-3, 0.9, 0.999, 1e-8, 1, None, None, None) != 0
     assert lib.fgnn_step(None, None, None, None) != 0 and lib.fgnn_policy(None, None, None) != 0
     assert lib.fgnn_destroy(None) == 0 and lib.fgnn_trainer_destroy(None) == 0       # destroying nothing is fine
+
+
+def test_general_actor_forward_argument_checks():
+    """fgnn_actor_forward_general / fgnn_actor_general_workspace (learner/actor.py:45-86 for any ind_agg): shapes are
+    checked before any CUDA call, the workspace size is 2 ping-pong buffers of the widest activation."""
+    import ctypes
+    lib = engine.load_library()
+    widths = (ctypes.c_int32 * 4)(6, 16, 24, 2)
+    assert lib.fgnn_actor_general_workspace(2, 40, 3, 3, widths) == 2 * (2 * 24 * 3 * 40) * 4
+    assert lib.fgnn_actor_general_workspace(2, 40, 3, 3, None) == -1
+    assert lib.fgnn_actor_general_workspace(0, 40, 3, 3, widths) == -1
+    bad = (ctypes.c_int32 * 4)(6, 0, 24, 2)
+    assert lib.fgnn_actor_general_workspace(2, 40, 3, 3, bad) == -1
+    assert b"widths" in lib.fgnn_last_error()
+    assert lib.fgnn_actor_forward_general(0, 2, 40, 3, 3, widths, 1, None, None, None, None, None, None, None) != 0
+    assert b"null" in lib.fgnn_last_error()
+    # ind_agg beyond the layers with K > 1 leaves K rows: the reference's final view fails, so does this call
+    one = ctypes.c_float(0.0)
+    ptrs = (ctypes.c_void_p * 3)(*[ctypes.addressof(one)] * 3)
+    p = ctypes.addressof(one)
+    assert lib.fgnn_actor_forward_general(0, 2, 40, 3, 3, widths, 3, ptrs, ptrs, p, p, p, p, None) != 0
+    assert b"ind_agg" in lib.fgnn_last_error()

@@ -3,7 +3,7 @@ against the dense one (CPU only)."""
 import numpy as np
 import pytest
 
-from conftest import rel_inf, load_golden
+from conftest import rel_inf, load_golden, agg_golden_names, load_agg_golden
 from oracle import flock_env, learner, sparse
 
 TOL_ACTION = 1e-5      # north_star: actions within 1e-5 relative fp32
@@ -38,6 +38,17 @@ def test_learner_restatement_matches_reference(golden):
         assert rel_inf(z, g["z"][t]) <= 2e-6
         a = learner.select_action(layers, state)
         assert rel_inf(a, g["action"][t]) <= TOL_ACTION
+
+
+@pytest.mark.parametrize("name", agg_golden_names())
+def test_actor_restatement_for_any_aggregation_index(name):
+    """oracle.learner.actor_forward_any against the UNMODIFIED reference Actor.forward with ind_agg in {0, 1, 2} and unequal
+    layer widths (oracle/gen_golden_agg.py): fp32 sums in a different order, so 2e-6 of the output's inf-norm."""
+    g = load_agg_golden(name)
+    layers = learner.weights_from_state_dict(g["state_dict"])
+    out = learner.actor_forward(layers, g["delay_state"], g["delay_gso"], ind_agg=g["ind_agg"])
+    assert out.shape == g["out"].shape
+    assert rel_inf(out, g["out"]) <= 2e-6
 
 
 def test_delay_state_structure():
