@@ -134,3 +134,16 @@ def test_shard_ranges_and_depth():
     assert parallel.halo_depth(3, 1.0, 0.5) == 3.5
     b = parallel.strip_bounds(np.array([[0.0, 0, 0, 0], [1.0, 0, 0, 0], [3.0, 0, 0, 0], [4.0, 0, 0, 0]]), [(0, 2), (2, 2)])
     assert b[1] == 2.0 and b[0] < -1e200 and b[2] > 1e200
+
+
+def test_cpu_binding_is_best_effort():
+    """parallel.bind_to_local_cpus (one process per GPU: rank on its GPU's NUMA node) must never raise and must leave the
+    affinity alone where it cannot name a proper subset of the allowed CPUs -- e.g. here, without a GPU / NVML device."""
+    import os
+    from multiagent_gnn_policies_b200 import parallel
+    before = os.sched_getaffinity(0)
+    got = parallel.bind_to_local_cpus(0)
+    after = os.sched_getaffinity(0)
+    assert got is None or (set(got) == after and after < before)
+    if got is None:
+        assert after == before
