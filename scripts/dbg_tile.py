@@ -1,4 +1,5 @@
-"""Debug aid: the tile-fused kernel (FGNN_STEP_MODE=1) against the separate round-1 kernels (FGNN_STEP_MODE=0), array by array."""
+"""Debug aid: the warp-tile adjacency kernel k_pair_adjacency (FGNN_STEP_MODE=1) against the round-1 kernel k_adjacency_t
+(FGNN_STEP_MODE=0), array by array (first written for the removed cell-tile kernel, hence the name)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np

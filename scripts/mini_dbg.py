@@ -1,3 +1,4 @@
+"""Debug aid: the single-CTA path at N = 100 over a range of edge-capacity hints (shared-memory sizing of its adjacency stage)."""
 import sys
 sys.path.insert(0, "/root/repo")
 import numpy as np
