@@ -104,7 +104,7 @@ class Actor(nn.Module):
         if not needs_grad and self._engine_supported():
             eng = self._dense_engine(delay_state.device)
             return eng.actor_forward_dense(delay_state, delay_gso)
-        if not needs_grad and (0 <= self.ind_agg < self.n_layers or self.k == 1):
+        if not needs_grad and self.n_layers <= 16 and (0 <= self.ind_agg < self.n_layers or self.k == 1):
             return self._forward_general(delay_state, delay_gso)
         # autograd path (training on dense tensors): same arithmetic, torch ops on the GPU so that gradients flow.  TF32 is
         # switched off for it (cuDNN convolutions default to TF32): the reference computes in fp32 on the CPU.
